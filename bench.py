@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py — slices/sec of the two-stage generator forward (256x256), BASELINE.json's metric.
+
+Workload (config.workload): BASELINE.json configs[1] = batch-16 256x256 two-stage generator
+inference on one B200 (weights: oracle.synth random-init, spectral norm converged; inputs:
+oracle.synth.synthetic_slices).  One "step" = one Generator.forward over one batch of 16 slices.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision fp32|bf16] [--impl reference]
+
+* value      : slices/s with inputs resident in HBM; every step is timed with its own CUDA-event pair
+               on the launching stream and L2 is flushed (256 MiB write) between steps.
+* e2e        : the same metric through the public API (healthivert_gan_b200.Generator.forward) from
+               pinned HOST buffers: H2D of the step's inputs and D2H of its outputs inside the timed region.
+* roofline   : the dominant kernel (the 64->64 3x3 conv family: 19 of 47 layers) timed alone, live,
+               with CUDA events; achieved = algorithmic FLOPs per launch / mean launch time.
+* cpu_baseline : the oracle port of the reference forward on the host cores (rank 0, N=1 only).
+* --impl reference : the reference's CPU implementation (oracle port; /root/reference cannot travel to
+               the GPU box) on all host threads, same config / metric.
+Multi-GPU (torchrun): weak scaling, every rank runs its own batch-16 stream of slices, no collective
+on the data path; barrier + synchronize around the timed region, max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 16
+FLOP_PER_SLICE = 17.54e9          # 14.187 (47 convs) + 1.208 + 2.147 (attention) GFLOP
+METRIC = "slices/sec two-stage gen fwd (256x256)"
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def _cpu_forward_rate(steps, warmup, batch=BATCH):
+    """Oracle port of the reference forward on all host threads: slices/s over `steps` batches."""
+    import torch
+    from oracle import generator_ref as gr
+    from oracle import synth
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = synth.synthetic_generator_state_dict()
+    x, mask, cam, ratio = synth.synthetic_slices(batch, seed=123)
+    with torch.no_grad():
+        for _ in range(warmup):
+            gr.generator_forward(sd, x, mask, cam, ratio)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            gr.generator_forward(sd, x, mask, cam, ratio)
+        dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps * 1e3, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 40))
+    rate, ms, threads = _cpu_forward_rate(steps, min(args.warmup, 3))
+    sample = f"{steps} steps x batch {BATCH} (each step = one full batch-{BATCH} forward), oracle port of the reference"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "slices/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"batch-{BATCH} 256x256 two-stage generator inference (BASELINE.json configs[1])",
+                   "batch": BATCH, "precision": "fp32", "device": "host CPU"},
+        "cpu_baseline": {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "slices/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import healthivert_gan_b200 as hv
+    from healthivert_gan_b200 import _lib
+    from healthivert_gan_b200.inpaint_networks import conv2d_fused
+    from oracle import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    sd = synth.synthetic_generator_state_dict()
+    g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    g.load_state_dict(sd)
+    g = g.to(dev).eval()
+    g.precision = args.precision
+    g.return_flow = True
+    host = [t.pin_memory() for t in synth.synthetic_slices(BATCH, seed=123 + rank)]
+    x, mask, cam, ratio = (t.to(dev) for t in host)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        with torch.no_grad():
+            return g(x, mask, cam, ratio)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    wall0 = time.perf_counter()
+    launches0 = _lib.launch_count()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        step()
+        e1.record(stream)
+        evs.append((e0, e1))
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = _lib.launch_count() - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # ---------------- end to end through the public API from pinned host buffers
+    outs_host = None
+    e2e_evs = []
+    barrier()
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        dx, dm, dc, dr = (t.to(dev, non_blocking=True) for t in host)
+        with torch.no_grad():
+            out = g(dx, dm, dc, dr)
+        keep = [out[i] for i in (0, 1, 2, 3, 5, 6)]
+        if outs_host is None:
+            outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in keep]
+        for h, t in zip(outs_host, keep):
+            h.copy_(t, non_blocking=True)
+        e1.record(stream)
+        e1.synchronize()
+        e2e_evs.append((e0, e1))
+    barrier()
+    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = sum(t.numel() * t.element_size() for t in outs_host)
+
+    # ---------------- dominant kernel alone (roofline): 64->64 3x3 conv on the batch's 64x64 maps
+    a = torch.randn(BATCH, 64, 64, 64, device=dev)
+    w = torch.randn(64, 64, 3, 3, device=dev) * 0.05
+    b = torch.zeros(64, device=dev)
+    for _ in range(3):
+        conv2d_fused([(a, 0)], w, b, 3, 1, 1, 1, "elu", 64, 64)
+    reps = 20
+    kev = []
+    for _ in range(reps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        conv2d_fused([(a, 0)], w, b, 3, 1, 1, 1, "elu", 64, 64)
+        e1.record(stream)
+        kev.append((e0, e1))
+    torch.cuda.synchronize()
+    k_ms = sum(x0.elapsed_time(x1) for x0, x1 in kev) / reps
+    k_flop = 2.0 * BATCH * 64 * 64 * 64 * 576
+
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t.tolist()
+        lt = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(lt)
+        launches = int(lt.item())
+    if rank == 0:
+        peaks = _peaks()
+        value = world * BATCH * args.steps / (dev_ms * 1e-3)
+        e2e = world * BATCH * args.steps / (e2e_ms * 1e-3)
+        achieved = k_flop / (k_ms * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "slices/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"batch-{BATCH} 256x256 two-stage generator inference (BASELINE.json configs[1])",
+                       "batch": BATCH, "precision": args.precision, "l2": "flushed (256 MiB write) between steps",
+                       "timing": "per-step CUDA-event pairs on the launch stream, summed; max over ranks",
+                       "parallelism": f"slice-sharded x{world}, no collective"},
+            "e2e": {"value": e2e, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv 64->64 3x3 (fp32 SIMT parity kernel)"
+                         if args.precision == "fp32" else "conv 64->64 3x3 (tcgen05 bf16)",
+                         "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "peak_source": peaks["source"] + " burst bf16 (kernel timed alone)",
+                         "whole_forward_tensor_frac_sustained": value / world * FLOP_PER_SLICE / (peaks["bf16_tflops_sustained"] * 1e12)},
+            "wall_s_timed_region": wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, ms, threads = _cpu_forward_rate(10, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": "slices/s", "cores": threads, "kind": "port",
+                                    "sample": f"10 steps x batch {BATCH} of the same workload ({ms:.0f} ms/step), oracle port of the reference forward"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("HV_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

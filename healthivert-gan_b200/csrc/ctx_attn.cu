@@ -1,0 +1,386 @@
+// Contextual attention, fp32 parity path (dense closed form).
+//
+// Replaces ContextualAttention.forward(f, f, mask) (reference models/inpaint_networks.py:247-410,
+// helpers models/inpaint_tools.py:7-70) for ksize=3, stride=1, rate=2, fuse_k=3:
+//   P  = 3x3 patches of the ::2-downsampled feature      [L, 9c]
+//   R  = 4x4 stride-2 patches of the full feature         [L, 16c]
+//   S  = diag(1/max(|P_b|,1e-4)) P P^T                    [L_b, L_f]        (tensor contraction 1)
+//   U  = two flat-index diagonal 3-tap sums of S (row-major, then column-major ordering)
+//   A  = softmax_b(scale * U * mm_b) * mm_b ; argmax_b A
+//   y  = fold(R^T A) / 4                                   (tensor contraction 2 + overlap-add)
+// Per-sample intermediates live in a caller-provided workspace.
+#include "hv_common.cuh"
+#include "kernels.h"
+
+namespace hv {
+
+// ------------------------------------------------------------------ batched SGEMM (SIMT)
+constexpr int GM = 128, GN = 128, GK = 8;
+
+template <bool A_KMAJOR, bool B_KMAJOR>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                    float* __restrict__ C, const float* __restrict__ rowscale,
+                                                    int M, int N, int K, long long sA, long long sB,
+                                                    long long sC, long long sS) {
+  __shared__ __align__(16) float As[2][GK][GM];
+  __shared__ __align__(16) float Bs[2][GK][GN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
+  A += blockIdx.z * sA; B += blockIdx.z * sB; C += blockIdx.z * sC;
+  if (rowscale) rowscale += blockIdx.z * sS;
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  float4 ra, rb;
+  auto gload = [&](int k0) {
+    if (A_KMAJOR) { int m = tid >> 1, k = (tid & 1) * 4; ra = *reinterpret_cast<const float4*>(A + (size_t)(m0 + m) * K + k0 + k); }
+    else { int k = tid >> 5, m = (tid & 31) * 4; ra = *reinterpret_cast<const float4*>(A + (size_t)(k0 + k) * M + m0 + m); }
+    if (B_KMAJOR) { int n = tid >> 1, k = (tid & 1) * 4; rb = *reinterpret_cast<const float4*>(B + (size_t)(n0 + n) * K + k0 + k); }
+    else { int k = tid >> 5, n = (tid & 31) * 4; rb = *reinterpret_cast<const float4*>(B + (size_t)(k0 + k) * N + n0 + n); }
+  };
+  auto sstore = [&](int buf) {
+    if (A_KMAJOR) { int m = tid >> 1, k = (tid & 1) * 4; As[buf][k][m] = ra.x; As[buf][k + 1][m] = ra.y; As[buf][k + 2][m] = ra.z; As[buf][k + 3][m] = ra.w; }
+    else { int k = tid >> 5, m = (tid & 31) * 4; *reinterpret_cast<float4*>(&As[buf][k][m]) = ra; }
+    if (B_KMAJOR) { int n = tid >> 1, k = (tid & 1) * 4; Bs[buf][k][n] = rb.x; Bs[buf][k + 1][n] = rb.y; Bs[buf][k + 2][n] = rb.z; Bs[buf][k + 3][n] = rb.w; }
+    else { int k = tid >> 5, n = (tid & 31) * 4; *reinterpret_cast<float4*>(&Bs[buf][k][n]) = rb; }
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = K / GK;
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * GK);
+#pragma unroll
+    for (int k = 0; k < GK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) sstore(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+    const float sc = rowscale ? rowscale[m] : 1.f;
+    float4 o0 = make_float4(acc[i][0] * sc, acc[i][1] * sc, acc[i][2] * sc, acc[i][3] * sc);
+    float4 o1 = make_float4(acc[i][4] * sc, acc[i][5] * sc, acc[i][6] * sc, acc[i][7] * sc);
+    *reinterpret_cast<float4*>(C + (size_t)m * N + n0 + tx * 4) = o0;
+    *reinterpret_cast<float4*>(C + (size_t)m * N + n0 + 64 + tx * 4) = o1;
+  }
+}
+
+int sgemm_batched(const float* A, const float* B, float* C, const float* rowscale, int M, int N, int K,
+                  bool a_kmajor, bool b_kmajor, long long sA, long long sB, long long sC, long long sS,
+                  int batch, cudaStream_t st) {
+  HV_CHECK_ARG(M % GM == 0 && N % GN == 0 && K % GK == 0, "sgemm: M,N must be multiples of 128 and K of 8 (got %d,%d,%d)", M, N, K);
+  dim3 grid(N / GN, M / GM, batch);
+  if (a_kmajor && b_kmajor) sgemm_kernel<true, true><<<grid, 256, 0, st>>>(A, B, C, rowscale, M, N, K, sA, sB, sC, sS);
+  else if (!a_kmajor && !b_kmajor) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(A, B, C, rowscale, M, N, K, sA, sB, sC, sS);
+  else if (a_kmajor) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(A, B, C, rowscale, M, N, K, sA, sB, sC, sS);
+  else sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, B, C, rowscale, M, N, K, sA, sB, sC, sS);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+// ------------------------------------------------------------------ patch extraction
+// P[n][l][c*9+ky*3+kx] = Fd[n][c][lh+ky-1][lw+kx-1], Fd = F[:, :, ::2, ::2]  (:282-295)
+// R[n][l][c*16+ky*4+kx] = F[n][c][2lh-1+ky][2lw-1+kx]                        (:270-278)
+// inv_norm[n][l] = 1 / max(sqrt(sum_k P^2), 1e-4)                             (:341-345)
+__global__ void __launch_bounds__(256) ca_patches_kernel(const float* __restrict__ f, float* __restrict__ P,
+                                                         float* __restrict__ R, float* __restrict__ inv_norm,
+                                                         int c, int h, int w) {
+  const int hs = h >> 1, ws = w >> 1, L = hs * ws;
+  const int l = blockIdx.x, n = blockIdx.y;
+  const int lh = l / ws, lw = l - lh * ws;
+  const float* fn = f + (size_t)n * c * h * w;
+  float* Pl = P + ((size_t)n * L + l) * (c * 9);
+  float* Rl = R + ((size_t)n * L + l) * (c * 16);
+  __shared__ float red[32];
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < c * 9; i += blockDim.x) {
+    int ch = i / 9, t = i - ch * 9, ky = t / 3, kx = t - ky * 3;
+    int y = lh + ky - 1, x = lw + kx - 1;
+    float v = (y >= 0 && y < hs && x >= 0 && x < ws) ? fn[((size_t)ch * h + 2 * y) * w + 2 * x] : 0.f;
+    Pl[i] = v;
+    ss = fmaf(v, v, ss);
+  }
+  for (int i = threadIdx.x; i < c * 16; i += blockDim.x) {
+    int ch = i >> 4, ky = (i >> 2) & 3, kx = i & 3;
+    int y = 2 * lh - 1 + ky, x = 2 * lw - 1 + kx;
+    Rl[i] = (y >= 0 && y < h && x >= 0 && x < w) ? fn[((size_t)ch * h + y) * w + x] : 0.f;
+  }
+  float tot = block_sum(ss, red);
+  if (threadIdx.x == 0) inv_norm[(size_t)n * L + l] = 1.f / fmaxf(sqrtf(tot), 1e-4f);
+}
+
+// mm[n][l] = 1 iff the zero-padded 3x3 neighbourhood of mask[src, 0, ::8, ::8] at l is all zero (:304-317)
+__global__ void ca_mask_kernel(const float* __restrict__ mask, float* __restrict__ mm, int n, int hs, int ws,
+                               int mh, int mw, int step, int per_sample) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * hs * ws) return;
+  int s = i / (hs * ws), l = i - s * hs * ws, lh = l / ws, lw = l - lh * ws;
+  const float* m = mask + (size_t)(per_sample ? s : 0) * mh * mw;
+  float acc = 0.f;
+  for (int dy = -1; dy <= 1; ++dy)
+    for (int dx = -1; dx <= 1; ++dx) {
+      int y = lh + dy, x = lw + dx;
+      if (y >= 0 && y < hs && x >= 0 && x < ws) acc += m[(size_t)(y * step) * mw + x * step];
+    }
+  mm[i] = (acc / 9.f == 0.f) ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------ fuse (:350-361)
+// U[i][j] = sum_{cc in -1..1} T[cmi(cm(i)+cc)][cmi(cm(j)+cc)],  T[p][q] = sum_{a in -1..1} S[p+a][q+a]
+// with flat indices outside [0,L) contributing zero; cm = row-major -> column-major index.
+__global__ void __launch_bounds__(256) ca_fuse_kernel(const float* __restrict__ S, float* __restrict__ U, int side) {
+  const int L = side * side;
+  const float* Sn = S + (size_t)blockIdx.z * L * L;
+  float* Un = U + (size_t)blockIdx.z * L * L;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= L) return;
+  const int ci = (i % side) * side + i / side, cj = (j % side) * side + j / side;
+  float acc = 0.f;
+#pragma unroll
+  for (int cc = -1; cc <= 1; ++cc) {
+    const int pi = ci + cc, pj = cj + cc;
+    if (pi < 0 || pi >= L || pj < 0 || pj >= L) continue;
+    const int p = (pi % side) * side + pi / side, q = (pj % side) * side + pj / side;
+#pragma unroll
+    for (int a = -1; a <= 1; ++a) {
+      const int r = p + a, s = q + a;
+      if (r < 0 || r >= L || s < 0 || s >= L) continue;
+      acc += Sn[(size_t)r * L + s];
+    }
+  }
+  Un[(size_t)i * L + j] = acc;
+}
+
+// ------------------------------------------------------------------ masked scaled softmax + argmax (:364-368)
+// one CTA per (32 foreground columns, sample); 8 row groups; in place on U -> A
+__global__ void __launch_bounds__(256) ca_softmax_kernel(float* __restrict__ U, const float* __restrict__ mm,
+                                                         int32_t* __restrict__ argmax_out, int L, float scale,
+                                                         int mm_stride) {
+  float* Un = U + (size_t)blockIdx.y * L * L;
+  const float* m = mm + (size_t)blockIdx.y * mm_stride;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + lane;
+  __shared__ float s_red[8][32];
+  __shared__ int s_idx[8][32];
+  float mx = -INFINITY;
+  for (int b = g; b < L; b += 8) mx = fmaxf(mx, Un[(size_t)b * L + f] * m[b] * scale);
+  s_red[g][lane] = mx;
+  __syncthreads();
+  mx = s_red[0][lane];
+#pragma unroll
+  for (int k = 1; k < 8; ++k) mx = fmaxf(mx, s_red[k][lane]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int b = g; b < L; b += 8) sum += expf(Un[(size_t)b * L + f] * m[b] * scale - mx);
+  s_red[g][lane] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sum += s_red[k][lane];
+  __syncthreads();
+  float best = -1.f;
+  int bi = 0;
+  for (int b = g; b < L; b += 8) {
+    const float mb = m[b];
+    const float a = expf(Un[(size_t)b * L + f] * mb * scale - mx) / sum * mb;
+    Un[(size_t)b * L + f] = a;
+    if (a > best) { best = a; bi = b; }
+  }
+  s_red[g][lane] = best;
+  s_idx[g][lane] = bi;
+  __syncthreads();
+  if (g == 0) {
+    for (int k = 1; k < 8; ++k) {
+      const float v = s_red[k][lane];
+      const int id = s_idx[k][lane];
+      if (v > best || (v == best && id < bi)) { best = v; bi = id; }
+    }
+    argmax_out[(size_t)blockIdx.y * L + f] = bi;
+  }
+}
+
+// ------------------------------------------------------------------ overlap-add of the pasted patches (:377-379)
+// y[n][c][oy][ox] = 0.25 * sum_{ky,kx,hf,wf : 2hf-1+ky=oy, 2wf-1+kx=ox} cols[n][c*16+ky*4+kx][hf*ws+wf]
+__global__ void __launch_bounds__(256) ca_fold_kernel(const float* __restrict__ cols, float* __restrict__ y, int c,
+                                                      int h, int w) {
+  const int hs = h >> 1, ws = w >> 1, L = hs * ws;
+  const size_t total = (size_t)c * h * w;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = blockIdx.y;
+  const int ox = i % w, oy = (i / w) % h, ch = i / ((size_t)w * h);
+  const float* cn = cols + (size_t)n * (c * 16) * L;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ky = ((oy + 1) & 1) + 2 * a, hf = (oy + 1 - ky) >> 1;
+    if (oy + 1 - ky < 0 || hf >= hs) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kx = ((ox + 1) & 1) + 2 * b, wf = (ox + 1 - kx) >> 1;
+      if (ox + 1 - kx < 0 || wf >= ws) continue;
+      acc += cn[(size_t)(ch * 16 + ky * 4 + kx) * L + hf * ws + wf];
+    }
+  }
+  y[(size_t)n * total + i] = acc * 0.25f;
+}
+
+// ------------------------------------------------------------------ offsets + flow colouring (:368-408)
+__constant__ unsigned char c_wheel[55][3];
+static bool g_wheel_ready = false;
+
+static void make_wheel(unsigned char wheel[55][3]) {  // models/inpaint_tools.py:244-273
+  const int RY = 15, YG = 6, GC = 4, CB = 11, BM = 13, MR = 6;
+  int col = 0;
+  for (int i = 0; i < 55; ++i) wheel[i][0] = wheel[i][1] = wheel[i][2] = 0;
+  for (int i = 0; i < RY; ++i) { wheel[col + i][0] = 255; wheel[col + i][1] = (unsigned char)(255 * i / RY); }
+  col += RY;
+  for (int i = 0; i < YG; ++i) { wheel[col + i][0] = (unsigned char)(255 - 255 * i / YG); wheel[col + i][1] = 255; }
+  col += YG;
+  for (int i = 0; i < GC; ++i) { wheel[col + i][1] = 255; wheel[col + i][2] = (unsigned char)(255 * i / GC); }
+  col += GC;
+  for (int i = 0; i < CB; ++i) { wheel[col + i][1] = (unsigned char)(255 - 255 * i / CB); wheel[col + i][2] = 255; }
+  col += CB;
+  for (int i = 0; i < BM; ++i) { wheel[col + i][2] = 255; wheel[col + i][0] = (unsigned char)(255 * i / BM); }
+  col += BM;
+  for (int i = 0; i < MR; ++i) { wheel[col + i][2] = (unsigned char)(255 - 255 * i / MR); wheel[col + i][0] = 255; }
+}
+
+// one CTA per sample: offsets = argmax (row, col) - own (row, col); flow colour uses the running
+// maximum radius over samples 0..n (the reference carries maxrad across the batch).
+__global__ void __launch_bounds__(256) ca_offsets_flow_kernel(const int32_t* __restrict__ argmax,
+                                                              int32_t* __restrict__ offsets,
+                                                              float* __restrict__ flow, int side, int up) {
+  const int L = side * side, n = blockIdx.x;
+  __shared__ int s_max[256];
+  int mx = 0;
+  for (int s = 0; s <= n; ++s)
+    for (int l = threadIdx.x; l < L; l += blockDim.x) {
+      const int am = argmax[(size_t)s * L + l];
+      const int du = am / side - l / side, dv = am % side - l % side;
+      mx = max(mx, du * du + dv * dv);
+    }
+  s_max[threadIdx.x] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const double maxrad = sqrt((double)s_max[0]) + 2.220446049250313e-16;
+  const int W = side * up;
+  for (int l = threadIdx.x; l < L; l += blockDim.x) {
+    const int am = argmax[(size_t)n * L + l];
+    const int du = am / side - l / side, dv = am % side - l % side;
+    if (offsets) {
+      offsets[((size_t)n * 2 + 0) * L + l] = du;
+      offsets[((size_t)n * 2 + 1) * L + l] = dv;
+    }
+    if (!flow) continue;
+    const double u = du / maxrad, v = dv / maxrad;
+    const double rad = sqrt(u * u + v * v);
+    const double a = atan2(-v, -u) / 3.141592653589793;
+    const double fk = (a + 1.0) / 2.0 * 54.0 + 1.0;
+    int k0 = (int)floor(fk), k1 = k0 + 1;
+    if (k1 == 56) k1 = 1;
+    const double fr = fk - k0;
+    for (int ch = 0; ch < 3; ++ch) {
+      const double c0 = c_wheel[k0 - 1][ch] / 255.0, c1 = c_wheel[k1 - 1][ch] / 255.0;
+      double col = (1.0 - fr) * c0 + fr * c1;
+      if (rad <= 1.0) col = 1.0 - rad * (1.0 - col); else col *= 0.75;
+      const float px = (float)(unsigned char)floor(255.0 * col) / 255.f;
+      const int y0 = (l / side) * up, x0 = (l % side) * up;
+      float* dst = flow + ((size_t)n * 3 + ch) * W * W;
+      for (int yy = 0; yy < up; ++yy)
+        for (int xx = 0; xx < up; ++xx) dst[(size_t)(y0 + yy) * W + x0 + xx] = px;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host orchestration
+struct CaWorkspace {
+  float *P, *R, *inv_norm, *mm, *S, *U, *cols;
+  int32_t* argmax;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t ca_layout(int n, int c, int h, int w, char* base, CaWorkspace* ws) {
+  const size_t L = (size_t)(h / 2) * (w / 2);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  char* p;
+  p = take(sizeof(float) * n * L * c * 9);  if (ws) ws->P = (float*)p;
+  p = take(sizeof(float) * n * L * c * 16); if (ws) ws->R = (float*)p;
+  p = take(sizeof(float) * n * L);          if (ws) ws->inv_norm = (float*)p;
+  p = take(sizeof(float) * n * L);          if (ws) ws->mm = (float*)p;
+  p = take(sizeof(float) * n * L * L);      if (ws) ws->S = (float*)p;
+  p = take(sizeof(float) * n * L * L);      if (ws) ws->U = (float*)p;
+  p = take(sizeof(float) * n * L * c * 16); if (ws) ws->cols = (float*)p;
+  p = take(sizeof(int32_t) * n * L);        if (ws) ws->argmax = (int32_t*)p;
+  return off;
+}
+
+size_t ctx_attn_workspace_bytes(int n, int c, int h, int w) { return ca_layout(n, c, h, w, nullptr, nullptr); }
+
+int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offsets, float* flow, int n, int c,
+                      int h, int w, float scale, int fuse, int per_sample_mask, void* workspace, cudaStream_t st) {
+  HV_CHECK_ARG(f && mask && y && workspace, "ctx_attn_fwd: null argument");
+  HV_CHECK_ARG(n > 0 && n <= 65535 && c > 0 && h > 0 && w > 0, "ctx_attn_fwd: bad extent");
+  HV_CHECK_ARG(h == w && (h % 2) == 0, "ctx_attn_fwd: square even feature maps only (h=%d w=%d)", h, w);
+  const int side = h / 2, L = side * side;
+  HV_CHECK_ARG(L % 128 == 0 && c % 8 == 0, "ctx_attn_fwd: needs (h/2)^2 %% 128 == 0 and c %% 8 == 0");
+  CaWorkspace ws;
+  ca_layout(n, c, h, w, (char*)workspace, &ws);
+  if (!g_wheel_ready) {
+    unsigned char wheel[55][3];
+    make_wheel(wheel);
+    HV_CUDA(cudaMemcpyToSymbol(c_wheel, wheel, sizeof(wheel)));
+    g_wheel_ready = true;
+  }
+  ca_patches_kernel<<<dim3(L, n), 256, 0, st>>>(f, ws.P, ws.R, ws.inv_norm, c, h, w);
+  HV_LAUNCH_CHECK();
+  ca_mask_kernel<<<(n * L + 255) / 256, 256, 0, st>>>(mask, ws.mm, n, side, side, 4 * h, 4 * w, 8, per_sample_mask);
+  HV_LAUNCH_CHECK();
+  int rc = sgemm_batched(ws.P, ws.P, ws.S, ws.inv_norm, L, L, c * 9, true, true, (long long)L * c * 9,
+                         (long long)L * c * 9, (long long)L * L, L, n, st);
+  if (rc) return rc;
+  float* A = ws.S;
+  if (fuse) {
+    ca_fuse_kernel<<<dim3((L + 255) / 256, L, n), 256, 0, st>>>(ws.S, ws.U, side);
+    HV_LAUNCH_CHECK();
+    A = ws.U;
+  }
+  ca_softmax_kernel<<<dim3(L / 32, n), 256, 0, st>>>(A, ws.mm, ws.argmax, L, scale, L);
+  HV_LAUNCH_CHECK();
+  // cols[ck][f] = sum_b R[b][ck] * A[b][f]
+  rc = sgemm_batched(ws.R, A, ws.cols, nullptr, c * 16, L, L, false, false, (long long)L * c * 16,
+                     (long long)L * L, (long long)L * c * 16, 0, n, st);
+  if (rc) return rc;
+  const size_t per = (size_t)c * h * w;
+  ca_fold_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(ws.cols, y, c, h, w);
+  HV_LAUNCH_CHECK();
+  if (offsets || flow) {
+    ca_offsets_flow_kernel<<<n, 256, 0, st>>>(ws.argmax, offsets, flow, side, 8);
+    HV_LAUNCH_CHECK();
+  }
+  return HV_OK;
+}
+
+}  // namespace hv

@@ -1,0 +1,333 @@
+// Native executor for the two-stage generator forward.
+//
+// Replaces Generator.forward = CoarseGenerator.forward + FineGenerator.forward
+// (reference models/inpaint_networks.py:28-32, :68-117, :169-232) in eval()/no_grad mode.
+// The plan owns: effective (spectrally normalised) weights, one activation buffer per conv
+// block (also the parity taps), the attention workspace, and a second stream + events so the
+// two independent branches of the fine network (dilated-conv branch, attention branch) run
+// concurrently.
+#include <string.h>
+#include <vector>
+#include "hv_common.cuh"
+#include "kernels.h"
+
+namespace hv {
+
+struct LayerSpec {
+  const char* name;
+  int cin, cout, k, stride, pad, dil, act, hout;  // hout = output height = width
+};
+
+// models/inpaint_networks.py:41-63 (coarse, 0..19) and :126-165 (fine, 20..46); state_dict order
+static const LayerSpec kLayers[] = {
+    {"coarse_generator.conv1", 3, 16, 5, 1, 2, 1, HV_ACT_ELU, 256},
+    {"coarse_generator.conv2_downsample", 16, 32, 3, 2, 1, 1, HV_ACT_ELU, 128},
+    {"coarse_generator.conv3", 32, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"coarse_generator.conv4_downsample", 32, 64, 3, 2, 1, 1, HV_ACT_ELU, 64},
+    {"coarse_generator.conv5", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"coarse_generator.conv6", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"coarse_generator.conv7_atrous", 64, 64, 3, 1, 2, 2, HV_ACT_ELU, 64},
+    {"coarse_generator.conv8_atrous", 64, 64, 3, 1, 4, 4, HV_ACT_ELU, 64},
+    {"coarse_generator.conv9_atrous", 64, 64, 3, 1, 8, 8, HV_ACT_ELU, 64},
+    {"coarse_generator.conv10_atrous", 64, 64, 3, 1, 16, 16, HV_ACT_ELU, 64},
+    {"coarse_generator.conv11", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"coarse_generator.conv12", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"coarse_generator.conv20", 65, 64, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"coarse_generator.conv13", 64, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"coarse_generator.conv14", 32, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"coarse_generator.conv19", 33, 32, 3, 1, 1, 1, HV_ACT_ELU, 256},
+    {"coarse_generator.conv15", 32, 16, 3, 1, 1, 1, HV_ACT_ELU, 256},
+    {"coarse_generator.conv16", 16, 8, 3, 1, 1, 1, HV_ACT_ELU, 256},
+    {"coarse_generator.conv17", 8, 1, 3, 1, 1, 1, HV_ACT_NONE, 256},
+    {"coarse_generator.conv18", 8, 1, 3, 1, 1, 1, HV_ACT_SIGMOID, 256},
+    {"fine_generator.conv1", 4, 16, 5, 1, 2, 1, HV_ACT_ELU, 256},
+    {"fine_generator.conv2_downsample", 16, 16, 3, 2, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.conv3", 16, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.conv4_downsample", 32, 32, 3, 2, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.conv5", 32, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.conv6", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.conv7_atrous", 64, 64, 3, 1, 2, 2, HV_ACT_ELU, 64},
+    {"fine_generator.conv8_atrous", 64, 64, 3, 1, 4, 4, HV_ACT_ELU, 64},
+    {"fine_generator.conv9_atrous", 64, 64, 3, 1, 8, 8, HV_ACT_ELU, 64},
+    {"fine_generator.conv10_atrous", 64, 64, 3, 1, 16, 16, HV_ACT_ELU, 64},
+    {"fine_generator.pmconv1", 4, 16, 5, 1, 2, 1, HV_ACT_ELU, 256},
+    {"fine_generator.pmconv2_downsample", 16, 16, 3, 2, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.pmconv3", 16, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.pmconv4_downsample", 32, 64, 3, 2, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.pmconv5", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.pmconv6", 64, 64, 3, 1, 1, 1, HV_ACT_RELU, 64},
+    {"fine_generator.pmconv9", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.pmconv10", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.allconv11", 128, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.allconv19", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.allconv12", 64, 64, 3, 1, 1, 1, HV_ACT_ELU, 64},
+    {"fine_generator.allconv13", 64, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.allconv14", 32, 32, 3, 1, 1, 1, HV_ACT_ELU, 128},
+    {"fine_generator.allconv15", 32, 16, 3, 1, 1, 1, HV_ACT_ELU, 256},
+    {"fine_generator.allconv16", 16, 8, 3, 1, 1, 1, HV_ACT_ELU, 256},
+    {"fine_generator.allconv17", 9, 1, 3, 1, 1, 1, HV_ACT_NONE, 256},
+    {"fine_generator.allconv18", 9, 1, 3, 1, 1, 1, HV_ACT_SIGMOID, 256},
+};
+constexpr int kNumLayers = sizeof(kLayers) / sizeof(kLayers[0]);
+static_assert(kNumLayers == 47, "the generator has 47 conv blocks");
+constexpr int kTapAttention = 47;
+
+enum {
+  C1 = 0, C2, C3, C4, C5, C6, C7, C8, C9, C10, C11, C12, C20, C13, C14, C19, C15, C16, C17, C18,
+  F1, F2, F3, F4, F5, F6, F7, F8, F9, F10, PM1, PM2, PM3, PM4, PM5, PM6, PM9, PM10, A11, A19, A12,
+  A13, A14, A15, A16, A17, A18
+};
+
+}  // namespace hv
+
+using namespace hv;
+
+struct hv_generator {
+  int max_batch = 0, precision = 0;
+  bool prepared = false;
+  int last_n = 0;
+  const float* w_orig[kNumLayers] = {};
+  float* u[kNumLayers] = {};
+  float* v[kNumLayers] = {};
+  const float* bias_src[kNumLayers] = {};
+  const float* fc_w[2] = {};
+  const float* fc_b[2] = {};
+  // owned device memory
+  float* w_eff[kNumLayers] = {};   // fp32 [cout][cin][k][k]; the two heads of a stage are contiguous
+  float* bias[kNumLayers] = {};    // owned copies (heads contiguous)
+  float* act[kNumLayers] = {};     // fp32 NCHW activation per layer (heads: not materialised)
+  float* ca_out = nullptr;
+  void* ca_ws = nullptr;
+  float* sigma = nullptr;
+  SnJob* d_jobs = nullptr;
+  float* blob_w = nullptr;
+  float* blob_b = nullptr;
+  const float* last_heads[4] = {};  // x_stage1, coarse_seg, x_stage2, fine_seg of the last forward
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+
+namespace hv {
+
+static size_t act_elems(int idx, int n) {
+  const LayerSpec& L = kLayers[idx];
+  return (size_t)n * L.cout * L.hout * L.hout;
+}
+
+static int run_conv(hv_generator* g, int idx, int n, int hin, std::initializer_list<hv_conv_src> srcs, float* y,
+                    float* y2, int act_override, int cout_override, cudaStream_t st) {
+  const LayerSpec& L = kLayers[idx];
+  hv_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.n = n; d.cin = L.cin; d.cout = cout_override > 0 ? cout_override : L.cout;
+  d.hin = hin; d.win = hin; d.k = L.k; d.stride = L.stride; d.pad = L.pad; d.dil = L.dil;
+  d.act = act_override >= 0 ? act_override : L.act;
+  d.nsrc = 0;
+  for (const hv_conv_src& s : srcs) d.src[d.nsrc++] = s;
+  return conv2d_fwd_fp32(&d, g->w_eff[idx], g->bias[idx], y, y2, st);
+}
+
+static hv_conv_src S(const float* p, int ch, int mode = HV_SRC_DIRECT) {
+  hv_conv_src s; s.ptr = p; s.channels = ch; s.mode = mode; return s;
+}
+
+#define RC(expr) do { int _rc = (expr); if (_rc) return _rc; } while (0)
+
+static int forward_fp32(hv_generator* g, const float* x, const float* mask, const float* cam, const float* ratio,
+                        int n, float* coarse_seg, float* fine_seg, float* x_stage1, float* x_stage2, float* flow,
+                        float* pred1_h, float* pred2_h, int32_t* offsets, int per_sample_mask, cudaStream_t st) {
+  float** a = g->act;
+  // ---- coarse network (models/inpaint_networks.py:68-117)
+  RC(run_conv(g, C1, n, 256, {S(x, 1), S(ratio, 1, HV_SRC_SCALAR), S(mask, 1)}, a[C1], nullptr, -1, 0, st));
+  RC(run_conv(g, C2, n, 256, {S(a[C1], 16)}, a[C2], nullptr, -1, 0, st));
+  RC(run_conv(g, C3, n, 128, {S(a[C2], 32)}, a[C3], nullptr, -1, 0, st));
+  RC(run_conv(g, C4, n, 128, {S(a[C3], 32)}, a[C4], nullptr, -1, 0, st));
+  int prev = C4;
+  for (int l : {C5, C6, C7, C8, C9, C10}) { RC(run_conv(g, l, n, 64, {S(a[prev], 64)}, a[l], nullptr, -1, 0, st)); prev = l; }
+  RC(gap_fc_sigmoid(a[C10], g->fc_w[0], g->fc_b[0], pred1_h, n, 64, 64 * 64, st));
+  RC(run_conv(g, C11, n, 64, {S(a[C10], 64)}, a[C11], nullptr, -1, 0, st));
+  RC(run_conv(g, C12, n, 64, {S(a[C11], 64)}, a[C12], nullptr, -1, 0, st));
+  RC(run_conv(g, C20, n, 128, {S(a[C12], 64, HV_SRC_UP2), S(cam, 1, HV_SRC_SUB2)}, a[C20], nullptr, -1, 0, st));
+  RC(run_conv(g, C13, n, 128, {S(a[C20], 64)}, a[C13], nullptr, -1, 0, st));
+  RC(run_conv(g, C14, n, 128, {S(a[C13], 32)}, a[C14], nullptr, -1, 0, st));
+  RC(run_conv(g, C19, n, 256, {S(a[C14], 32, HV_SRC_UP2), S(cam, 1)}, a[C19], nullptr, -1, 0, st));
+  RC(run_conv(g, C15, n, 256, {S(a[C19], 32)}, a[C15], nullptr, -1, 0, st));
+  RC(run_conv(g, C16, n, 256, {S(a[C15], 16)}, a[C16], nullptr, -1, 0, st));
+  // conv17 (none, clamp) + conv18 (sigmoid) read the same 8-channel input: one dual-head pass
+  RC(run_conv(g, C17, n, 256, {S(a[C16], 8)}, x_stage1, coarse_seg, HV_ACT_HEADS, 2, st));
+
+  // ---- fine network (:169-232): fork the attention branch onto the side stream
+  HV_CUDA(cudaEventRecord(g->ev_fork, st));
+  HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+  cudaStream_t sa = g->side;
+  // attention branch
+  RC(run_conv(g, PM1, n, 256, {S(x, 1), S(coarse_seg, 1), S(mask, 1), S(ratio, 1, HV_SRC_SCALAR)}, a[PM1], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM2, n, 256, {S(a[PM1], 16)}, a[PM2], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM3, n, 128, {S(a[PM2], 16)}, a[PM3], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM4, n, 128, {S(a[PM3], 32)}, a[PM4], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM5, n, 64, {S(a[PM4], 64)}, a[PM5], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM6, n, 64, {S(a[PM5], 64)}, a[PM6], nullptr, -1, 0, sa));
+  RC(ctx_attn_fwd_fp32(a[PM6], mask, g->ca_out, offsets, flow, n, 64, 64, 64, 10.f, 1, per_sample_mask, g->ca_ws, sa));
+  RC(run_conv(g, PM9, n, 64, {S(g->ca_out, 64)}, a[PM9], nullptr, -1, 0, sa));
+  RC(run_conv(g, PM10, n, 64, {S(a[PM9], 64)}, a[PM10], nullptr, -1, 0, sa));
+  HV_CUDA(cudaEventRecord(g->ev_join, sa));
+  // dilated-conv branch
+  RC(run_conv(g, F1, n, 256, {S(x, 1), S(coarse_seg, 1), S(mask, 1), S(ratio, 1, HV_SRC_SCALAR)}, a[F1], nullptr, -1, 0, st));
+  RC(run_conv(g, F2, n, 256, {S(a[F1], 16)}, a[F2], nullptr, -1, 0, st));
+  RC(run_conv(g, F3, n, 128, {S(a[F2], 16)}, a[F3], nullptr, -1, 0, st));
+  RC(run_conv(g, F4, n, 128, {S(a[F3], 32)}, a[F4], nullptr, -1, 0, st));
+  RC(run_conv(g, F5, n, 64, {S(a[F4], 32)}, a[F5], nullptr, -1, 0, st));
+  prev = F5;
+  for (int l : {F6, F7, F8, F9, F10}) { RC(run_conv(g, l, n, 64, {S(a[prev], 64)}, a[l], nullptr, -1, 0, st)); prev = l; }
+  // merge
+  HV_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
+  RC(run_conv(g, A11, n, 64, {S(a[F10], 64), S(a[PM10], 64)}, a[A11], nullptr, -1, 0, st));
+  RC(gap_fc_sigmoid(a[A11], g->fc_w[1], g->fc_b[1], pred2_h, n, 64, 64 * 64, st));
+  RC(run_conv(g, A12, n, 64, {S(a[A11], 64)}, a[A12], nullptr, -1, 0, st));
+  RC(run_conv(g, A19, n, 64, {S(a[A12], 64)}, a[A19], nullptr, -1, 0, st));
+  RC(run_conv(g, A13, n, 128, {S(a[A19], 64, HV_SRC_UP2)}, a[A13], nullptr, -1, 0, st));
+  RC(run_conv(g, A14, n, 128, {S(a[A13], 32)}, a[A14], nullptr, -1, 0, st));
+  RC(run_conv(g, A15, n, 256, {S(a[A14], 32, HV_SRC_UP2)}, a[A15], nullptr, -1, 0, st));
+  RC(run_conv(g, A16, n, 256, {S(a[A15], 16)}, a[A16], nullptr, -1, 0, st));
+  RC(run_conv(g, A17, n, 256, {S(a[A16], 8), S(x_stage1, 1)}, x_stage2, fine_seg, HV_ACT_HEADS, 2, st));
+  g->last_heads[0] = x_stage1; g->last_heads[1] = coarse_seg; g->last_heads[2] = x_stage2; g->last_heads[3] = fine_seg;
+  g->last_n = n;
+  return HV_OK;
+}
+
+}  // namespace hv
+
+// =============================================================================== C ABI
+extern "C" {
+
+int hv_generator_num_layers(void) { return kNumLayers; }
+
+int hv_generator_layer_info(int idx, char* name_out, int* cin, int* cout, int* k, int* stride, int* pad, int* dil,
+                            int* act) {
+  HV_CHECK_ARG(idx >= 0 && idx < kNumLayers, "layer_info: index %d out of range", idx);
+  const LayerSpec& L = kLayers[idx];
+  if (name_out) { strncpy(name_out, L.name, 63); name_out[63] = 0; }
+  if (cin) *cin = L.cin;
+  if (cout) *cout = L.cout;
+  if (k) *k = L.k;
+  if (stride) *stride = L.stride;
+  if (pad) *pad = L.pad;
+  if (dil) *dil = L.dil;
+  if (act) *act = L.act;
+  return HV_OK;
+}
+
+int hv_generator_destroy(hv_generator* g) {
+  if (!g) return HV_OK;
+  for (int i = 0; i < kNumLayers; ++i) cudaFree(g->act[i]);
+  cudaFree(g->ca_out); cudaFree(g->ca_ws); cudaFree(g->sigma); cudaFree(g->d_jobs);
+  cudaFree(g->blob_w); cudaFree(g->blob_b);
+  if (g->side) cudaStreamDestroy(g->side);
+  if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+  if (g->ev_join) cudaEventDestroy(g->ev_join);
+  delete g;
+  return HV_OK;
+}
+
+int hv_generator_create(hv_generator** out, int max_batch, int precision) {
+  HV_CHECK_ARG(out, "generator_create: null out pointer");
+  HV_CHECK_ARG(max_batch >= 1 && max_batch <= 4096, "generator_create: max_batch %d out of range", max_batch);
+  HV_CHECK_ARG(precision == HV_PREC_FP32 || precision == HV_PREC_BF16, "generator_create: bad precision %d", precision);
+  if (precision == HV_PREC_BF16) {
+    set_error("generator_create: bf16 tensor-core plan not built in this library version");
+    return HV_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  HV_CUDA(cudaGetDeviceCount(&ndev));
+  hv_generator* g = new hv_generator();
+  g->max_batch = max_batch; g->precision = precision;
+  size_t wtot = 0, btot = 0;
+  for (int i = 0; i < kNumLayers; ++i) { wtot += (size_t)kLayers[i].cout * kLayers[i].cin * kLayers[i].k * kLayers[i].k; btot += kLayers[i].cout; }
+#define GEN_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { hv::set_error("%s failed: %s", #expr, cudaGetErrorString(_e)); hv_generator_destroy(g); return HV_ERR_CUDA; } } while (0)
+  GEN_TRY(cudaMalloc(&g->blob_w, wtot * sizeof(float)));
+  GEN_TRY(cudaMalloc(&g->blob_b, btot * sizeof(float)));
+  GEN_TRY(cudaMalloc(&g->sigma, kNumLayers * sizeof(float)));
+  GEN_TRY(cudaMalloc(&g->d_jobs, kNumLayers * sizeof(SnJob)));
+  size_t wo = 0, bo = 0;
+  for (int i = 0; i < kNumLayers; ++i) {  // state_dict order keeps conv17/conv18 (allconv17/18) adjacent
+    g->w_eff[i] = g->blob_w + wo; g->bias[i] = g->blob_b + bo;
+    wo += (size_t)kLayers[i].cout * kLayers[i].cin * kLayers[i].k * kLayers[i].k; bo += kLayers[i].cout;
+    if (i == C17 || i == C18 || i == A17 || i == A18) continue;  // heads write straight to the outputs
+    GEN_TRY(cudaMalloc(&g->act[i], act_elems(i, max_batch) * sizeof(float)));
+  }
+  GEN_TRY(cudaMalloc(&g->ca_out, (size_t)max_batch * 64 * 64 * 64 * sizeof(float)));
+  GEN_TRY(cudaMalloc(&g->ca_ws, ctx_attn_workspace_bytes(max_batch, 64, 64, 64)));
+  GEN_TRY(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+  GEN_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+  GEN_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+#undef GEN_TRY
+  *out = g;
+  return HV_OK;
+}
+
+int hv_generator_set_layer(hv_generator* g, int idx, const float* w_orig, float* u, float* v, const float* bias) {
+  HV_CHECK_ARG(g && idx >= 0 && idx < kNumLayers, "generator_set_layer: bad handle or index %d", idx);
+  HV_CHECK_ARG(w_orig && u && v && bias, "generator_set_layer: null parameter pointer for layer %d", idx);
+  g->w_orig[idx] = w_orig; g->u[idx] = u; g->v[idx] = v; g->bias_src[idx] = bias;
+  g->prepared = false;
+  return HV_OK;
+}
+
+int hv_generator_set_fc(hv_generator* g, int which, const float* w, const float* b) {
+  HV_CHECK_ARG(g && (which == 0 || which == 1) && w && b, "generator_set_fc: bad argument");
+  g->fc_w[which] = w; g->fc_b[which] = b;
+  return HV_OK;
+}
+
+int hv_generator_prepare(hv_generator* g, int training, hv_stream_t stream) {
+  HV_CHECK_ARG(g, "generator_prepare: null handle");
+  cudaStream_t st = as_stream(stream);
+  std::vector<SnJob> jobs(kNumLayers);
+  for (int i = 0; i < kNumLayers; ++i) {
+    if (!g->w_orig[i]) { set_error("generator_prepare: layer %d (%s) has no parameters", i, kLayers[i].name); return HV_ERR_STATE; }
+    jobs[i].w = g->w_orig[i]; jobs[i].u = g->u[i]; jobs[i].v = g->v[i];
+    jobs[i].cout = kLayers[i].cout; jobs[i].kdim = kLayers[i].cin * kLayers[i].k * kLayers[i].k;
+    jobs[i].w_eff = g->w_eff[i]; jobs[i].sigma = g->sigma + i;
+    HV_CUDA(cudaMemcpyAsync(g->bias[i], g->bias_src[i], kLayers[i].cout * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  if (!g->fc_w[0] || !g->fc_w[1]) { set_error("generator_prepare: fc_height parameters missing"); return HV_ERR_STATE; }
+  // pageable host -> device copy is synchronous w.r.t. the host buffer, so `jobs` may go out of scope
+  HV_CUDA(cudaMemcpyAsync(g->d_jobs, jobs.data(), sizeof(SnJob) * kNumLayers, cudaMemcpyHostToDevice, st));
+  int rc = sn_prepare_batched(g->d_jobs, kNumLayers, training, st);
+  if (rc) return rc;
+  g->prepared = true;
+  return HV_OK;
+}
+
+int hv_generator_forward(hv_generator* g, const float* x, const float* mask, const float* cam, const float* ratio,
+                         int n, float* coarse_seg, float* fine_seg, float* x_stage1, float* x_stage2, float* flow,
+                         float* pred1_h, float* pred2_h, int32_t* offsets, int per_sample_mask, hv_stream_t stream) {
+  HV_CHECK_ARG(g, "generator_forward: null handle");
+  if (!g->prepared) { set_error("generator_forward: call hv_generator_prepare first"); return HV_ERR_STATE; }
+  HV_CHECK_ARG(n >= 1 && n <= g->max_batch, "generator_forward: batch %d outside 1..%d", n, g->max_batch);
+  HV_CHECK_ARG(x && mask && cam && ratio && coarse_seg && fine_seg && x_stage1 && x_stage2 && pred1_h && pred2_h,
+               "generator_forward: null tensor pointer");
+  return forward_fp32(g, x, mask, cam, ratio, n, coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h,
+                      offsets, per_sample_mask, as_stream(stream));
+}
+
+long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream) {
+  HV_CHECK_ARG(g && out, "generator_read_tap: null argument");
+  HV_CHECK_ARG(g->last_n > 0, "generator_read_tap: no forward has run");
+  const float* src = nullptr;
+  size_t count = 0;
+  if (idx == kTapAttention) { src = g->ca_out; count = (size_t)g->last_n * 64 * 64 * 64; }
+  else {
+    HV_CHECK_ARG(idx >= 0 && idx < kNumLayers, "generator_read_tap: index %d out of range", idx);
+    count = act_elems(idx, g->last_n);
+    if (idx == C17) src = g->last_heads[0];
+    else if (idx == C18) src = g->last_heads[1];
+    else if (idx == A17) src = g->last_heads[2];
+    else if (idx == A18) src = g->last_heads[3];
+    else src = g->act[idx];
+  }
+  HV_CUDA(cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return (long long)count;
+}
+
+}  // extern "C"

@@ -1,0 +1,410 @@
+"""Drop-in mirror of the reference's ``models/inpaint_networks.py`` on hand-written sm_100a kernels.
+
+Same class names, constructor arguments, attribute names and ``state_dict`` keys
+(``<net>.<layer>.conv.{weight_orig,weight_u,weight_v,bias}``, ``<net>.fc_height.*``) as the
+reference, so ``latest_net_G.pth`` loads unchanged and callers such as
+``eval_3d_sagittal_twostage.py:100-101`` / ``pix2pix_model.py:188-189`` keep working.
+All arithmetic runs in libhv_b200.so (C ABI in include/hv_b200.h); torch is only used for
+device memory, parameter registration and streams.
+
+* ``Generator.forward``      -> one native plan (hv_generator_*), reference :28-32
+* ``Conv2dBlock.forward``    -> hv_sn_prepare + hv_conv2d_fwd, reference :494-503
+* ``ContextualAttention``    -> hv_ctx_attn_fwd, reference :247-410
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import HV_ACT, HV_SRC_DIRECT, HV_SRC_SCALAR, HV_SRC_SUB2, HV_SRC_UP2, check, ptr
+
+_ACT_NAMES = ("relu", "elu", "sigmoid", "none", "lrelu")
+
+
+class SNConv2d(nn.Module):
+    """Parameter holder with the exact key layout of ``spectral_norm(nn.Conv2d(...))``:
+    ``weight_orig`` / ``bias`` parameters and ``weight_u`` / ``weight_v`` buffers.  The
+    initialisation draws from the torch RNG in the same order as the reference
+    (Conv2d.reset_parameters, then spectral_norm's u, v), so equal seeds give equal weights."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.padding, self.dilation = kernel_size, stride, padding, dilation
+        w = torch.empty(out_channels, in_channels, kernel_size, kernel_size)
+        nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        fan_in = in_channels * kernel_size * kernel_size
+        bound = 1 / math.sqrt(fan_in)
+        b = torch.empty(out_channels)
+        nn.init.uniform_(b, -bound, bound)
+        u = nn.functional.normalize(w.new_empty(out_channels).normal_(0, 1), dim=0, eps=1e-12)
+        v = nn.functional.normalize(w.new_empty(fan_in).normal_(0, 1), dim=0, eps=1e-12)
+        self.bias = nn.Parameter(b)
+        self.weight_orig = nn.Parameter(w)
+        self.register_buffer("weight_u", u)
+        self.register_buffer("weight_v", v)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, dilation={self.dilation}, spectral_norm")
+
+    @torch.no_grad()
+    def effective_weight(self, training):
+        """(W_orig / sigma, sigma) on the device; runs one power iteration in place on
+        ``weight_u`` / ``weight_v`` first when ``training`` (spectral_norm.py:92-114)."""
+        w = self.weight_orig.detach().contiguous()
+        w_eff = torch.empty_like(w)
+        sigma = torch.empty(1, device=w.device, dtype=torch.float32)
+        check(_lib.lib().hv_sn_prepare(ptr(w), ptr(self.weight_u), ptr(self.weight_v), self.out_channels,
+                                       w[0].numel(), int(training), ptr(w_eff), ptr(sigma), _lib.stream()))
+        return w_eff, sigma
+
+
+def conv2d_fused(sources, w_eff, bias, k, stride, pad, dil, act, hin, win, y2_head=False):
+    """hv_conv2d_fwd on a channel-concatenation of ``sources`` = [(tensor, mode), ...]."""
+    desc = _lib.hv_conv_desc()
+    first = sources[0][0]
+    n = first.shape[0]
+    cin = 0
+    keep = []
+    for i, (t, mode) in enumerate(sources):
+        t = t.contiguous()
+        keep.append(t)
+        ch = 1 if mode == HV_SRC_SCALAR else t.shape[1]
+        desc.src[i].ptr = ptr(t)
+        desc.src[i].channels = ch
+        desc.src[i].mode = mode
+        cin += ch
+    cout = w_eff.shape[0]
+    desc.n, desc.cin, desc.cout, desc.hin, desc.win = n, cin, cout, hin, win
+    desc.k, desc.stride, desc.pad, desc.dil = k, stride, pad, dil
+    desc.act = HV_ACT["heads"] if y2_head else HV_ACT[act]
+    desc.nsrc = len(sources)
+    eff = (k - 1) * dil + 1
+    hout = (hin + 2 * pad - eff) // stride + 1
+    wout = (win + 2 * pad - eff) // stride + 1
+    dev = first.device
+    if y2_head:
+        y = torch.empty(n, 1, hout, wout, device=dev, dtype=torch.float32)
+        y2 = torch.empty_like(y)
+    else:
+        y = torch.empty(n, cout, hout, wout, device=dev, dtype=torch.float32)
+        y2 = None
+    check(_lib.lib().hv_conv2d_fwd(desc, ptr(w_eff), ptr(bias), ptr(y), ptr(y2), _lib.stream()))
+    return (y, y2) if y2_head else y
+
+
+class Conv2dBlock(nn.Module):
+    """reference models/inpaint_networks.py:420-503 (spectral-norm conv + bias + activation)."""
+
+    def __init__(self, input_dim, output_dim, kernel_size, stride, padding=0, conv_padding=0, dilation=1,
+                 weight_norm="sn", norm="none", activation="relu", pad_type="zero", transpose=False):
+        super().__init__()
+        self.use_bias = True
+        assert pad_type == "zero" and padding == 0, "Unsupported padding type: {}".format(pad_type)
+        assert norm == "none", "Unsupported normalization: {}".format(norm)
+        assert weight_norm == "sn", "Unsupported normalization: {}".format(weight_norm)
+        assert activation in _ACT_NAMES, "Unsupported activation: {}".format(activation)
+        assert not transpose, "transpose convolution is not on the path"
+        self.pad = None
+        self.norm = None
+        self.activation_name = activation
+        self.conv = SNConv2d(input_dim, output_dim, kernel_size, stride, conv_padding, dilation)
+
+    def forward(self, x, sources=None, extent=None):
+        """``sources``/``extent`` (not in the reference) feed the conv from a fused channel
+        concatenation [(tensor, hv_src_mode), ...] with virtual input extent (h, w)."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.conv.weight_orig.requires_grad and self.training):
+            raise NotImplementedError("hv_b200: the backward of Conv2dBlock is not built yet; "
+                                      "call under torch.no_grad()")
+        c = self.conv
+        w_eff, _ = c.effective_weight(self.training)
+        srcs = sources if sources is not None else [(x, HV_SRC_DIRECT)]
+        hin, win = extent if extent is not None else (x.shape[2], x.shape[3])
+        return conv2d_fused(srcs, w_eff, c.bias.detach(), c.kernel_size, c.stride, c.padding, c.dilation,
+                            self.activation_name, hin, win)
+
+
+def gen_conv(input_dim, output_dim, kernel_size=3, stride=1, padding=0, rate=1, activation="elu"):
+    """reference models/inpaint_networks.py:413-417"""
+    return Conv2dBlock(input_dim, output_dim, kernel_size, stride, conv_padding=padding, dilation=rate,
+                       activation=activation)
+
+
+def _height_head(x, fc):
+    n, c, h, w = x.shape
+    out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
+    check(_lib.lib().hv_gap_fc_sigmoid(ptr(x.contiguous()), ptr(fc.weight.detach().contiguous()),
+                                       ptr(fc.bias.detach().contiguous()), ptr(out), n, c, h * w, _lib.stream()))
+    return out
+
+
+def _ratio(slice_ratio, x):
+    return slice_ratio.reshape(-1).to(device=x.device, dtype=torch.float32).contiguous()
+
+
+class CoarseGenerator(nn.Module):
+    """reference models/inpaint_networks.py:36-117"""
+
+    def __init__(self, input_dim, cnum, use_cuda):
+        super().__init__()
+        self.use_cuda = use_cuda
+        self.conv1 = gen_conv(input_dim + 2, cnum, 5, 1, 2)
+        self.conv2_downsample = gen_conv(cnum, cnum * 2, 3, 2, 1)
+        self.conv3 = gen_conv(cnum * 2, cnum * 2, 3, 1, 1)
+        self.conv4_downsample = gen_conv(cnum * 2, cnum * 4, 3, 2, 1)
+        self.conv5 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.conv6 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.conv7_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 2, rate=2)
+        self.conv8_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 4, rate=4)
+        self.conv9_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 8, rate=8)
+        self.conv10_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 16, rate=16)
+        self.conv11 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.conv12 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.conv20 = gen_conv(cnum * 4 + 1, cnum * 4, 3, 1, 1)
+        self.conv13 = gen_conv(cnum * 4, cnum * 2, 3, 1, 1)
+        self.conv14 = gen_conv(cnum * 2, cnum * 2, 3, 1, 1)
+        self.conv19 = gen_conv(cnum * 2 + 1, cnum * 2, 3, 1, 1)
+        self.conv15 = gen_conv(cnum * 2, cnum, 3, 1, 1)
+        self.conv16 = gen_conv(cnum, cnum // 2, 3, 1, 1)
+        self.conv17 = gen_conv(cnum // 2, input_dim, 3, 1, 1, activation="none")
+        self.conv18 = gen_conv(cnum // 2, input_dim, 3, 1, 1, activation="sigmoid")
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc_height = nn.Linear(cnum * 4, 1)
+
+    def forward(self, x, mask, CAM, slice_ratio):
+        """Layer-by-layer path through the stand-alone ops (Generator.forward uses the fused plan)."""
+        ratio = _ratio(slice_ratio, x)
+        mask = mask.to(x.device)
+        h, w = x.shape[2:]
+        t = self.conv1(x, [(x, HV_SRC_DIRECT), (ratio, HV_SRC_SCALAR), (mask, HV_SRC_DIRECT)])
+        for name in ("conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6", "conv7_atrous",
+                     "conv8_atrous", "conv9_atrous", "conv10_atrous"):
+            t = getattr(self, name)(t)
+        pred1_h = _height_head(t, self.fc_height)
+        t = self.conv12(self.conv11(t))
+        CAM = CAM.to(device=x.device, dtype=torch.float32)
+        t = self.conv20(t, [(t, HV_SRC_UP2), (CAM, HV_SRC_SUB2)], (h // 2, w // 2))
+        t = self.conv14(self.conv13(t))
+        t = self.conv19(t, [(t, HV_SRC_UP2), (CAM, HV_SRC_DIRECT)], (h, w))
+        t = self.conv16(self.conv15(t))
+        x_stage1 = torch.clamp(self.conv17(t), -1.0, 1.0)
+        coarse_seg_sigmoid = self.conv18(t)
+        return coarse_seg_sigmoid, x_stage1, pred1_h
+
+
+class FineGenerator(nn.Module):
+    """reference models/inpaint_networks.py:120-232"""
+
+    def __init__(self, input_dim, cnum, use_cuda=True):
+        super().__init__()
+        self.use_cuda = use_cuda
+        self.conv1 = gen_conv(input_dim + 3, cnum, 5, 1, 2)
+        self.conv2_downsample = gen_conv(cnum, cnum, 3, 2, 1)
+        self.conv3 = gen_conv(cnum, cnum * 2, 3, 1, 1)
+        self.conv4_downsample = gen_conv(cnum * 2, cnum * 2, 3, 2, 1)
+        self.conv5 = gen_conv(cnum * 2, cnum * 4, 3, 1, 1)
+        self.conv6 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.conv7_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 2, rate=2)
+        self.conv8_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 4, rate=4)
+        self.conv9_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 8, rate=8)
+        self.conv10_atrous = gen_conv(cnum * 4, cnum * 4, 3, 1, 16, rate=16)
+        self.pmconv1 = gen_conv(input_dim + 3, cnum, 5, 1, 2)
+        self.pmconv2_downsample = gen_conv(cnum, cnum, 3, 2, 1)
+        self.pmconv3 = gen_conv(cnum, cnum * 2, 3, 1, 1)
+        self.pmconv4_downsample = gen_conv(cnum * 2, cnum * 4, 3, 2, 1)
+        self.pmconv5 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.pmconv6 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1, activation="relu")
+        self.contextul_attention = ContextualAttention(self.use_cuda, ksize=3, stride=1, rate=2, fuse_k=3,
+                                                       softmax_scale=10, fuse=True)
+        self.pmconv9 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.pmconv10 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.allconv11 = gen_conv(cnum * 8, cnum * 4, 3, 1, 1)
+        self.allconv19 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.allconv12 = gen_conv(cnum * 4, cnum * 4, 3, 1, 1)
+        self.allconv13 = gen_conv(cnum * 4, cnum * 2, 3, 1, 1)
+        self.allconv14 = gen_conv(cnum * 2, cnum * 2, 3, 1, 1)
+        self.allconv15 = gen_conv(cnum * 2, cnum, 3, 1, 1)
+        self.allconv16 = gen_conv(cnum, cnum // 2, 3, 1, 1)
+        self.allconv17 = gen_conv(cnum // 2 + 1, 1, 3, 1, 1, activation="none")
+        self.allconv18 = gen_conv(cnum // 2 + 1, 1, 3, 1, 1, activation="sigmoid")
+        self.global_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc_height = nn.Linear(cnum * 4, 1)
+
+    def forward(self, xin, x_stage1, mask, coarse_seg, slice_ratio):
+        ratio = _ratio(slice_ratio, xin)
+        mask = mask.to(xin.device)
+        h, w = xin.shape[2:]
+        xnow = [(xin, HV_SRC_DIRECT), (coarse_seg, HV_SRC_DIRECT), (mask, HV_SRC_DIRECT), (ratio, HV_SRC_SCALAR)]
+        t = self.conv1(xin, xnow)
+        for name in ("conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6", "conv7_atrous",
+                     "conv8_atrous", "conv9_atrous", "conv10_atrous"):
+            t = getattr(self, name)(t)
+        x_hallu = t
+        t = self.pmconv1(xin, xnow)
+        for name in ("pmconv2_downsample", "pmconv3", "pmconv4_downsample", "pmconv5", "pmconv6"):
+            t = getattr(self, name)(t)
+        t, offset_flow = self.contextul_attention(t, t, mask)
+        pm = self.pmconv10(self.pmconv9(t))
+        t = self.allconv11(x_hallu, [(x_hallu, HV_SRC_DIRECT), (pm, HV_SRC_DIRECT)])
+        pred2_h = _height_head(t, self.fc_height)
+        t = self.allconv19(self.allconv12(t))
+        t = self.allconv13(t, [(t, HV_SRC_UP2)], (h // 2, w // 2))
+        t = self.allconv14(t)
+        t = self.allconv15(t, [(t, HV_SRC_UP2)], (h, w))
+        t = self.allconv16(t)
+        cat = [(t, HV_SRC_DIRECT), (x_stage1, HV_SRC_DIRECT)]
+        x_stage2 = torch.clamp(self.allconv17(t, cat), -1.0, 1.0)
+        fine_seg_sigmoid = self.allconv18(t, cat)
+        return fine_seg_sigmoid, x_stage2, offset_flow, pred2_h
+
+
+class ContextualAttention(nn.Module):
+    """reference models/inpaint_networks.py:235-410 (f is matched against itself: forward(f, f, mask))."""
+
+    def __init__(self, use_cuda, ksize=3, stride=1, rate=1, fuse_k=3, softmax_scale=10, fuse=False):
+        super().__init__()
+        self.ksize, self.stride, self.rate, self.fuse_k = ksize, stride, rate, fuse_k
+        self.softmax_scale, self.fuse, self.use_cuda = softmax_scale, fuse, use_cuda
+        self.per_sample_mask = False  # False == the reference (mask of sample 0 for the whole batch)
+        self.last_offsets = None
+
+    def forward(self, f, b, mask=None):
+        if b is not f and not (b.data_ptr() == f.data_ptr() and b.shape == f.shape):
+            raise NotImplementedError("hv_b200 ContextualAttention: only forward(x, x, mask) is built")
+        if not (self.ksize == 3 and self.stride == 1 and self.rate == 2 and self.fuse_k == 3):
+            raise NotImplementedError("hv_b200 ContextualAttention: only ksize=3, stride=1, rate=2, fuse_k=3")
+        n, c, h, w = f.shape
+        f = f.contiguous()
+        if mask is None:
+            mask = torch.zeros(n, 1, 4 * h, 4 * w, device=f.device, dtype=torch.float32)
+        mask = mask.to(f.device).contiguous()
+        y = torch.empty_like(f)
+        offsets = torch.empty(n, 2, h // 2, w // 2, device=f.device, dtype=torch.int32)
+        flow = torch.empty(n, 3, 4 * h, 4 * w, device=f.device, dtype=torch.float32)
+        L = _lib.lib()
+        ws = torch.empty(L.hv_ctx_attn_workspace_bytes(n, c, h, w), device=f.device, dtype=torch.uint8)
+        check(L.hv_ctx_attn_fwd(ptr(f), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w,
+                                float(self.softmax_scale), int(bool(self.fuse)), int(self.per_sample_mask), ptr(ws),
+                                _lib.stream()))
+        self.last_offsets = offsets
+        return y, flow
+
+
+class Generator(nn.Module):
+    """reference models/inpaint_networks.py:16-32.
+
+    ``forward`` runs the whole two-stage network as one native plan.  Extra attributes (not
+    in the reference): ``precision`` ('fp32' parity mode | 'bf16' tensor-core mode),
+    ``per_sample_mask`` (attention mask per sample instead of the reference's sample-0
+    quirk), ``return_flow`` (skip the colour-wheel image when False)."""
+
+    def __init__(self, config, use_cuda):
+        super().__init__()
+        self.input_dim = config["input_dim"]
+        self.cnum = config["ngf"]
+        self.use_cuda = use_cuda
+        self.coarse_generator = CoarseGenerator(self.input_dim, self.cnum, self.use_cuda)
+        self.fine_generator = FineGenerator(self.input_dim, self.cnum, self.use_cuda)
+        self.precision = "fp32"
+        self.per_sample_mask = False
+        self.return_flow = True
+        self._plan = None
+        self._plan_key = None
+        self._param_sig = None
+        self.last_offsets = None
+
+    # ---- native plan management -------------------------------------------------------
+    def _layers(self):
+        L = _lib.lib()
+        out = []
+        name = _lib.ctypes.create_string_buffer(64)
+        for i in range(L.hv_generator_num_layers()):
+            check(L.hv_generator_layer_info(i, name, None, None, None, None, None, None, None))
+            net, layer = name.value.decode().split(".")
+            out.append(getattr(getattr(self, net), layer).conv)
+        return out
+
+    def _destroy_plan(self):
+        if self._plan is not None:
+            _lib.lib().hv_generator_destroy(self._plan)
+            self._plan = None
+            self._plan_key = None
+            self._param_sig = None
+
+    def __del__(self):
+        try:
+            self._destroy_plan()
+        except Exception:
+            pass
+
+    def _ensure_plan(self, n, device):
+        if self.input_dim != 1 or self.cnum != 16:
+            raise NotImplementedError("hv_b200 Generator plan is built for input_dim=1, ngf=16 (the reference's "
+                                      "hard-coded configuration, pix2pix_model.py:103)")
+        L = _lib.lib()
+        key = (device.index, self.precision)
+        if self._plan is None or self._plan_key[:2] != key or self._plan_key[2] < n:
+            self._destroy_plan()
+            cap = max(n, 16)
+            handle = _lib.c_void_p()
+            check(L.hv_generator_create(_lib.ctypes.byref(handle), cap, _lib.HV_PREC[self.precision]))
+            self._plan = handle
+            self._plan_key = key + (cap,)
+        convs = self._layers()
+        fcs = (self.coarse_generator.fc_height, self.fine_generator.fc_height)
+        sig = tuple((c.weight_orig.data_ptr(), c.weight_orig._version, c.bias.data_ptr(), c.bias._version,
+                     c.weight_u.data_ptr(), c.weight_u._version, c.weight_v.data_ptr(), c.weight_v._version)
+                    for c in convs) + tuple((f.weight.data_ptr(), f.weight._version, f.bias.data_ptr(),
+                                             f.bias._version) for f in fcs)
+        training = self.training
+        if sig != self._param_sig or training:
+            for i, c in enumerate(convs):
+                for t in (c.weight_orig, c.bias, c.weight_u, c.weight_v):
+                    if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                        raise _lib.HvError("Generator parameters must be contiguous fp32 CUDA tensors "
+                                           "(call .cuda() / .to(device) first)")
+                check(L.hv_generator_set_layer(self._plan, i, ptr(c.weight_orig.data), ptr(c.weight_u),
+                                               ptr(c.weight_v), ptr(c.bias.data)))
+            for i, f in enumerate(fcs):
+                check(L.hv_generator_set_fc(self._plan, i, ptr(f.weight.data), ptr(f.bias.data)))
+            check(L.hv_generator_prepare(self._plan, int(training), _lib.stream()))
+            self._param_sig = None if training else sig
+        return self._plan
+
+    def forward(self, x, mask, CAM, slice_ratio):
+        if not x.is_cuda:
+            raise _lib.HvError("hv_b200 Generator needs CUDA tensors (no CPU fallback)")
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("hv_b200 Generator: autograd backward is not built yet; run the forward "
+                                      "under torch.no_grad() (eval driver / evaluate_model path)")
+        dev = x.device
+        n, _, h, w = x.shape
+        if (h, w) != (256, 256):
+            raise NotImplementedError("hv_b200 Generator plan is built for 256x256 slices")
+        with torch.no_grad():
+            x = x.to(torch.float32).contiguous()
+            mask = mask.to(device=dev, dtype=torch.float32).contiguous()
+            CAM = CAM.to(device=dev, dtype=torch.float32).contiguous()
+            ratio = _ratio(slice_ratio, x)
+            plan = self._ensure_plan(n, dev)
+            mk = lambda *s: torch.empty(*s, device=dev, dtype=torch.float32)
+            coarse_seg, fine_seg, x_stage1, x_stage2 = (mk(n, 1, h, w) for _ in range(4))
+            flow = mk(n, 3, h, w) if self.return_flow else None
+            pred1_h, pred2_h = mk(n, 1), mk(n, 1)
+            offsets = torch.empty(n, 2, 32, 32, device=dev, dtype=torch.int32)
+            check(_lib.lib().hv_generator_forward(
+                plan, ptr(x), ptr(mask), ptr(CAM), ptr(ratio), n, ptr(coarse_seg), ptr(fine_seg), ptr(x_stage1),
+                ptr(x_stage2), ptr(flow), ptr(pred1_h), ptr(pred2_h), ptr(offsets), int(self.per_sample_mask),
+                _lib.stream()))
+            self.last_offsets = offsets
+        return coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h
+
+    @torch.no_grad()
+    def read_tap(self, idx):
+        """Activation of conv block ``idx`` (state_dict order; 47 = attention output) of the last forward."""
+        L = _lib.lib()
+        buf = torch.empty(self._plan_key[2] * 16 * 256 * 256, device=self.coarse_generator.fc_height.weight.device)
+        cnt = check(L.hv_generator_read_tap(self._plan, idx, ptr(buf), _lib.stream()))
+        return buf[:cnt].clone()
