@@ -135,8 +135,8 @@ def gen_conv(input_dim, output_dim, kernel_size=3, stride=1, padding=0, rate=1, 
 def _height_head(x, fc):
     n, c, h, w = x.shape
     out = torch.empty(n, 1, device=x.device, dtype=torch.float32)
-    check(_lib.lib().hv_gap_fc_sigmoid(ptr(x.contiguous()), ptr(fc.weight.detach().contiguous()),
-                                       ptr(fc.bias.detach().contiguous()), ptr(out), n, c, h * w, _lib.stream()))
+    xc, wc, bc = x.contiguous(), fc.weight.detach().contiguous(), fc.bias.detach().contiguous()
+    check(_lib.lib().hv_gap_fc_sigmoid(ptr(xc), ptr(wc), ptr(bc), ptr(out), n, c, h * w, _lib.stream()))
     return out
 
 
@@ -314,6 +314,7 @@ class Generator(nn.Module):
         self._plan_key = None
         self._param_sig = None
         self.last_offsets = None
+        self._last_out = None
 
     # ---- native plan management -------------------------------------------------------
     def _layers(self):
@@ -399,7 +400,9 @@ class Generator(nn.Module):
                 ptr(x_stage2), ptr(flow), ptr(pred1_h), ptr(pred2_h), ptr(offsets), int(self.per_sample_mask),
                 _lib.stream()))
             self.last_offsets = offsets
-        return coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h
+        out = (coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h)
+        self._last_out = out  # the head taps of read_tap() alias these buffers
+        return out
 
     @torch.no_grad()
     def read_tap(self, idx):

@@ -34,8 +34,11 @@ def stitch(gen, real, pred_h, x1, x2, height, maxheight=40, return_rows=False):
     pred_h = pred_h.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
     out = torch.empty_like(gen)
     rows = torch.empty(n, 4, device=dev, dtype=torch.int32)
-    check(_lib.lib().hv_stitch(ptr(gen), ptr(real), ptr(pred_h), ptr(_i32(x1, dev)), ptr(_i32(x2, dev)),
-                               ptr(_i32(height, dev)), int(maxheight), ptr(out), ptr(rows), n, h, w, _lib.stream()))
+    # keep every converted tensor alive until the launch is enqueued (the caching allocator would
+    # otherwise hand a dead temporary's block to the next one)
+    x1d, x2d, hd = _i32(x1, dev), _i32(x2, dev), _i32(height, dev)
+    check(_lib.lib().hv_stitch(ptr(gen), ptr(real), ptr(pred_h), ptr(x1d), ptr(x2d), ptr(hd), int(maxheight),
+                               ptr(out), ptr(rows), n, h, w, _lib.stream()))
     return (out, rows) if return_rows else out
 
 
@@ -49,8 +52,13 @@ def column_heights(vol_fake, vol_label, axis, z0, z1):
     nz = z1 - z0
     counts = torch.empty(max(nz, 0), 8, ncols, device=vol_label.device, dtype=torch.int32)
     meta = torch.empty(max(nz, 0), 8, device=vol_label.device, dtype=torch.int32)
-    check(_lib.lib().hv_column_heights(ptr(vol_fake.contiguous()), ptr(vol_label.contiguous()), d0, d1, d2, axis,
-                                       z0, z1, ptr(counts), ptr(meta), _lib.stream()))
+    if nz <= 0:
+        if nz < 0:
+            raise _lib.HvError(f"column_heights: empty window [{z0},{z1})")
+        return counts, meta
+    vf, vl = vol_fake.contiguous(), vol_label.contiguous()
+    check(_lib.lib().hv_column_heights(ptr(vf), ptr(vl), d0, d1, d2, axis, z0, z1, ptr(counts), ptr(meta),
+                                       _lib.stream()))
     return counts, meta
 
 

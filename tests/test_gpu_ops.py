@@ -55,14 +55,15 @@ def test_conv2d_fused_sources_upsample_concat_scalar():
 def test_conv2d_rejects_bad_arguments():
     x = torch.zeros(1, 3, 8, 8, device="cuda")
     w = torch.zeros(4, 5, 3, 3, device="cuda")
+    d = _lib.hv_conv_desc()
+    d.n, d.cin, d.cout, d.hin, d.win, d.k, d.stride, d.pad, d.dil, d.act, d.nsrc = 1, 5, 4, 8, 8, 3, 1, 1, 1, 1, 1
+    d.src[0].ptr, d.src[0].channels, d.src[0].mode = x.data_ptr(), 3, 0
     with pytest.raises(_lib.HvError, match="cin"):
-        conv2d_fused([(x, 0)], w[:, :3].contiguous(), None, 3, 1, 1, 1, "elu", 8, 8) and None
-        d = _lib.hv_conv_desc()
-        d.n, d.cin, d.cout, d.hin, d.win, d.k, d.stride, d.pad, d.dil, d.act, d.nsrc = 1, 5, 4, 8, 8, 3, 1, 1, 1, 1, 1
-        d.src[0].ptr, d.src[0].channels, d.src[0].mode = x.data_ptr(), 3, 0
         _lib.check(_lib.lib().hv_conv2d_fwd(d, w.data_ptr(), None, x.data_ptr(), None, None))
     with pytest.raises(_lib.HvError, match="not built"):
         conv2d_fused([(x, 0)], torch.zeros(4, 3, 7, 7, device="cuda"), None, 7, 1, 3, 1, "elu", 8, 8)
+    with pytest.raises(_lib.HvError, match="null"):
+        _lib.check(_lib.lib().hv_conv2d_fwd(d, None, None, x.data_ptr(), None, None))
 
 
 def test_spectral_norm_prepare_eval_and_train():
@@ -80,7 +81,8 @@ def test_spectral_norm_prepare_eval_and_train():
         conv = conv.cuda()
         w_eff, s = conv.effective_weight(training)
         assert abs(float(s) - float(sigma)) <= 1e-5 * abs(float(sigma))
-        assert float((w_eff.cpu() - w / sigma).abs().max()) <= 1e-5
+        ref_eff = w / sigma
+        assert float((w_eff.cpu() - ref_eff).abs().max()) <= 1e-5 * float(ref_eff.abs().max())
         assert float((conv.weight_u.cpu() - uu).abs().max()) <= 1e-6
         assert float((conv.weight_v.cpu() - vv).abs().max()) <= 1e-6
 
@@ -94,19 +96,21 @@ def test_contextual_attention_against_oracle():
     mask[2, :, 180:221] = 1
     ca = hv.ContextualAttention(True, ksize=3, stride=1, rate=2, fuse_k=3, softmax_scale=10, fuse=True)
     y_ref, off_ref, inter = gr.contextual_attention(f, mask, return_intermediates=True)
-    y, flow = ca(f.cuda(), f.cuda(), mask.cuda())
+    fc = f.cuda()
+    y, flow = ca(fc, fc, mask.cuda())
     assert float((y.cpu() - y_ref).abs().max()) <= 1e-4
     agree = (ca.last_offsets.cpu().long() == off_ref).float().mean()
     assert agree >= 0.999   # argmax ties between near-equal scores may break differently
     assert ((flow.cpu() - gr.flow_image(off_ref)).abs() > 1e-6).float().mean() < 0.01
     ca.per_sample_mask = True
-    y2, _ = ca(f.cuda(), f.cuda(), mask.cuda())
+    y2, _ = ca(fc, fc, mask.cuda())
     for i in range(3):
         yi, _ = gr.contextual_attention(f[i:i + 1], mask[i:i + 1])
         assert float((y2[i:i + 1].cpu() - yi).abs().max()) <= 1e-4
     # no fuse, empty mask (the reference's mask=None branch)
     ca2 = hv.ContextualAttention(True, ksize=3, stride=1, rate=2, fuse_k=3, softmax_scale=10, fuse=False)
-    y3, _ = ca2(f[:1].cuda(), f[:1].cuda(), None)
+    f1 = f[:1].cuda()
+    y3, _ = ca2(f1, f1, None)
     y3_ref, _ = gr.contextual_attention(f[:1], torch.zeros(1, 1, 256, 256), fuse=False)
     assert float((y3.cpu() - y3_ref).abs().max()) <= 1e-4
 
@@ -163,6 +167,12 @@ def test_column_heights_and_rhlv_against_oracle(axis, golden_dir):
     tl = torch.from_numpy(lab.astype(np.uint8)).cuda()
     counts, meta = mask_ops.column_heights(tf, tl, axis, c - ln, c + ln)
     counts, meta = counts.cpu().numpy(), meta.cpu().numpy()
+    win_f = np.moveaxis(np.take(fk, range(c - ln, c + ln), axis=axis), axis, 0)   # [s, rows, cols]
+    win_l = np.moveaxis(np.take(lab, range(c - ln, c + ln), axis=axis), axis, 0)
+    for s in range(2 * ln):
+        if meta[s, 0]:
+            assert np.array_equal(counts[s, 0], np.count_nonzero(win_f[s], axis=0)), ("raw fake counts", s)
+            assert np.array_equal(counts[s, 4], np.count_nonzero(win_l[s], axis=0)), ("raw label counts", s)
     sl = [slice(None)] * 3
     sl[axis] = slice(c - ln, c + ln)
     recs = {r["z"]: r for r in mo.column_heights(fk[tuple(sl)], lab[tuple(sl)], axis)}
