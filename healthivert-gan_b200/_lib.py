@@ -37,6 +37,7 @@ SIGNATURES = {
     "hv_launch_count": (c_uint64, []),
     "hv_sn_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "hv_conv2d_fwd": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_conv2d_bf16": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "hv_gap_fc_sigmoid": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hv_ctx_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "hv_ctx_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,

@@ -1,0 +1,629 @@
+// bf16 implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM), operands staged by TMA, fused bias + activation epilogue.  See conv_tc.cuh for the layout.
+//
+// Replaces Conv2dBlock.forward (reference models/inpaint_networks.py:494-503) in bf16 mode for every
+// conv block of the generator, including the fused channel concat (multi-source K blocks), the fused
+// nearest x2 upsample (the producer's epilogue writes the 2x2 replicated pixels) and the dual output
+// heads (conv17+conv18 / allconv17+allconv18: clamp and sigmoid from one accumulator tile).
+//
+// Kernel structure (one persistent CTA per SM, 192 threads):
+//   warp 0   : TMA producer  - weights once (cp.async.bulk), then per tile one box per (source, ky) band
+//   warp 1   : TMEM allocator + single-thread tcgen05.mma issuer; M=128 positions x N=Cout_pad x K=16
+//   warps 2-5: epilogue       - tcgen05.ld (one TMEM lane quadrant each) -> bias/act -> bf16 -> global
+// Pipelines: smem band ring (full/empty mbarriers, tcgen05.commit frees a slot) and a 2-deep TMEM
+// accumulator ring so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <string.h>
+#include <vector>
+#include "hv_common.cuh"
+#include "conv_tc.cuh"
+
+namespace hv {
+
+// ------------------------------------------------------------------------------------------- PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// K-major, no-swizzle UMMA shared-memory descriptor: core matrix = 8 rows x 16 B contiguous;
+// LBO = byte distance between the two 8-element K chunks of one MMA, SBO = distance between 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float act_fast(float x, int act) {
+  switch (act) {
+    case HV_ACT_ELU: return x > 0.f ? x : __expf(x) - 1.f;
+    case HV_ACT_RELU: return fmaxf(x, 0.f);
+    case HV_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
+    case HV_ACT_LRELU02: return x > 0.f ? x : 0.2f * x;
+    case HV_ACT_CLAMP1: return fminf(fmaxf(x, -1.f), 1.f);
+    default: return x;
+  }
+}
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 128;
+
+// ------------------------------------------------------------------------------------------- kernel
+template <int N_PAD>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t w_region = (p.w_bytes + 127u) & ~127u;
+  uint8_t* s_slots = smem + w_region;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + (size_t)p.nslots * p.slot_bytes);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8u * p.nslots;
+  const uint32_t bar_w = bar_empty + 8u * p.nslots;
+  const uint32_t bar_tfull = bar_w + 8u;
+  const uint32_t bar_tempty = bar_tfull + 16u;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 5);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[1]) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < p.nslots; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
+      mbar_init(bar_w, 1);
+      for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TC_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(bar_w, p.w_bytes);
+      bulk_load(smem_u32(smem), p.w_packed, p.w_bytes, bar_w);
+      int slot = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int img = tile / p.tiles_per_image;
+        const int o0 = (tile - img * p.tiles_per_image) * TC_TILE_M;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg& sg = p.segs[s];
+          mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+          const uint32_t fb = bar_full + 8u * slot;
+          mbar_expect_tx(fb, (uint32_t)sg.npix * sg.nchunks * 16u);
+          const uint32_t dst = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
+          if (p.stride == 1) tma_load_4d(dst, &p.maps[sg.map], fb, 0, o0 + p.q_first + sg.rel_start, 0, img);
+          else tma_load_5d(dst, &p.maps[sg.map], fb, 0, sg.parity, o0 + sg.rel_start, 0, img);
+          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_PAD >> 3) << 17) | ((128u >> 4) << 24);
+      mbar_wait(bar_w, 0);
+      tc_fence_after();
+      const uint32_t w_base = smem_u32(smem);
+      int slot = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_PAD);
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const TcSeg& sg = p.segs[s];
+          mbar_wait(bar_full + 8u * slot, phase);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
+          const uint32_t a_lbo = (uint32_t)sg.npix * 16u;
+          const int ksteps = sg.nchunks >> 1;
+          for (int t = sg.tap_begin; t < sg.tap_end; ++t) {
+            const uint32_t a0 = a_base + (uint32_t)p.taps[t].pix_off * 16u;
+            const uint32_t b0 = w_base + (uint32_t)p.taps[t].w_off;
+            for (int ks = 0; ks < ksteps; ++ks) {
+              const uint64_t ad = umma_desc(a0 + (uint32_t)ks * 2u * a_lbo, a_lbo, 128u);
+              const uint64_t bd = umma_desc(b0 + (uint32_t)ks * 2u * (N_PAD * 16u), N_PAD * 16u, 128u);
+              umma_bf16(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(bar_empty + 8u * slot);  // frees the band slot once these MMAs have read it
+          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        }
+        umma_commit(bar_tfull + 8u * acc);  // accumulator tile complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int img = tile / p.tiles_per_image;
+      const int o = (tile - img * p.tiles_per_image) * TC_TILE_M + quad * 32 + lane;
+      mbar_wait(bar_tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      float v[N_PAD];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD);
+#pragma unroll
+      for (int g = 0; g < N_PAD / 16; ++g) tmem_ld16(taddr + g * 16, v + g * 16);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8u * acc);  // accumulator stage may be overwritten by the next tile
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+
+      int yy, xx;
+      if (p.stride == 1) {
+        const int q = o + p.q_first;
+        yy = q / p.in_pitch - p.in_border;
+        xx = q - (yy + p.in_border) * p.in_pitch - p.in_border;
+      } else {
+        yy = o / p.in_pitch;
+        xx = o - yy * p.in_pitch;
+      }
+      if (yy < 0 || yy >= p.h_out || xx < 0 || xx >= p.w_out) continue;
+
+      if (p.out_mode == TC_OUT_HEADS) {
+        const float a0 = act_fast(v[0] + __ldg(p.bias + 0), HV_ACT_CLAMP1);
+        const float a1 = act_fast(v[1] + __ldg(p.bias + 1), HV_ACT_SIGMOID);
+        const size_t pix = ((size_t)img * p.h_out + yy) * p.w_out + xx;
+        p.head0[pix] = a0;
+        p.head1[pix] = a1;
+        if (p.aux0.ptr) {
+          const TcAux& a = p.aux0;
+          a.ptr[(((size_t)img * a.chunks + a.chunk) * a.plane + (size_t)(yy + a.border) * a.pitch + xx + a.border) * 8 + a.channel] = __float2bfloat16(a0);
+        }
+        if (p.aux1.ptr) {
+          const TcAux& a = p.aux1;
+          a.ptr[(((size_t)img * a.chunks + a.chunk) * a.plane + (size_t)(yy + a.border) * a.pitch + xx + a.border) * 8 + a.channel] = __float2bfloat16(a1);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < N_PAD / 8; ++c) {
+        if (c >= p.out_nchunks) break;
+        uint32_t pk[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float f0 = act_fast(v[c * 8 + 2 * j] + __ldg(p.bias + c * 8 + 2 * j), p.act);
+          const float f1 = act_fast(v[c * 8 + 2 * j + 1] + __ldg(p.bias + c * 8 + 2 * j + 1), p.act);
+          __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        __nv_bfloat16* plane = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off + c) * p.out_plane * 8;
+        if (p.out_mode == TC_OUT_CHUNKED) {
+          const size_t pos = (size_t)(yy + p.out_border) * p.out_pitch + xx + p.out_border;
+          *reinterpret_cast<uint4*>(plane + pos * 8) = val;
+        } else {  // nearest x2 upsample fused into the store (inpaint_networks.py:97,:105,:219,:222)
+          const size_t pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
+          *reinterpret_cast<uint4*>(plane + pos * 8) = val;
+          *reinterpret_cast<uint4*>(plane + (pos + 1) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch + 1) * 8) = val;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host: tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* map, const TcBuf& b, int stride, int box_pix, int box_chunks) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return HV_ERR_CUDA; }
+  const cuuint64_t plane = (cuuint64_t)b.plane();
+  CUresult r;
+  if (stride == 1) {
+    cuuint64_t dims[4] = {8, plane, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+    cuuint64_t strides[3] = {16, plane * 16, plane * 16 * b.chunks};
+    cuuint32_t box[4] = {8, (cuuint32_t)box_pix, (cuuint32_t)box_chunks, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {8, 2, plane / 2, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+    cuuint64_t strides[4] = {16, 32, plane * 16, plane * 16 * b.chunks};
+    cuuint32_t box[5] = {8, 1, (cuuint32_t)box_pix, (cuuint32_t)box_chunks, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return HV_ERR_CUDA; }
+  return HV_OK;
+}
+
+// ------------------------------------------------------------------------------------------- host: setup
+int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images) {
+  HV_CHECK_ARG(nsrc >= 1 && nsrc <= 2, "tc_conv: 1 or 2 sources supported");
+  HV_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || (stride == 2 && k == 3 && dil == 1)), "tc_conv: unsupported k/stride");
+  memset(&c.p, 0, sizeof(c.p));
+  c.k = k; c.stride = stride; c.dil = dil; c.nsrc = nsrc; c.cout_real = cout_real;
+  for (int i = 0; i < nsrc; ++i) c.src[i] = srcs[i];
+  c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
+  HV_CHECK_ARG(cout_real <= 64, "tc_conv: cout <= 64");
+  const TcBuf& b0 = srcs[0].buf;
+  const int half = (k - 1) / 2;
+  for (int i = 0; i < nsrc; ++i) {
+    const TcBuf& b = srcs[i].buf;
+    HV_CHECK_ARG(b.ptr && (b.chunks % 2) == 0, "tc_conv: source %d needs an even number of channel chunks", i);
+    HV_CHECK_ARG(b.h == b0.h && b.w == b0.w && b.border == b0.border && b.n == b0.n, "tc_conv: concat sources must share geometry");
+    HV_CHECK_ARG(b.border >= half * dil, "tc_conv: source border %d < conv padding %d", b.border, half * dil);
+    HV_CHECK_ARG(srcs[i].real_channels <= b.chunks * 8, "tc_conv: real_channels > buffer channels");
+  }
+  HV_CHECK_ARG(b0.n == n_images, "tc_conv: batch mismatch");
+  TcParams& p = c.p;
+  p.stride = stride;
+  p.in_pitch = b0.pitch(); p.in_border = b0.border;
+  int seg = 0, tap = 0, woff = 0;
+  uint32_t max_seg_bytes = 0;
+  if (stride == 1) {
+    p.h_out = b0.h; p.w_out = b0.w;
+    p.q_first = b0.border * b0.pitch() + b0.border;
+    const int span = b0.h * b0.pitch();  // positions from (0,0) to the end of the last row (incl. side borders)
+    p.tiles_per_image = (span + TC_TILE_M - 1) / TC_TILE_M;
+    for (int s = 0; s < nsrc; ++s)
+      for (int ky = 0; ky < k; ++ky) {
+        HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
+        TcSeg& sg = p.segs[seg];
+        sg.map = s; sg.parity = 0; sg.nchunks = srcs[s].buf.chunks;
+        sg.rel_start = (ky - half) * dil * b0.pitch() - half * dil;
+        sg.npix = TC_TILE_M + 2 * half * dil;
+        sg.tap_begin = tap;
+        for (int kx = 0; kx < k; ++kx) {
+          HV_CHECK_ARG(tap < TC_MAX_TAPS, "tc_conv: too many taps");
+          p.taps[tap].pix_off = kx * dil;
+          p.taps[tap].w_off = woff;
+          woff += sg.nchunks * c.n_pad * 16;
+          ++tap;
+        }
+        sg.tap_end = tap;
+        max_seg_bytes = max(max_seg_bytes, (uint32_t)sg.npix * sg.nchunks * 16u);
+        ++seg;
+      }
+  } else {
+    p.h_out = b0.h / 2; p.w_out = b0.w / 2;
+    p.q_first = 0;
+    const int span = p.h_out * b0.pitch();
+    p.tiles_per_image = (span + TC_TILE_M - 1) / TC_TILE_M;
+    const int B = b0.border;
+    for (int s = 0; s < nsrc; ++s)
+      for (int ky = 0; ky < 3; ++ky)
+        for (int par = 0; par < 2; ++par) {
+          // input position of output o, tap (ky,kx): 2*o + r, r = (ky-1+B)*pitch + (kx-1+B)
+          int dmin = 1 << 30, dmax = -1, cnt = 0;
+          for (int kx = 0; kx < 3; ++kx) {
+            const int r = (ky - 1 + B) * b0.pitch() + (kx - 1 + B);
+            if ((r & 1) != par) continue;
+            dmin = min(dmin, r >> 1); dmax = max(dmax, r >> 1); ++cnt;
+          }
+          if (!cnt) continue;
+          HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
+          TcSeg& sg = p.segs[seg];
+          sg.map = s; sg.parity = par; sg.nchunks = srcs[s].buf.chunks;
+          sg.rel_start = dmin; sg.npix = TC_TILE_M + (dmax - dmin);
+          sg.tap_begin = tap;
+          for (int kx = 0; kx < 3; ++kx) {
+            const int r = (ky - 1 + B) * b0.pitch() + (kx - 1 + B);
+            if ((r & 1) != par) continue;
+            p.taps[tap].pix_off = (r >> 1) - dmin;
+            // weights are packed in (source, ky, kx) order independent of the segment order
+            p.taps[tap].w_off = ((s * 3 + ky) * 3 + kx) * sg.nchunks * c.n_pad * 16;
+            ++tap;
+          }
+          sg.tap_end = tap;
+          max_seg_bytes = max(max_seg_bytes, (uint32_t)sg.npix * sg.nchunks * 16u);
+          ++seg;
+        }
+    woff = 0;
+    for (int s = 0; s < nsrc; ++s) woff += 9 * srcs[s].buf.chunks * c.n_pad * 16;
+    HV_CHECK_ARG(nsrc == 1, "tc_conv: stride-2 layers take a single source");
+  }
+  p.nseg = seg; p.ntap = tap;
+  p.w_bytes = (uint32_t)woff;
+  p.total_tiles = p.tiles_per_image * n_images;
+  p.slot_bytes = (max_seg_bytes + 127u) & ~127u;
+  const size_t budget = 227 * 1024 - 1024;
+  const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 256;
+  HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
+  int nslots = (int)((budget - fixed) / p.slot_bytes);
+  nslots = min(nslots, max(2 * seg, 4));
+  nslots = min(nslots, 12);
+  p.nslots = nslots;
+  c.smem = fixed + (size_t)nslots * p.slot_bytes;
+  for (int s = 0; s < nsrc; ++s) {
+    int npix = 0;
+    for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) npix = max(npix, p.segs[i].npix);
+    // every segment of a source uses the same box; shorter (parity) segments are padded to the longest
+    for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) p.segs[i].npix = npix;
+    int rc = make_map(&p.maps[s], srcs[s].buf, stride, npix, srcs[s].buf.chunks);
+    if (rc) return rc;
+  }
+  if (nsrc == 1) p.maps[1] = p.maps[0];
+  HV_CUDA(cudaMalloc(&c.w_packed, p.w_bytes));
+  HV_CUDA(cudaMalloc(&c.bias_pad, c.n_pad * sizeof(float)));
+  p.w_packed = c.w_packed;
+  p.bias = c.bias_pad;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  c.grid = min(p.total_tiles, sms);
+  return HV_OK;
+}
+
+void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act) {
+  TcParams& p = c.p;
+  p.out_mode = up2 ? TC_OUT_CHUNKED_UP2 : TC_OUT_CHUNKED;
+  p.out = out.ptr; p.out_pitch = out.pitch(); p.out_border = out.border; p.out_plane = out.plane();
+  p.out_chunks_total = out.chunks; p.out_chunk_off = chunk_off; p.out_nchunks = nchunks;
+  p.act = act;
+}
+
+void tc_conv_set_output_heads(TcConv& c, float* head0, float* head1, const TcAux* aux0, const TcAux* aux1) {
+  TcParams& p = c.p;
+  p.out_mode = TC_OUT_HEADS;
+  p.head0 = head0; p.head1 = head1;
+  memset(&p.aux0, 0, sizeof(TcAux)); memset(&p.aux1, 0, sizeof(TcAux));
+  if (aux0) p.aux0 = *aux0;
+  if (aux1) p.aux1 = *aux1;
+}
+
+void tc_conv_free(TcConv& c) {
+  cudaFree(c.w_packed); cudaFree(c.bias_pad);
+  c.w_packed = nullptr; c.bias_pad = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------- weight packing
+// dst[(tap entry e = (source, ky, kx))][chunk][n_pad][8] bf16; padded channels / filters are zero.
+struct PackSrc { int ch_off, real, chunks; };
+__global__ void pack_weights_kernel(const float* __restrict__ wa, const float* __restrict__ ba, int cout_a,
+                                    const float* __restrict__ wb, const float* __restrict__ bb, int cout_b, int cin_total,
+                                    int k, int n_pad, PackSrc s0, PackSrc s1, int nsrc, __nv_bfloat16* __restrict__ dst,
+                                    float* __restrict__ bias_pad, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_pad) {
+    float b = 0.f;
+    if (i < cout_a) b = ba ? ba[i] : 0.f;
+    else if (i < cout_a + cout_b) b = bb ? bb[i - cout_a] : 0.f;
+    bias_pad[i] = b;
+  }
+  if (i >= total) return;
+  const int kk = k * k;
+  int rem = i;
+  const int c8 = rem & 7; rem >>= 3;
+  const int n = rem % n_pad; rem /= n_pad;
+  // rem = linear (entry, chunk) index with per-source chunk counts
+  const int per0 = kk * s0.chunks;
+  PackSrc s = s0;
+  if (rem >= per0) { rem -= per0; s = s1; }
+  const int chunk = rem % s.chunks, tap = rem / s.chunks;
+  const int ch = chunk * 8 + c8;
+  float v = 0.f;
+  if (ch < s.real) {
+    const int cin = s.ch_off + ch;
+    if (n < cout_a) v = wa[((size_t)n * cin_total + cin) * kk + tap];
+    else if (n < cout_a + cout_b) v = wb[((size_t)(n - cout_a) * cin_total + cin) * kk + tap];
+  }
+  dst[i] = __float2bfloat16(v);
+}
+
+int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a, const float* wb, const float* bb,
+                         int cout_b, cudaStream_t st) {
+  HV_CHECK_ARG(cout_a + cout_b == c.cout_real, "tc_conv_pack_weights: filter count mismatch");
+  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks}, s1{0, 0, 1};
+  int cin_total = c.src[0].real_channels;
+  if (c.nsrc == 2) { s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks}; cin_total += c.src[1].real_channels; }
+  const int total = (int)(c.p.w_bytes / 2);
+  pack_weights_kernel<<<(max(total, c.n_pad) + 255) / 256, 256, 0, st>>>(wa, ba, cout_a, wb, bb, cout_b, cin_total, c.k, c.n_pad, s0,
+                                                                          s1, c.nsrc, (__nv_bfloat16*)c.w_packed, c.bias_pad, total);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+template <int N_PAD>
+static int tc_launch_n(const TcConv& c, cudaStream_t st) {
+  static bool configured = false;  // per instantiation; the attribute is sticky for the process
+  if (!configured) {
+    HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  conv_tc_kernel<N_PAD><<<c.grid, TC_THREADS, c.smem, st>>>(c.p);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+int tc_conv_launch(const TcConv& c, cudaStream_t st) {
+  switch (c.n_pad) {
+    case 16: return tc_launch_n<16>(c, st);
+    case 32: return tc_launch_n<32>(c, st);
+    case 64: return tc_launch_n<64>(c, st);
+    default: set_error("tc_conv: bad n_pad %d", c.n_pad); return HV_ERR_INVALID;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- layout converters
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels, int mode, __nv_bfloat16* __restrict__ dst,
+                                 int chunks, int h, int w, int border, int pitch, int plane, int ch0) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w;
+  float v;
+  if (mode == HV_SRC_SCALAR) v = src[n];
+  else if (mode == HV_SRC_SUB2) v = src[(((size_t)n * src_channels + c) * (2 * h) + 2 * y) * (2 * w) + 2 * x];
+  else if (mode == HV_SRC_UP2) v = src[(((size_t)n * src_channels + c) * (h / 2) + y / 2) * (w / 2) + x / 2];
+  else v = src[(((size_t)n * src_channels + c) * h + y) * w + x];
+  const int ch = ch0 + c;
+  dst[(((size_t)n * chunks + (ch >> 3)) * plane + (size_t)(y + border) * pitch + x + border) * 8 + (ch & 7)] = __float2bfloat16(v);
+}
+
+int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst, int ch0, cudaStream_t st) {
+  HV_CHECK_ARG(src && dst.ptr && ch0 + src_channels <= dst.chunks * 8, "tc_pack_nchw: bad argument");
+  dim3 grid((dst.h * dst.w + 255) / 256, src_channels, dst.n);
+  pack_nchw_kernel<<<grid, 256, 0, st>>>(src, src_channels, mode, dst.ptr, dst.chunks, dst.h, dst.w, dst.border, dst.pitch(),
+                                         dst.plane(), ch0);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+__global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, int chunks, int h, int w, int border, int pitch,
+                                   int plane, int ch0, int channels, float* __restrict__ dst) {
+  const int n = blockIdx.z, c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w, ch = ch0 + c;
+  dst[((size_t)n * channels + c) * h * w + i] =
+      __bfloat162float(src[(((size_t)n * chunks + (ch >> 3)) * plane + (size_t)(y + border) * pitch + x + border) * 8 + (ch & 7)]);
+}
+
+int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st) {
+  HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8, "tc_unpack_nchw: bad argument");
+  dim3 grid((src.h * src.w + 255) / 256, channels, src.n);
+  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src.ptr, src.chunks, src.h, src.w, src.border, src.pitch(), src.plane(), ch0, channels, dst);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+// SHRM height head on a chunked buffer: sigmoid(fc(mean_HW(x)))  (inpaint_networks.py:90-93,:211-214)
+__global__ void __launch_bounds__(256) tc_gap_fc_kernel(const __nv_bfloat16* __restrict__ x, int chunks, int h, int w, int border,
+                                                        int pitch, int plane, const float* __restrict__ fw,
+                                                        const float* __restrict__ fb, float* __restrict__ out) {
+  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __shared__ float red[8];
+  float dot = 0.f;
+  for (int c = warp; c < chunks; c += nw) {
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __nv_bfloat16* pl = x + ((size_t)n * chunks + c) * plane * 8;
+    for (int i = lane; i < h * w; i += 32) {
+      const int y = i / w, xx = i - y * w;
+      const uint4 raw = *reinterpret_cast<const uint4*>(pl + ((size_t)(y + border) * pitch + xx + border) * 8);
+      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(hp[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dot += (warp_sum(acc[j]) / (float)(h * w)) * fw[c * 8 + j];
+  }
+  if (lane == 0) red[warp] = dot;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < nw; ++i) t += red[i];
+    out[n] = 1.f / (1.f + expf(-(t + fb[0])));
+  }
+}
+
+int tc_gap_fc_sigmoid(const TcBuf& x, const float* fw, const float* fb, float* out, cudaStream_t st) {
+  HV_CHECK_ARG(x.ptr && fw && fb && out, "tc_gap_fc_sigmoid: null argument");
+  tc_gap_fc_kernel<<<x.n, 256, 0, st>>>(x.ptr, x.chunks, x.h, x.w, x.border, x.pitch(), x.plane(), fw, fb, out);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+}  // namespace hv

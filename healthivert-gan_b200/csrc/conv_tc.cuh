@@ -1,0 +1,113 @@
+// bf16 tensor-core convolution path (tcgen05 + TMEM + TMA): shared declarations.
+//
+// Activation layout ("chunked"): [n][chunk = channel/8][plane position][8 channels] bf16, where a
+// plane is the zero-bordered image flattened row-major: position = (y + border) * pitch + (x + border),
+// pitch = w + 2*border.  With this layout
+//   * a run of consecutive positions of one chunk is contiguous (16 B per position), so TMA brings a
+//     [chunks][positions][8] box straight into the canonical no-swizzle K-major UMMA operand layout;
+//   * a conv tap is a constant shift of the flattened position, so every tap of a band reads the SAME
+//     shared-memory tile through a shifted start address (no per-tap reload from L2);
+//   * the epilogue stores 32 consecutive positions x 16 B = 512 contiguous bytes per warp instruction.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hv {
+
+struct TcBuf {
+  __nv_bfloat16* ptr = nullptr;
+  int n = 0, chunks = 0, h = 0, w = 0, border = 0;
+  int pitch() const { return w + 2 * border; }
+  int rows() const { return h + 2 * border; }
+  int plane() const { return (pitch() * rows() + 1) & ~1; }  // even, for the stride-2 parity view
+  size_t elems() const { return (size_t)n * chunks * plane() * 8; }
+  size_t bytes() const { return elems() * sizeof(__nv_bfloat16); }
+};
+
+constexpr int TC_MAX_SEGS = 10;
+constexpr int TC_MAX_TAPS = 50;
+constexpr int TC_TILE_M = 128;
+
+struct TcSeg {
+  int map;        // which tensor map (source)
+  int rel_start;  // start position relative to the tile origin
+  int npix;       // positions in the box
+  int parity;     // stride-2 parity plane (0/1); unused for stride 1
+  int nchunks;    // channel chunks of this source
+  int tap_begin, tap_end;
+};
+
+struct TcTap {
+  int pix_off;   // shift (positions) inside the segment tile
+  int w_off;     // byte offset of this tap's weight slab [chunk][n_pad][8] in shared memory
+};
+
+enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2 };
+
+struct TcAux {  // optional bf16 side output of a head: one channel of a chunked buffer
+  __nv_bfloat16* ptr;
+  int chunks, chunk, channel, pitch, border, plane;
+};
+
+struct TcParams {
+  CUtensorMap maps[2];
+  TcSeg segs[TC_MAX_SEGS];
+  TcTap taps[TC_MAX_TAPS];
+  int nseg, ntap;
+  const void* w_packed;
+  uint32_t w_bytes;
+  const float* bias;  // [n_pad]
+  int stride;
+  int tiles_per_image, total_tiles;
+  int in_pitch, in_border, q_first;
+  int h_out, w_out;
+  int act;
+  int out_mode;
+  __nv_bfloat16* out;
+  int out_pitch, out_border, out_plane, out_chunks_total, out_chunk_off, out_nchunks;
+  float* head0;
+  float* head1;
+  TcAux aux0, aux1;
+  uint32_t slot_bytes;
+  int nslots;
+};
+
+struct TcSource {
+  TcBuf buf;
+  int real_channels;  // channels of this source that carry weights (<= buf.chunks*8)
+};
+
+struct TcConv {
+  TcParams p;
+  int n_pad = 0;
+  int grid = 0;
+  size_t smem = 0;
+  void* w_packed = nullptr;   // owned
+  float* bias_pad = nullptr;  // owned
+  int k = 0, stride = 1, dil = 1;
+  int nsrc = 0;
+  TcSource src[2];
+  int cout_real = 0;
+};
+
+// geometry + tensor maps + tables; allocates the packed-weight / bias buffers
+int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real,
+                  int n_images);
+// w_eff_a: [cout_a][cin_total][k][k] fp32 effective weights (cin_total = sum real_channels);
+// w_eff_b (heads only): second filter bank stacked after the first along cout
+int tc_conv_pack_weights(TcConv& c, const float* w_eff_a, const float* bias_a, int cout_a, const float* w_eff_b,
+                         const float* bias_b, int cout_b, cudaStream_t st);
+void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act);
+void tc_conv_set_output_heads(TcConv& c, float* head0, float* head1, const TcAux* aux0, const TcAux* aux1);
+int tc_conv_launch(const TcConv& c, cudaStream_t st);
+void tc_conv_free(TcConv& c);
+
+// fp32 NCHW <-> chunked bf16 converters (channel c of the source lands in chunk c/8, lane c%8)
+int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, const TcBuf& dst, int dst_channel0,
+                 cudaStream_t st);
+int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st);
+int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, cudaStream_t st);
+
+}  // namespace hv

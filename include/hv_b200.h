@@ -78,6 +78,14 @@ typedef struct hv_conv_desc {
 int hv_conv2d_fwd(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2,
                   hv_stream_t stream);
 
+/* bf16 tensor-core variant of hv_conv2d_fwd (tcgen05.mma, fp32 accumulate in TMEM): same
+ * descriptor and fp32 NCHW tensors; inputs and weights are rounded to bf16, the output is rounded to
+ * bf16 (heads: fp32).  k in {3,5}, 'same' padding, stride 1 or (k=3) 2, cout <= 64.
+ * up2_out != 0 additionally applies the nearest x2 upsample of the NEXT layer to the stored
+ * result (y is [n,cout,2*hout,2*wout]).                                                        */
+int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2,
+                   int up2_out, hv_stream_t stream);
+
 /* replaces global_pool + fc_height + sigmoid (models/inpaint_networks.py:90-93,:211-214) */
 int hv_gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* out,
                       int n, int c, int hw, hv_stream_t stream);
