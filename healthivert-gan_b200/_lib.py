@@ -57,6 +57,7 @@ SIGNATURES = {
     "hv_generator_set_fc": (c_int, [c_void_p, c_int, c_void_p, c_void_p]),
     "hv_generator_prepare": (c_int, [c_void_p, c_int, c_void_p]),
     "hv_generator_forward": (c_int, [c_void_p] + [c_void_p] * 4 + [c_int] + [c_void_p] * 8 + [c_int, c_void_p]),
+    "hv_generator_run_layer": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "hv_generator_read_tap": (c_longlong, [c_void_p, c_int, c_void_p, c_void_p]),
 }
 

@@ -10,6 +10,7 @@
 #include <vector>
 #include "hv_common.cuh"
 #include "kernels.h"
+#include "conv_tc.cuh"
 
 namespace hv {
 
@@ -82,6 +83,8 @@ enum {
 
 using namespace hv;
 
+namespace hv { struct TcPlan; }
+
 struct hv_generator {
   int max_batch = 0, precision = 0;
   bool prepared = false;
@@ -105,6 +108,7 @@ struct hv_generator {
   const float* last_heads[4] = {};  // x_stage1, coarse_seg, x_stage2, fine_seg of the last forward
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  struct hv::TcPlan* tc = nullptr;  // bf16 tensor-core plan (precision == HV_PREC_BF16)
 };
 
 namespace hv {
@@ -197,6 +201,198 @@ static int forward_fp32(hv_generator* g, const float* x, const float* mask, cons
 
 }  // namespace hv
 
+// =============================================================================== bf16 tensor-core plan
+namespace hv {
+
+// chunked bf16 activation buffers of the plan (channels, extent, zero border = padding of the consumer)
+enum BufId {
+  B_IN_C, B_C1, B_C2, B_C3, B_C4, B_C5, B_C6, B_C7, B_C8, B_C9, B_C10, B_C11, B_C12U, B_CAM128, B_C20, B_C13, B_C14U,
+  B_CAM256, B_C19, B_C15, B_C16,
+  B_IN_F, B_F1, B_F2, B_F3, B_F4, B_F5, B_F6, B_F7, B_F8, B_F9, B_F10,
+  B_P1, B_P2, B_P3, B_P4, B_P5, B_P6, B_CA, B_P9, B_P10,
+  B_A11, B_A12, B_A19U, B_A13, B_A14U, B_A15, B_A16CAT, B_COUNT
+};
+struct BufSpec { int channels, extent, border; };
+static const BufSpec kBufs[B_COUNT] = {
+    {16, 256, 2}, {16, 256, 1}, {32, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
+    {64, 64, 8}, {64, 64, 16}, {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {16, 128, 1}, {64, 128, 1}, {32, 128, 1},
+    {32, 256, 1}, {16, 256, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
+    {16, 256, 2}, {16, 256, 1}, {16, 128, 1}, {32, 128, 1}, {32, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
+    {64, 64, 8}, {64, 64, 16}, {64, 64, 1},
+    {16, 256, 1}, {16, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1},
+    {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {32, 128, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
+};
+
+// layer -> (sources, output).  real = channels of the source that carry weights.
+struct TcLayerSpec { int layer; int src0, real0, src1, real1; int out; bool up2; int out_chunks; };
+static const TcLayerSpec kTcLayers[] = {
+    {C1, B_IN_C, 3, -1, 0, B_C1, false, 2},     {C2, B_C1, 16, -1, 0, B_C2, false, 4},
+    {C3, B_C2, 32, -1, 0, B_C3, false, 4},      {C4, B_C3, 32, -1, 0, B_C4, false, 8},
+    {C5, B_C4, 64, -1, 0, B_C5, false, 8},      {C6, B_C5, 64, -1, 0, B_C6, false, 8},
+    {C7, B_C6, 64, -1, 0, B_C7, false, 8},      {C8, B_C7, 64, -1, 0, B_C8, false, 8},
+    {C9, B_C8, 64, -1, 0, B_C9, false, 8},      {C10, B_C9, 64, -1, 0, B_C10, false, 8},
+    {C11, B_C10, 64, -1, 0, B_C11, false, 8},   {C12, B_C11, 64, -1, 0, B_C12U, true, 8},
+    {C20, B_C12U, 64, B_CAM128, 1, B_C20, false, 8}, {C13, B_C20, 64, -1, 0, B_C13, false, 4},
+    {C14, B_C13, 32, -1, 0, B_C14U, true, 4},   {C19, B_C14U, 32, B_CAM256, 1, B_C19, false, 4},
+    {C15, B_C19, 32, -1, 0, B_C15, false, 2},   {C16, B_C15, 16, -1, 0, B_C16, false, 2},
+    {C17, B_C16, 8, -1, 0, -1, false, 0},       // heads conv17 + conv18
+    {F1, B_IN_F, 4, -1, 0, B_F1, false, 2},     {F2, B_F1, 16, -1, 0, B_F2, false, 2},
+    {F3, B_F2, 16, -1, 0, B_F3, false, 4},      {F4, B_F3, 32, -1, 0, B_F4, false, 4},
+    {F5, B_F4, 32, -1, 0, B_F5, false, 8},      {F6, B_F5, 64, -1, 0, B_F6, false, 8},
+    {F7, B_F6, 64, -1, 0, B_F7, false, 8},      {F8, B_F7, 64, -1, 0, B_F8, false, 8},
+    {F9, B_F8, 64, -1, 0, B_F9, false, 8},      {F10, B_F9, 64, -1, 0, B_F10, false, 8},
+    {PM1, B_IN_F, 4, -1, 0, B_P1, false, 2},    {PM2, B_P1, 16, -1, 0, B_P2, false, 2},
+    {PM3, B_P2, 16, -1, 0, B_P3, false, 4},     {PM4, B_P3, 32, -1, 0, B_P4, false, 8},
+    {PM5, B_P4, 64, -1, 0, B_P5, false, 8},     {PM6, B_P5, 64, -1, 0, B_P6, false, 8},
+    {PM9, B_CA, 64, -1, 0, B_P9, false, 8},     {PM10, B_P9, 64, -1, 0, B_P10, false, 8},
+    {A11, B_F10, 64, B_P10, 64, B_A11, false, 8}, {A12, B_A11, 64, -1, 0, B_A12, false, 8},
+    {A19, B_A12, 64, -1, 0, B_A19U, true, 8},   {A13, B_A19U, 64, -1, 0, B_A13, false, 4},
+    {A14, B_A13, 32, -1, 0, B_A14U, true, 4},   {A15, B_A14U, 32, -1, 0, B_A15, false, 2},
+    {A16, B_A15, 16, -1, 0, B_A16CAT, false, 1}, // writes chunk 0 only; chunk 1 holds x_stage1
+    {A17, B_A16CAT, 9, -1, 0, -1, false, 0},    // heads allconv17 + allconv18
+};
+constexpr int kNumTcLayers = sizeof(kTcLayers) / sizeof(kTcLayers[0]);
+
+struct TcPlan {
+  TcBuf buf[B_COUNT];
+  TcConv conv[kNumLayers];   // indexed by layer id (heads: C17 / A17 entries only)
+  bool has[kNumLayers] = {};
+  int out_buf[kNumLayers];
+  bool out_up2[kNumLayers] = {};
+  float* pm6_f32 = nullptr;  // attention bridge (fp32 NCHW)
+  __nv_bfloat16* blob = nullptr;
+};
+
+static TcAux make_aux(const TcBuf& b, int channel) {
+  TcAux a;
+  a.ptr = b.ptr; a.chunks = b.chunks; a.chunk = channel >> 3; a.channel = channel & 7;
+  a.pitch = b.pitch(); a.border = b.border; a.plane = b.plane();
+  return a;
+}
+
+static void tc_plan_destroy(hv_generator* g) {
+  if (!g->tc) return;
+  for (int i = 0; i < kNumLayers; ++i) if (g->tc->has[i]) tc_conv_free(g->tc->conv[i]);
+  cudaFree(g->tc->blob); cudaFree(g->tc->pm6_f32);
+  delete g->tc;
+  g->tc = nullptr;
+}
+
+static int tc_plan_create(hv_generator* g) {
+  TcPlan* t = new TcPlan();
+  g->tc = t;
+  const int n = g->max_batch;
+  size_t total = 0;
+  for (int i = 0; i < B_COUNT; ++i) {
+    TcBuf& b = t->buf[i];
+    b.n = n; b.chunks = kBufs[i].channels / 8; b.h = b.w = kBufs[i].extent; b.border = kBufs[i].border;
+    total += (b.bytes() + 255) & ~(size_t)255;
+  }
+  HV_CUDA(cudaMalloc((void**)&t->blob, total));
+  HV_CUDA(cudaMemset(t->blob, 0, total));  // zero borders and padding channels, once
+  size_t off = 0;
+  for (int i = 0; i < B_COUNT; ++i) {
+    t->buf[i].ptr = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(t->blob) + off);
+    off += (t->buf[i].bytes() + 255) & ~(size_t)255;
+  }
+  HV_CUDA(cudaMalloc((void**)&t->pm6_f32, (size_t)n * 64 * 64 * 64 * sizeof(float)));
+  for (int i = 0; i < kNumLayers; ++i) t->out_buf[i] = -1;
+  for (int i = 0; i < kNumTcLayers; ++i) {
+    const TcLayerSpec& s = kTcLayers[i];
+    const LayerSpec& L = kLayers[s.layer];
+    TcSource srcs[2];
+    srcs[0].buf = t->buf[s.src0]; srcs[0].real_channels = s.real0;
+    int nsrc = 1;
+    if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; nsrc = 2; }
+    const bool heads = s.out < 0;
+    TcConv& c = t->conv[s.layer];
+    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, heads ? 2 : L.cout, n);
+    if (rc) return rc;
+    t->has[s.layer] = true;
+    if (heads) {
+      TcAux a0 = make_aux(t->buf[B_A16CAT], 8), a1 = make_aux(t->buf[B_IN_F], 1);
+      tc_conv_set_output_heads(c, nullptr, nullptr, s.layer == C17 ? &a0 : nullptr, s.layer == C17 ? &a1 : nullptr);
+    } else {
+      tc_conv_set_output_chunked(c, t->buf[s.out], 0, s.out_chunks, s.up2, L.act);
+      t->out_buf[s.layer] = s.out; t->out_up2[s.layer] = s.up2;
+    }
+  }
+  return HV_OK;
+}
+
+// batch-size dependent fields (the plan is sized for max_batch; a smaller batch runs fewer tiles)
+static void tc_set_batch(TcConv& c, int n) {
+  c.p.total_tiles = c.p.tiles_per_image * n;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  c.grid = c.p.total_tiles < sms ? c.p.total_tiles : sms;
+}
+
+static int tc_plan_pack_weights(hv_generator* g, cudaStream_t st) {
+  TcPlan* t = g->tc;
+  for (int i = 0; i < kNumTcLayers; ++i) {
+    const int l = kTcLayers[i].layer;
+    int rc;
+    if (kTcLayers[i].out < 0)  // heads: conv17|conv18 and allconv17|allconv18 are adjacent layer ids
+      rc = tc_conv_pack_weights(t->conv[l], g->w_eff[l], g->bias[l], 1, g->w_eff[l + 1], g->bias[l + 1], 1, st);
+    else
+      rc = tc_conv_pack_weights(t->conv[l], g->w_eff[l], g->bias[l], kLayers[l].cout, nullptr, nullptr, 0, st);
+    if (rc) return rc;
+  }
+  return HV_OK;
+}
+
+static int forward_bf16(hv_generator* g, const float* x, const float* mask, const float* cam, const float* ratio, int n,
+                        float* coarse_seg, float* fine_seg, float* x_stage1, float* x_stage2, float* flow, float* pred1_h,
+                        float* pred2_h, int32_t* offsets, int per_sample_mask, cudaStream_t st) {
+  TcPlan* t = g->tc;
+  auto view = [&](int id) { TcBuf b = t->buf[id]; b.n = n; return b; };
+  auto run = [&](int layer, cudaStream_t s) -> int {
+    TcConv& c = t->conv[layer];
+    tc_set_batch(c, n);
+    return tc_conv_launch(c, s);
+  };
+  // ---- pack the fp32 NCHW inputs into the chunked bf16 input buffers (torch.cat of :77 / :179)
+  RC(tc_pack_nchw(x, 1, HV_SRC_DIRECT, view(B_IN_C), 0, st));
+  RC(tc_pack_nchw(ratio, 1, HV_SRC_SCALAR, view(B_IN_C), 1, st));
+  RC(tc_pack_nchw(mask, 1, HV_SRC_DIRECT, view(B_IN_C), 2, st));
+  RC(tc_pack_nchw(x, 1, HV_SRC_DIRECT, view(B_IN_F), 0, st));
+  RC(tc_pack_nchw(mask, 1, HV_SRC_DIRECT, view(B_IN_F), 2, st));
+  RC(tc_pack_nchw(ratio, 1, HV_SRC_SCALAR, view(B_IN_F), 3, st));
+  RC(tc_pack_nchw(cam, 1, HV_SRC_SUB2, view(B_CAM128), 0, st));
+  RC(tc_pack_nchw(cam, 1, HV_SRC_DIRECT, view(B_CAM256), 0, st));
+  // ---- coarse network
+  for (int l : {C1, C2, C3, C4, C5, C6, C7, C8, C9, C10}) RC(run(l, st));
+  RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, st));
+  for (int l : {C11, C12, C20, C13, C14, C19, C15, C16}) RC(run(l, st));
+  t->conv[C17].p.head0 = x_stage1; t->conv[C17].p.head1 = coarse_seg;
+  RC(run(C17, st));
+  // ---- fine network: attention branch on the side stream
+  HV_CUDA(cudaEventRecord(g->ev_fork, st));
+  HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
+  cudaStream_t sa = g->side;
+  for (int l : {PM1, PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
+  RC(tc_unpack_nchw(view(B_P6), 0, 64, t->pm6_f32, sa));
+  RC(ctx_attn_fwd_fp32(t->pm6_f32, mask, g->ca_out, offsets, flow, n, 64, 64, 64, 10.f, 1, per_sample_mask, g->ca_ws, sa));
+  RC(tc_pack_nchw(g->ca_out, 64, HV_SRC_DIRECT, view(B_CA), 0, sa));
+  RC(run(PM9, sa));
+  RC(run(PM10, sa));
+  HV_CUDA(cudaEventRecord(g->ev_join, sa));
+  for (int l : {F1, F2, F3, F4, F5, F6, F7, F8, F9, F10}) RC(run(l, st));
+  HV_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
+  RC(run(A11, st));
+  RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, st));
+  for (int l : {A12, A19, A13, A14, A15, A16}) RC(run(l, st));
+  t->conv[A17].p.head0 = x_stage2; t->conv[A17].p.head1 = fine_seg;
+  RC(run(A17, st));
+  g->last_heads[0] = x_stage1; g->last_heads[1] = coarse_seg; g->last_heads[2] = x_stage2; g->last_heads[3] = fine_seg;
+  g->last_n = n;
+  return HV_OK;
+}
+
+}  // namespace hv
+
 // =============================================================================== C ABI
 extern "C" {
 
@@ -219,6 +415,7 @@ int hv_generator_layer_info(int idx, char* name_out, int* cin, int* cout, int* k
 
 int hv_generator_destroy(hv_generator* g) {
   if (!g) return HV_OK;
+  tc_plan_destroy(g);
   for (int i = 0; i < kNumLayers; ++i) cudaFree(g->act[i]);
   cudaFree(g->ca_out); cudaFree(g->ca_ws); cudaFree(g->sigma); cudaFree(g->d_jobs);
   cudaFree(g->blob_w); cudaFree(g->blob_b);
@@ -233,10 +430,6 @@ int hv_generator_create(hv_generator** out, int max_batch, int precision) {
   HV_CHECK_ARG(out, "generator_create: null out pointer");
   HV_CHECK_ARG(max_batch >= 1 && max_batch <= 4096, "generator_create: max_batch %d out of range", max_batch);
   HV_CHECK_ARG(precision == HV_PREC_FP32 || precision == HV_PREC_BF16, "generator_create: bad precision %d", precision);
-  if (precision == HV_PREC_BF16) {
-    set_error("generator_create: bf16 tensor-core plan not built in this library version");
-    return HV_ERR_UNSUPPORTED;
-  }
   int ndev = 0;
   HV_CUDA(cudaGetDeviceCount(&ndev));
   hv_generator* g = new hv_generator();
@@ -253,6 +446,7 @@ int hv_generator_create(hv_generator** out, int max_batch, int precision) {
     g->w_eff[i] = g->blob_w + wo; g->bias[i] = g->blob_b + bo;
     wo += (size_t)kLayers[i].cout * kLayers[i].cin * kLayers[i].k * kLayers[i].k; bo += kLayers[i].cout;
     if (i == C17 || i == C18 || i == A17 || i == A18) continue;  // heads write straight to the outputs
+    if (precision == HV_PREC_BF16) continue;                     // bf16 plan keeps chunked bf16 activations
     GEN_TRY(cudaMalloc(&g->act[i], act_elems(i, max_batch) * sizeof(float)));
   }
   GEN_TRY(cudaMalloc(&g->ca_out, (size_t)max_batch * 64 * 64 * 64 * sizeof(float)));
@@ -261,6 +455,10 @@ int hv_generator_create(hv_generator** out, int max_batch, int precision) {
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
 #undef GEN_TRY
+  if (precision == HV_PREC_BF16) {
+    int rc = tc_plan_create(g);
+    if (rc) { hv_generator_destroy(g); return rc; }
+  }
   *out = g;
   return HV_OK;
 }
@@ -295,6 +493,10 @@ int hv_generator_prepare(hv_generator* g, int training, hv_stream_t stream) {
   HV_CUDA(cudaMemcpyAsync(g->d_jobs, jobs.data(), sizeof(SnJob) * kNumLayers, cudaMemcpyHostToDevice, st));
   int rc = sn_prepare_batched(g->d_jobs, kNumLayers, training, st);
   if (rc) return rc;
+  if (g->tc) {
+    rc = tc_plan_pack_weights(g, st);
+    if (rc) return rc;
+  }
   g->prepared = true;
   return HV_OK;
 }
@@ -307,8 +509,21 @@ int hv_generator_forward(hv_generator* g, const float* x, const float* mask, con
   HV_CHECK_ARG(n >= 1 && n <= g->max_batch, "generator_forward: batch %d outside 1..%d", n, g->max_batch);
   HV_CHECK_ARG(x && mask && cam && ratio && coarse_seg && fine_seg && x_stage1 && x_stage2 && pred1_h && pred2_h,
                "generator_forward: null tensor pointer");
+  if (g->tc)
+    return forward_bf16(g, x, mask, cam, ratio, n, coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h,
+                        offsets, per_sample_mask, as_stream(stream));
   return forward_fp32(g, x, mask, cam, ratio, n, coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h,
                       offsets, per_sample_mask, as_stream(stream));
+}
+
+int hv_generator_run_layer(hv_generator* g, int idx, int n, hv_stream_t stream) {
+  HV_CHECK_ARG(g && g->tc, "generator_run_layer: needs a bf16 plan");
+  if (!g->prepared) { set_error("generator_run_layer: call hv_generator_prepare first"); return HV_ERR_STATE; }
+  HV_CHECK_ARG(idx >= 0 && idx < kNumLayers && g->tc->has[idx] && g->tc->out_buf[idx] >= 0,
+               "generator_run_layer: layer %d is not a stand-alone tensor-core conv", idx);
+  HV_CHECK_ARG(n >= 1 && n <= g->max_batch, "generator_run_layer: batch %d outside 1..%d", n, g->max_batch);
+  tc_set_batch(g->tc->conv[idx], n);
+  return tc_conv_launch(g->tc->conv[idx], as_stream(stream));
 }
 
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream) {
@@ -324,6 +539,17 @@ long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_
     else if (idx == C18) src = g->last_heads[1];
     else if (idx == A17) src = g->last_heads[2];
     else if (idx == A18) src = g->last_heads[3];
+    else if (g->tc) {
+      const int b = g->tc->out_buf[idx];
+      HV_CHECK_ARG(b >= 0, "generator_read_tap: layer %d has no tap in bf16 mode", idx);
+      TcBuf v = g->tc->buf[b];
+      v.n = g->last_n;
+      if (g->tc->out_up2[idx]) { set_error("generator_read_tap: layer %d is stored upsampled in bf16 mode", idx); return HV_ERR_UNSUPPORTED; }
+      const int ch = idx == A16 ? 8 : kLayers[idx].cout;
+      int rc = tc_unpack_nchw(v, 0, ch, out, as_stream(stream));
+      if (rc) return rc;
+      return (long long)count;
+    }
     else src = g->act[idx];
   }
   HV_CUDA(cudaMemcpyAsync(out, src, count * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));

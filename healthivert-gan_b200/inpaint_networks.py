@@ -404,6 +404,10 @@ class Generator(nn.Module):
         self._last_out = out  # the head taps of read_tap() alias these buffers
         return out
 
+    def run_layer(self, idx, n):
+        """Measurement hook: launch the tensor-core conv kernel of layer ``idx`` alone (bf16 plan)."""
+        check(_lib.lib().hv_generator_run_layer(self._plan, idx, n, _lib.stream()))
+
     @torch.no_grad()
     def read_tap(self, idx):
         """Activation of conv block ``idx`` (state_dict order; 47 = attention output) of the last forward."""

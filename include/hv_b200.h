@@ -160,6 +160,9 @@ int hv_generator_forward(hv_generator* g, const float* x, const float* mask, con
                          float* x_stage1, float* x_stage2, float* flow, float* pred1_h,
                          float* pred2_h, int32_t* offsets, int per_sample_mask,
                          hv_stream_t stream);
+/* measurement hook (bf16 plan): launch the tensor-core conv kernel of layer idx alone on the
+ * activations of the last forward (bench.py times the dominant kernel with it)            */
+int hv_generator_run_layer(hv_generator* g, int idx, int n, hv_stream_t stream);
 /* debug/parity tap: copy the fp32 NCHW activation of layer idx (or idx==47: attention
  * output) of the LAST forward into out; returns element count or negative status        */
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream);

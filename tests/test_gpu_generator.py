@@ -135,3 +135,57 @@ def test_checkpoint_roundtrip(gen, tmp_path, synthetic_sd):
     args = synth.synthetic_slices(1, seed=3)
     for a, b in zip(_run(gen, *args), _run(g2, *args)):
         assert torch.equal(a, b)
+
+
+# ------------------------------------------------------------------------------ bf16 tensor-core mode
+def _psnr(a, b, data_range):
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * np.log10(data_range ** 2 / mse)
+
+
+@pytest.fixture(scope="module")
+def gen_bf16(synthetic_sd):
+    g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    g.load_state_dict(synthetic_sd)
+    g = g.cuda().eval()
+    g.precision = "bf16"
+    return g
+
+
+@pytest.mark.parametrize("n", [1, 16])
+def test_bf16_mode_psnr_against_fp32_oracle(gen_bf16, synthetic_sd, n):
+    """north star: PSNR >= 45 dB vs the fp32 reference in bf16 mode (data range 2 for CT, 1 for seg)."""
+    x, mask, cam, ratio = synth.synthetic_slices(n, seed=60 + n)
+    with torch.no_grad():
+        ref = gr.generator_forward(synthetic_sd, x, mask, cam, ratio, flow=False)
+    out = _run(gen_bf16, x, mask, cam, ratio)
+    got = dict(zip(NAMES, out))
+    want = dict(zip(NAMES, ref))
+    for name, rng in (("x_stage1", 2.0), ("x_stage2", 2.0), ("coarse_seg", 1.0), ("fine_seg", 1.0)):
+        p = _psnr(got[name], want[name], rng)
+        assert p >= 45.0, (name, p)
+    for name in ("pred1_h", "pred2_h"):
+        assert float((got[name] - want[name]).abs().max()) <= 5e-3, name
+    # thresholded masks may only differ inside a bf16-sized guard band around 0.5
+    for name in ("coarse_seg", "fine_seg"):
+        guard = (want[name] - 0.5).abs() > 0.05
+        assert torch.equal((got[name] > 0.5)[guard], (want[name] > 0.5)[guard]), name
+
+
+def test_bf16_layer_taps_track_fp32_oracle(gen_bf16, synthetic_sd):
+    x, mask, cam, ratio = synth.synthetic_slices(2, seed=71)
+    taps = {}
+    with torch.no_grad():
+        gr.generator_forward(synthetic_sd, x, mask, cam, ratio, taps=taps, flow=False)
+    _run(gen_bf16, x, mask, cam, ratio)
+    names = [f"{l[0]}.{l[1]}" for l in gr.all_layers()]
+    stored_upsampled = {"coarse_generator.conv12", "coarse_generator.conv14", "fine_generator.allconv19",
+                        "fine_generator.allconv14"}
+    for idx, name in enumerate(names):
+        if name in stored_upsampled:
+            continue
+        ref = taps[name]
+        got = gen_bf16.read_tap(idx).cpu().reshape(ref.shape)
+        scale = float(ref.abs().max())
+        err = float((got - ref).abs().max())
+        assert err <= 0.03 * scale + 1e-3, (name, err, scale)
