@@ -60,6 +60,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
   asm volatile(
@@ -92,7 +98,20 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+// TMEM -> registers: NCOL consecutive fp32 columns of this warp's 32 lanes (one row per thread)
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld<8>(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, float* v) {
   uint32_t r[16];
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
@@ -102,10 +121,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+template <>
+__device__ __forceinline__ void tmem_ld<32>(uint32_t taddr, float* v) {
+  tmem_ld<16>(taddr, v);
+  tmem_ld<16>(taddr + 16, v + 16);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-__device__ __forceinline__ float act_fast(float x, int act) {
-  switch (act) {
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x, int act_rt) {
+  if (ACT == HV_ACT_ELU) return x > 0.f ? x : __expf(x) - 1.f;
+  if (ACT == HV_ACT_RELU) return fmaxf(x, 0.f);
+  switch (act_rt) {
     case HV_ACT_ELU: return x > 0.f ? x : __expf(x) - 1.f;
     case HV_ACT_RELU: return fmaxf(x, 0.f);
     case HV_ACT_SIGMOID: return 1.f / (1.f + __expf(-x));
@@ -115,23 +142,28 @@ __device__ __forceinline__ float act_fast(float x, int act) {
   }
 }
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
 constexpr int TC_TMEM_COLS = 128;
+constexpr int TC_BAR_BYTES = 512;
 
 // ------------------------------------------------------------------------------------------- kernel
-template <int N_PAD>
+template <int N_PAD, int ACT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int ACC_STAGES = TC_TMEM_COLS / N_PAD;  // 2 / 4 / 8 accumulator tiles in flight
+  constexpr int NCOL = N_PAD / 2;                   // columns per epilogue warp (two warps share a lane quadrant)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_region = (p.w_bytes + 127u) & ~127u;
   uint8_t* s_slots = smem + w_region;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + (size_t)p.nslots * p.slot_bytes);
+  // 1 KB pad after the band ring: the last chunk of a shifted tap view reads past its band
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + (size_t)p.nslots * p.slot_bytes + 1024);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8u * p.nslots;
   const uint32_t bar_w = bar_empty + 8u * p.nslots;
   const uint32_t bar_tfull = bar_w + 8u;
-  const uint32_t bar_tempty = bar_tfull + 16u;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 5);
+  const uint32_t bar_tempty = bar_tfull + 8u * ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 1 + 2 * ACC_STAGES);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[0]) : "memory");
@@ -141,7 +173,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       for (int i = 0; i < p.nslots; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
       mbar_init(bar_w, 1);
-      for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 128); }
+      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * TC_EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -164,15 +196,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int img = tile / p.tiles_per_image;
-        const int o0 = (tile - img * p.tiles_per_image) * TC_TILE_M;
+        const int o0 = (tile - img * p.tiles_per_image) * p.tile_adv;
         for (int s = 0; s < p.nseg; ++s) {
           const TcSeg& sg = p.segs[s];
           mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
           const uint32_t fb = bar_full + 8u * slot;
-          mbar_expect_tx(fb, (uint32_t)sg.npix * sg.nchunks * 16u);
+          mbar_expect_tx(fb, (uint32_t)TC_TILE_M * sg.nchunks * 16u);
           const uint32_t dst = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
-          if (p.stride == 1) tma_load_4d(dst, &p.maps[sg.map], fb, 0, o0 + p.q_first + sg.rel_start, 0, img);
-          else tma_load_5d(dst, &p.maps[sg.map], fb, 0, sg.parity, o0 + sg.rel_start, 0, img);
+          const int c0 = 2 * (o0 + p.q_first + sg.rel_start);  // tensor-map inner unit = 8 B (half a position)
+          if (!p.s2d_in) tma_load_3d(dst, &p.maps[sg.map], fb, c0, 0, img);
+          else tma_load_4d(dst, &p.maps[sg.map], fb, c0, sg.sub, 0, img);
           if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         }
       }
@@ -197,7 +230,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           mbar_wait(bar_full + 8u * slot, phase);
           tc_fence_after();
           const uint32_t a_base = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
-          const uint32_t a_lbo = (uint32_t)sg.npix * 16u;
+          constexpr uint32_t a_lbo = TC_TILE_M * 16u;  // one band = [chunk][128 positions][8 ch]
           const int ksteps = sg.nchunks >> 1;
           for (int t = sg.tap_begin; t < sg.tap_end; ++t) {
             const uint32_t a0 = a_base + (uint32_t)p.taps[t].pix_off * 16u;
@@ -213,44 +246,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         }
         umma_commit(bar_tfull + 8u * acc);  // accumulator tile complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue (warps 2..9)
+    const int quad = warp & 3;               // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;        // which half of the N_PAD columns
+    const int col0 = half * NCOL;
+    float bias_r[NCOL];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) bias_r[i] = __ldg(p.bias + col0 + i);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.tiles_per_image;
-      const int o = (tile - img * p.tiles_per_image) * TC_TILE_M + quad * 32 + lane;
+      const int m = quad * 32 + lane;
+      const int o = (tile - img * p.tiles_per_image) * p.tile_adv + m;
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
-      float v[N_PAD];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD);
-#pragma unroll
-      for (int g = 0; g < N_PAD / 16; ++g) tmem_ld16(taddr + g * 16, v + g * 16);
+      float v[NCOL];
+      tmem_ld<NCOL>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD + col0), v);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(bar_tempty + 8u * acc);  // accumulator stage may be overwritten by the next tile
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
+      mbar_arrive(bar_tempty + 8u * acc);  // accumulator stage may be overwritten by a later tile
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 
-      int yy, xx;
-      if (p.stride == 1) {
-        const int q = o + p.q_first;
-        yy = q / p.in_pitch - p.in_border;
-        xx = q - (yy + p.in_border) * p.in_pitch - p.in_border;
-      } else {
-        yy = o / p.in_pitch;
-        xx = o - yy * p.in_pitch;
-      }
-      if (yy < 0 || yy >= p.h_out || xx < 0 || xx >= p.w_out) continue;
+      // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
+      const int q = o + p.q_first;
+      const int yy = q / p.in_pitch - p.in_border;
+      const int xx = q - (yy + p.in_border) * p.in_pitch - p.in_border;
+      if (m >= p.tile_adv || yy < 0 || yy >= p.h_out || xx < 0 || xx >= p.w_out) continue;
 
       if (p.out_mode == TC_OUT_HEADS) {
-        const float a0 = act_fast(v[0] + __ldg(p.bias + 0), HV_ACT_CLAMP1);
-        const float a1 = act_fast(v[1] + __ldg(p.bias + 1), HV_ACT_SIGMOID);
+        if (half != 0) continue;
+        const float a0 = fminf(fmaxf(v[0] + bias_r[0], -1.f), 1.f);
+        const float a1 = 1.f / (1.f + __expf(-(v[1] + bias_r[1])));
         const size_t pix = ((size_t)img * p.h_out + yy) * p.w_out + xx;
         p.head0[pix] = a0;
         p.head1[pix] = a1;
@@ -264,25 +295,27 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         continue;
       }
+      size_t pos;
+      if (p.out_mode == TC_OUT_CHUNKED) pos = (size_t)(yy + p.out_border) * p.out_pitch + xx + p.out_border;
+      else if (p.out_mode == TC_OUT_CHUNKED_S2D)  // consumer is a stride-2 conv: scatter by pixel parity
+        pos = (size_t)((yy & 1) * 2 + (xx & 1)) * p.out_sub_plane + (size_t)((yy >> 1) + p.out_border) * p.out_pitch + (xx >> 1) + p.out_border;
+      else pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
 #pragma unroll
-      for (int c = 0; c < N_PAD / 8; ++c) {
+      for (int j = 0; j < NCOL / 8; ++j) {
+        const int c = half * (NCOL / 8) + j;
         if (c >= p.out_nchunks) break;
         uint32_t pk[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float f0 = act_fast(v[c * 8 + 2 * j] + __ldg(p.bias + c * 8 + 2 * j), p.act);
-          const float f1 = act_fast(v[c * 8 + 2 * j + 1] + __ldg(p.bias + c * 8 + 2 * j + 1), p.act);
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = act_fast<ACT>(v[j * 8 + 2 * e] + bias_r[j * 8 + 2 * e], p.act);
+          const float f1 = act_fast<ACT>(v[j * 8 + 2 * e + 1] + bias_r[j * 8 + 2 * e + 1], p.act);
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
-          pk[j] = *reinterpret_cast<uint32_t*>(&h);
+          pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         __nv_bfloat16* plane = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off + c) * p.out_plane * 8;
-        if (p.out_mode == TC_OUT_CHUNKED) {
-          const size_t pos = (size_t)(yy + p.out_border) * p.out_pitch + xx + p.out_border;
-          *reinterpret_cast<uint4*>(plane + pos * 8) = val;
-        } else {  // nearest x2 upsample fused into the store (inpaint_networks.py:97,:105,:219,:222)
-          const size_t pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
-          *reinterpret_cast<uint4*>(plane + pos * 8) = val;
+        *reinterpret_cast<uint4*>(plane + pos * 8) = val;
+        if (p.out_mode == TC_OUT_CHUNKED_UP2) {  // nearest x2 upsample fused into the store (inpaint_networks.py:97,:105,:219,:222)
           *reinterpret_cast<uint4*>(plane + (pos + 1) * 8) = val;
           *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch) * 8) = val;
           *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch + 1) * 8) = val;
@@ -315,28 +348,35 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* map, const TcBuf& b, int stride, int box_pix, int box_chunks) {
+// Tensor map over one chunked buffer.  The inner dimension is the contiguous run of positions of one
+// chunk, described in 8-byte units (two per position) so that one 128-position band is a single
+// 2 KB box row (box rows of 16 B make TMA ~20x slower and fetch half-empty sectors).
+static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return HV_ERR_CUDA; }
-  const cuuint64_t plane = (cuuint64_t)b.plane();
-  CUresult r;
-  if (stride == 1) {
-    cuuint64_t dims[4] = {8, plane, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-    cuuint64_t strides[3] = {16, plane * 16, plane * 16 * b.chunks};
-    cuuint32_t box[4] = {8, (cuuint32_t)box_pix, (cuuint32_t)box_chunks, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  } else {
-    cuuint64_t dims[5] = {8, 2, plane / 2, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-    cuuint64_t strides[4] = {16, 32, plane * 16, plane * 16 * b.chunks};
-    cuuint32_t box[5] = {8, 1, (cuuint32_t)box_pix, (cuuint32_t)box_chunks, 1};
-    cuuint32_t es[5] = {1, 1, 1, 1, 1};
-    r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  const cuuint64_t plane_b = (cuuint64_t)b.plane() * 16, sub_b = (cuuint64_t)b.sub_plane() * 16;
+  CUresult r = CUDA_SUCCESS;
+  const CUtensorMapDataType types[2] = {CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    if (!b.s2d) {
+      cuuint64_t dims[3] = {(cuuint64_t)b.sub_plane() * 2, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+      cuuint64_t strides[2] = {plane_b, plane_b * b.chunks};
+      cuuint32_t box[3] = {2 * TC_TILE_M, (cuuint32_t)box_chunks, 1};
+      cuuint32_t es[3] = {1, 1, 1};
+      r = enc(map, types[attempt], 3, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, 4, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+      cuuint64_t strides[3] = {sub_b, plane_b, plane_b * b.chunks};
+      cuuint32_t box[4] = {2 * TC_TILE_M, 1, (cuuint32_t)box_chunks, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r == CUDA_SUCCESS) return HV_OK;
   }
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return HV_ERR_CUDA; }
-  return HV_OK;
+  set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return HV_ERR_CUDA;
 }
 
 // ------------------------------------------------------------------------------------------- host: setup
@@ -346,91 +386,80 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   memset(&c.p, 0, sizeof(c.p));
   c.k = k; c.stride = stride; c.dil = dil; c.nsrc = nsrc; c.cout_real = cout_real;
   for (int i = 0; i < nsrc; ++i) c.src[i] = srcs[i];
+  HV_CHECK_ARG(cout_real >= 1 && cout_real <= 64, "tc_conv: cout must be in 1..64");
   c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
-  HV_CHECK_ARG(cout_real <= 64, "tc_conv: cout <= 64");
   const TcBuf& b0 = srcs[0].buf;
   const int half = (k - 1) / 2;
   for (int i = 0; i < nsrc; ++i) {
     const TcBuf& b = srcs[i].buf;
     HV_CHECK_ARG(b.ptr && (b.chunks % 2) == 0, "tc_conv: source %d needs an even number of channel chunks", i);
-    HV_CHECK_ARG(b.h == b0.h && b.w == b0.w && b.border == b0.border && b.n == b0.n, "tc_conv: concat sources must share geometry");
-    HV_CHECK_ARG(b.border >= half * dil, "tc_conv: source border %d < conv padding %d", b.border, half * dil);
+    HV_CHECK_ARG(b.h == b0.h && b.w == b0.w && b.border == b0.border && b.n == b0.n && b.s2d == b0.s2d,
+                 "tc_conv: concat sources must share geometry");
+    HV_CHECK_ARG(b.s2d == (stride == 2), "tc_conv: a stride-2 conv reads a space-to-depth buffer (and only it does)");
+    HV_CHECK_ARG(b.border >= (stride == 2 ? 1 : half * dil), "tc_conv: source border %d smaller than the conv padding", b.border);
     HV_CHECK_ARG(srcs[i].real_channels <= b.chunks * 8, "tc_conv: real_channels > buffer channels");
   }
   HV_CHECK_ARG(b0.n == n_images, "tc_conv: batch mismatch");
+  HV_CHECK_ARG(stride == 1 || nsrc == 1, "tc_conv: stride-2 layers take a single source");
   TcParams& p = c.p;
-  p.stride = stride;
-  p.in_pitch = b0.pitch(); p.in_border = b0.border;
-  int seg = 0, tap = 0, woff = 0;
-  uint32_t max_seg_bytes = 0;
-  if (stride == 1) {
-    p.h_out = b0.h; p.w_out = b0.w;
-    p.q_first = b0.border * b0.pitch() + b0.border;
-    const int span = b0.h * b0.pitch();  // positions from (0,0) to the end of the last row (incl. side borders)
-    p.tiles_per_image = (span + TC_TILE_M - 1) / TC_TILE_M;
-    for (int s = 0; s < nsrc; ++s)
+  const int pitch = b0.pitch();
+  p.s2d_in = stride == 2;
+  p.in_pitch = pitch; p.in_border = b0.border;
+  p.h_out = b0.sub_h(); p.w_out = b0.sub_w();
+  p.q_first = b0.border * pitch + b0.border;
+  int seg = 0, tap = 0, woff = 0, max_shift = 0;
+  for (int s = 0; s < nsrc; ++s) {
+    const int nch = srcs[s].buf.chunks;
+    if (stride == 1) {
       for (int ky = 0; ky < k; ++ky) {
         HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
-        TcSeg& sg = p.segs[seg];
-        sg.map = s; sg.parity = 0; sg.nchunks = srcs[s].buf.chunks;
-        sg.rel_start = (ky - half) * dil * b0.pitch() - half * dil;
-        sg.npix = TC_TILE_M + 2 * half * dil;
+        TcSeg& sg = p.segs[seg++];
+        sg.map = s; sg.sub = 0; sg.nchunks = nch;
+        sg.rel_start = (ky - half) * dil * pitch - half * dil;
         sg.tap_begin = tap;
         for (int kx = 0; kx < k; ++kx) {
           HV_CHECK_ARG(tap < TC_MAX_TAPS, "tc_conv: too many taps");
           p.taps[tap].pix_off = kx * dil;
-          p.taps[tap].w_off = woff;
-          woff += sg.nchunks * c.n_pad * 16;
+          p.taps[tap].w_off = woff + (ky * k + kx) * nch * c.n_pad * 16;
+          max_shift = max(max_shift, kx * dil);
           ++tap;
         }
         sg.tap_end = tap;
-        max_seg_bytes = max(max_seg_bytes, (uint32_t)sg.npix * sg.nchunks * 16u);
-        ++seg;
       }
-  } else {
-    p.h_out = b0.h / 2; p.w_out = b0.w / 2;
-    p.q_first = 0;
-    const int span = p.h_out * b0.pitch();
-    p.tiles_per_image = (span + TC_TILE_M - 1) / TC_TILE_M;
-    const int B = b0.border;
-    for (int s = 0; s < nsrc; ++s)
+    } else {
+      // input pixel (2y+ky-1, 2x+kx-1) lives in sub-plane ((ky+1)&1, (kx+1)&1) at (y+dy, x+dx), dy/dx = -1 for k*=0
       for (int ky = 0; ky < 3; ++ky)
-        for (int par = 0; par < 2; ++par) {
-          // input position of output o, tap (ky,kx): 2*o + r, r = (ky-1+B)*pitch + (kx-1+B)
-          int dmin = 1 << 30, dmax = -1, cnt = 0;
-          for (int kx = 0; kx < 3; ++kx) {
-            const int r = (ky - 1 + B) * b0.pitch() + (kx - 1 + B);
-            if ((r & 1) != par) continue;
-            dmin = min(dmin, r >> 1); dmax = max(dmax, r >> 1); ++cnt;
-          }
-          if (!cnt) continue;
+        for (int px = 1; px >= 0; --px) {
           HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
-          TcSeg& sg = p.segs[seg];
-          sg.map = s; sg.parity = par; sg.nchunks = srcs[s].buf.chunks;
-          sg.rel_start = dmin; sg.npix = TC_TILE_M + (dmax - dmin);
+          TcSeg& sg = p.segs[seg++];
+          const int py = (ky + 1) & 1, dy = ky == 0 ? -1 : 0;
+          sg.map = s; sg.sub = py * 2 + px; sg.nchunks = nch;
+          sg.rel_start = dy * pitch + (px == 1 ? -1 : 0);
           sg.tap_begin = tap;
           for (int kx = 0; kx < 3; ++kx) {
-            const int r = (ky - 1 + B) * b0.pitch() + (kx - 1 + B);
-            if ((r & 1) != par) continue;
-            p.taps[tap].pix_off = (r >> 1) - dmin;
-            // weights are packed in (source, ky, kx) order independent of the segment order
-            p.taps[tap].w_off = ((s * 3 + ky) * 3 + kx) * sg.nchunks * c.n_pad * 16;
+            if (((kx + 1) & 1) != px) continue;
+            const int dx = kx == 0 ? -1 : 0;
+            p.taps[tap].pix_off = dx - (px == 1 ? -1 : 0);
+            p.taps[tap].w_off = woff + (ky * 3 + kx) * nch * c.n_pad * 16;
+            max_shift = max(max_shift, p.taps[tap].pix_off);
             ++tap;
           }
           sg.tap_end = tap;
-          max_seg_bytes = max(max_seg_bytes, (uint32_t)sg.npix * sg.nchunks * 16u);
-          ++seg;
         }
-    woff = 0;
-    for (int s = 0; s < nsrc; ++s) woff += 9 * srcs[s].buf.chunks * c.n_pad * 16;
-    HV_CHECK_ARG(nsrc == 1, "tc_conv: stride-2 layers take a single source");
+    }
+    woff += k * k * nch * c.n_pad * 16;
   }
   p.nseg = seg; p.ntap = tap;
   p.w_bytes = (uint32_t)woff;
+  p.tile_adv = TC_TILE_M - max_shift;
+  const int span = p.h_out * pitch;  // positions from output (0,0) to the end of the last row (incl. side borders)
+  p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
   p.total_tiles = p.tiles_per_image * n_images;
-  p.slot_bytes = (max_seg_bytes + 127u) & ~127u;
-  const size_t budget = 227 * 1024 - 1024;
-  const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 256;
+  int max_chunks = 0;
+  for (int s = 0; s < nsrc; ++s) max_chunks = max(max_chunks, srcs[s].buf.chunks);
+  p.slot_bytes = (uint32_t)TC_TILE_M * max_chunks * 16u;
+  const size_t budget = 227 * 1024 - 2048;
+  const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
   HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
   int nslots = (int)((budget - fixed) / p.slot_bytes);
   nslots = min(nslots, max(2 * seg, 4));
@@ -438,11 +467,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.nslots = nslots;
   c.smem = fixed + (size_t)nslots * p.slot_bytes;
   for (int s = 0; s < nsrc; ++s) {
-    int npix = 0;
-    for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) npix = max(npix, p.segs[i].npix);
-    // every segment of a source uses the same box; shorter (parity) segments are padded to the longest
-    for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) p.segs[i].npix = npix;
-    int rc = make_map(&p.maps[s], srcs[s].buf, stride, npix, srcs[s].buf.chunks);
+    int rc = make_map(&p.maps[s], srcs[s].buf, srcs[s].buf.chunks);
     if (rc) return rc;
   }
   if (nsrc == 1) p.maps[1] = p.maps[0];
@@ -459,8 +484,9 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
 
 void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act) {
   TcParams& p = c.p;
-  p.out_mode = up2 ? TC_OUT_CHUNKED_UP2 : TC_OUT_CHUNKED;
+  p.out_mode = up2 ? TC_OUT_CHUNKED_UP2 : (out.s2d ? TC_OUT_CHUNKED_S2D : TC_OUT_CHUNKED);
   p.out = out.ptr; p.out_pitch = out.pitch(); p.out_border = out.border; p.out_plane = out.plane();
+  p.out_sub_plane = out.sub_plane();
   p.out_chunks_total = out.chunks; p.out_chunk_off = chunk_off; p.out_nchunks = nchunks;
   p.act = act;
 }
@@ -526,16 +552,22 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
   return HV_OK;
 }
 
-template <int N_PAD>
-static int tc_launch_n(const TcConv& c, cudaStream_t st) {
+template <int N_PAD, int ACT>
+static int tc_launch_na(const TcConv& c, cudaStream_t st) {
   static bool configured = false;  // per instantiation; the attribute is sticky for the process
   if (!configured) {
-    HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv_tc_kernel<N_PAD><<<c.grid, TC_THREADS, c.smem, st>>>(c.p);
+  conv_tc_kernel<N_PAD, ACT><<<c.grid, TC_THREADS, c.smem, st>>>(c.p);
   HV_LAUNCH_CHECK();
   return HV_OK;
+}
+
+template <int N_PAD>
+static int tc_launch_n(const TcConv& c, cudaStream_t st) {
+  if (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_ELU) return tc_launch_na<N_PAD, HV_ACT_ELU>(c, st);
+  return tc_launch_na<N_PAD, -1>(c, st);
 }
 
 int tc_conv_launch(const TcConv& c, cudaStream_t st) {
@@ -548,9 +580,8 @@ int tc_conv_launch(const TcConv& c, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------- layout converters
-__global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels, int mode, __nv_bfloat16* __restrict__ dst,
-                                 int chunks, int h, int w, int border, int pitch, int plane, int ch0) {
-  const int n = blockIdx.z, c = blockIdx.y;
+__global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels, int mode, TcBuf dst, int ch0) {
+  const int n = blockIdx.z, c = blockIdx.y, h = dst.h, w = dst.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int y = i / w, x = i - y * w;
@@ -560,49 +591,47 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels
   else if (mode == HV_SRC_UP2) v = src[(((size_t)n * src_channels + c) * (h / 2) + y / 2) * (w / 2) + x / 2];
   else v = src[(((size_t)n * src_channels + c) * h + y) * w + x];
   const int ch = ch0 + c;
-  dst[(((size_t)n * chunks + (ch >> 3)) * plane + (size_t)(y + border) * pitch + x + border) * 8 + (ch & 7)] = __float2bfloat16(v);
+  dst.ptr[(((size_t)n * dst.chunks + (ch >> 3)) * dst.plane() + dst.pos(y, x)) * 8 + (ch & 7)] = __float2bfloat16(v);
 }
 
 int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst, int ch0, cudaStream_t st) {
   HV_CHECK_ARG(src && dst.ptr && ch0 + src_channels <= dst.chunks * 8, "tc_pack_nchw: bad argument");
   dim3 grid((dst.h * dst.w + 255) / 256, src_channels, dst.n);
-  pack_nchw_kernel<<<grid, 256, 0, st>>>(src, src_channels, mode, dst.ptr, dst.chunks, dst.h, dst.w, dst.border, dst.pitch(),
-                                         dst.plane(), ch0);
+  pack_nchw_kernel<<<grid, 256, 0, st>>>(src, src_channels, mode, dst, ch0);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
 
-__global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ src, int chunks, int h, int w, int border, int pitch,
-                                   int plane, int ch0, int channels, float* __restrict__ dst) {
-  const int n = blockIdx.z, c = blockIdx.y;
+__global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst) {
+  const int n = blockIdx.z, c = blockIdx.y, h = src.h, w = src.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int y = i / w, x = i - y * w, ch = ch0 + c;
   dst[((size_t)n * channels + c) * h * w + i] =
-      __bfloat162float(src[(((size_t)n * chunks + (ch >> 3)) * plane + (size_t)(y + border) * pitch + x + border) * 8 + (ch & 7)]);
+      __bfloat162float(src.ptr[(((size_t)n * src.chunks + (ch >> 3)) * src.plane() + src.pos(y, x)) * 8 + (ch & 7)]);
 }
 
 int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st) {
   HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8, "tc_unpack_nchw: bad argument");
   dim3 grid((src.h * src.w + 255) / 256, channels, src.n);
-  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src.ptr, src.chunks, src.h, src.w, src.border, src.pitch(), src.plane(), ch0, channels, dst);
+  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src, ch0, channels, dst);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
 
 // SHRM height head on a chunked buffer: sigmoid(fc(mean_HW(x)))  (inpaint_networks.py:90-93,:211-214)
-__global__ void __launch_bounds__(256) tc_gap_fc_kernel(const __nv_bfloat16* __restrict__ x, int chunks, int h, int w, int border,
-                                                        int pitch, int plane, const float* __restrict__ fw,
-                                                        const float* __restrict__ fb, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) tc_gap_fc_kernel(TcBuf x, const float* __restrict__ fw, const float* __restrict__ fb,
+                                                        float* __restrict__ out) {
   const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int h = x.h, w = x.w;
   __shared__ float red[8];
   float dot = 0.f;
-  for (int c = warp; c < chunks; c += nw) {
+  for (int c = warp; c < x.chunks; c += nw) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const __nv_bfloat16* pl = x + ((size_t)n * chunks + c) * plane * 8;
+    const __nv_bfloat16* pl = x.ptr + ((size_t)n * x.chunks + c) * x.plane() * 8;
     for (int i = lane; i < h * w; i += 32) {
       const int y = i / w, xx = i - y * w;
-      const uint4 raw = *reinterpret_cast<const uint4*>(pl + ((size_t)(y + border) * pitch + xx + border) * 8);
+      const uint4 raw = *reinterpret_cast<const uint4*>(pl + x.pos(y, xx) * 8);
       const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
       for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(hp[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
@@ -620,8 +649,8 @@ __global__ void __launch_bounds__(256) tc_gap_fc_kernel(const __nv_bfloat16* __r
 }
 
 int tc_gap_fc_sigmoid(const TcBuf& x, const float* fw, const float* fb, float* out, cudaStream_t st) {
-  HV_CHECK_ARG(x.ptr && fw && fb && out, "tc_gap_fc_sigmoid: null argument");
-  tc_gap_fc_kernel<<<x.n, 256, 0, st>>>(x.ptr, x.chunks, x.h, x.w, x.border, x.pitch(), x.plane(), fw, fb, out);
+  HV_CHECK_ARG(x.ptr && fw && fb && out && !x.s2d, "tc_gap_fc_sigmoid: bad argument");
+  tc_gap_fc_kernel<<<x.n, 256, 0, st>>>(x, fw, fb, out);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }

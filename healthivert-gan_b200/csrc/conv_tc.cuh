@@ -16,12 +16,23 @@
 
 namespace hv {
 
+// s2d ("space to depth"): the buffer feeds a stride-2 conv; it is stored as 4 sub-planes selected by
+// (y&1, x&1), each a zero-bordered (h/2) x (w/2) image, so that every stride-2 tap is a constant shift
+// inside one sub-plane (the producer's epilogue scatters its pixels accordingly).
 struct TcBuf {
   __nv_bfloat16* ptr = nullptr;
   int n = 0, chunks = 0, h = 0, w = 0, border = 0;
-  int pitch() const { return w + 2 * border; }
-  int rows() const { return h + 2 * border; }
-  int plane() const { return (pitch() * rows() + 1) & ~1; }  // even, for the stride-2 parity view
+  bool s2d = false;
+  __host__ __device__ int sub_h() const { return s2d ? h / 2 : h; }
+  __host__ __device__ int sub_w() const { return s2d ? w / 2 : w; }
+  __host__ __device__ int pitch() const { return sub_w() + 2 * border; }
+  __host__ __device__ int rows() const { return sub_h() + 2 * border; }
+  __host__ __device__ int sub_plane() const { return (pitch() * rows() + 7) & ~7; }
+  __host__ __device__ int plane() const { return s2d ? 4 * sub_plane() : sub_plane(); }
+  __host__ __device__ size_t pos(int y, int x) const {
+    if (!s2d) return (size_t)(y + border) * pitch() + x + border;
+    return (size_t)((y & 1) * 2 + (x & 1)) * sub_plane() + (size_t)((y >> 1) + border) * pitch() + (x >> 1) + border;
+  }
   size_t elems() const { return (size_t)n * chunks * plane() * 8; }
   size_t bytes() const { return elems() * sizeof(__nv_bfloat16); }
 };
@@ -32,9 +43,8 @@ constexpr int TC_TILE_M = 128;
 
 struct TcSeg {
   int map;        // which tensor map (source)
-  int rel_start;  // start position relative to the tile origin
-  int npix;       // positions in the box
-  int parity;     // stride-2 parity plane (0/1); unused for stride 1
+  int rel_start;  // start position of the 128-position band relative to the tile origin
+  int sub;        // sub-plane (s2d sources); 0 otherwise
   int nchunks;    // channel chunks of this source
   int tap_begin, tap_end;
 };
@@ -44,7 +54,7 @@ struct TcTap {
   int w_off;     // byte offset of this tap's weight slab [chunk][n_pad][8] in shared memory
 };
 
-enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2 };
+enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2, TC_OUT_CHUNKED_S2D = 3 };
 
 struct TcAux {  // optional bf16 side output of a head: one channel of a chunked buffer
   __nv_bfloat16* ptr;
@@ -59,14 +69,15 @@ struct TcParams {
   const void* w_packed;
   uint32_t w_bytes;
   const float* bias;  // [n_pad]
-  int stride;
+  int s2d_in;     // sources are space-to-depth buffers (stride-2 conv)
+  int tile_adv;   // valid output positions per 128-row MMA tile (128 - widest tap shift)
   int tiles_per_image, total_tiles;
   int in_pitch, in_border, q_first;
   int h_out, w_out;
   int act;
   int out_mode;
   __nv_bfloat16* out;
-  int out_pitch, out_border, out_plane, out_chunks_total, out_chunk_off, out_nchunks;
+  int out_pitch, out_border, out_plane, out_sub_plane, out_chunks_total, out_chunk_off, out_nchunks;
   float* head0;
   float* head1;
   TcAux aux0, aux1;

@@ -8,8 +8,8 @@
 
 namespace hv {
 
-static int alloc_buf(TcBuf& b, int n, int channels, int h, int w, int border, cudaStream_t st) {
-  b.n = n; b.chunks = ((channels + 15) / 16) * 2; b.h = h; b.w = w; b.border = border;
+static int alloc_buf(TcBuf& b, int n, int channels, int h, int w, int border, bool s2d, cudaStream_t st) {
+  b.n = n; b.chunks = ((channels + 15) / 16) * 2; b.h = h; b.w = w; b.border = border; b.s2d = s2d;
   HV_CUDA(cudaMallocAsync((void**)&b.ptr, b.bytes(), st));
   HV_CUDA(cudaMemsetAsync(b.ptr, 0, b.bytes(), st));
   return HV_OK;
@@ -31,13 +31,13 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
   int ch0 = d->src[0].channels, ch1 = 0;
   for (int i = 1; i < d->nsrc; ++i) ch1 += d->src[i].channels;
   HV_CHECK_ARG(ch0 + ch1 == d->cin, "conv2d_bf16: sources have %d channels, cin=%d", ch0 + ch1, d->cin);
-  int rc = alloc_buf(srcs[0].buf, d->n, ch0, d->hin, d->win, border, st);
+  int rc = alloc_buf(srcs[0].buf, d->n, ch0, d->hin, d->win, border, d->stride == 2, st);
   if (rc) return rc;
   srcs[0].real_channels = ch0;
   rc = tc_pack_nchw(d->src[0].ptr, ch0, d->src[0].mode, srcs[0].buf, 0, st);
   if (rc) return rc;
   if (nts == 2) {
-    rc = alloc_buf(srcs[1].buf, d->n, ch1, d->hin, d->win, border, st);
+    rc = alloc_buf(srcs[1].buf, d->n, ch1, d->hin, d->win, border, d->stride == 2, st);
     if (rc) return rc;
     srcs[1].real_channels = ch1;
     int off = 0;
@@ -60,7 +60,7 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
     rc = tc_conv_pack_weights(c, w, bias, d->cout, nullptr, nullptr, 0, st);
     if (rc) return rc;
     const int sc = up2_out ? 2 : 1;
-    rc = alloc_buf(out, d->n, d->cout, ho * sc, wo * sc, 1, st);
+    rc = alloc_buf(out, d->n, d->cout, ho * sc, wo * sc, 1, false, st);
     if (rc) return rc;
     tc_conv_set_output_chunked(c, out, 0, c.n_pad / 8, up2_out != 0, d->act);
   }

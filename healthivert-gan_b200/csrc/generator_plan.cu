@@ -286,6 +286,8 @@ static int tc_plan_create(hv_generator* g) {
   for (int i = 0; i < B_COUNT; ++i) {
     TcBuf& b = t->buf[i];
     b.n = n; b.chunks = kBufs[i].channels / 8; b.h = b.w = kBufs[i].extent; b.border = kBufs[i].border;
+    // buffers consumed by a stride-2 conv are stored space-to-depth
+    b.s2d = (i == B_C1 || i == B_C3 || i == B_F1 || i == B_F3 || i == B_P1 || i == B_P3);
     total += (b.bytes() + 255) & ~(size_t)255;
   }
   HV_CUDA(cudaMalloc((void**)&t->blob, total));
