@@ -79,6 +79,15 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
+// one lane of the (fully converged) warp; the role loops stay warp-uniform so that ptxas keeps descriptor
+// arithmetic in uniform registers and emits back-to-back UTCHMMA (a divergent `if (lane == 0)` body wraps every
+// tcgen05.mma in an ELECT/BRA waterfall loop: ~150 cycles per MMA instead of 40-48, see profiles/r1_probe_mma_tma.log)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok));
+  return ok != 0;
+}
+
 // K-major, no-swizzle UMMA shared-memory descriptor: core matrix = 8 rows x 16 B contiguous;
 // LBO = byte distance between the two 8-element K chunks of one MMA, SBO = distance between 8-row groups.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -142,16 +151,65 @@ __device__ __forceinline__ float act_fast(float x, int act_rt) {
   }
 }
 
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
-constexpr int TC_TMEM_COLS = 128;
+// optional per-CTA event trace (debug / profiling aid, see tools/trace_conv.py): CTA 0 appends (tag, clock) pairs
+__device__ __forceinline__ void trace_ev(long long* tr, int& n, int tag) {
+  if (tr && blockIdx.x == 0 && n < 2000) { tr[2 * n] = tag; tr[2 * n + 1] = clock64(); ++n; }
+}
+
+
+// All MMAs of one segment, fully unrolled for the common (rows, taps, k-steps) shapes: every descriptor is
+// `uniform base + small uniform offset`, so ptxas emits back-to-back UTCHMMA fed from uniform registers.
+template <int N_PAD, int NROWS, int NTAPS, int KSTEPS>
+__device__ __forceinline__ void issue_segment(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t a_step,
+                                              uint32_t b_step, uint32_t b_row_step, uint32_t idesc, uint32_t first_acc) {
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  constexpr uint32_t a_lbo = (uint32_t)NROWS * TC_TILE_M;
+  if (leader) {
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+      for (int i = 0; i < NTAPS; ++i)
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t a_lo = a_base + (uint32_t)r * TC_TILE_M + (uint32_t)i * a_step + (uint32_t)ks * 2u * a_lbo;
+          const uint32_t b_lo = b_base + (uint32_t)r * b_row_step + (uint32_t)i * b_step + (uint32_t)ks * 2u * N_PAD;
+          umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc,
+                    (r | i | ks) == 0 ? first_acc : 1u);
+        }
+  }
+}
+
+// generic (slow) fallback for shapes without an unrolled instance
+template <int N_PAD>
+__device__ __forceinline__ void issue_segment_generic(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t a_step,
+                                                      uint32_t b_step, uint32_t b_row_step, uint32_t idesc, uint32_t first_acc,
+                                                      int nrows, int ntaps, int ksteps) {
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  const uint32_t a_lbo = (uint32_t)nrows * TC_TILE_M;
+  uint32_t accumulate = first_acc;
+  for (int r = 0; r < nrows; ++r)
+    for (int i = 0; i < ntaps; ++i)
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t a_lo = a_base + (uint32_t)r * TC_TILE_M + (uint32_t)i * a_step + (uint32_t)ks * 2u * a_lbo;
+        const uint32_t b_lo = b_base + (uint32_t)r * b_row_step + (uint32_t)i * b_step + (uint32_t)ks * 2u * N_PAD;
+        if (leader) umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, accumulate);
+        accumulate = 1;
+      }
+}
+
+constexpr int TC_TMEM_COLS = 256;
 constexpr int TC_BAR_BYTES = 512;
+__host__ __device__ constexpr int tc_epi_warps(int n_pad) { return n_pad == 16 ? 8 : 16; }
+__host__ __device__ constexpr int tc_threads(int n_pad) { return 64 + 32 * tc_epi_warps(n_pad); }
+__host__ __device__ constexpr int tc_acc_stages(int n_pad) { return TC_TMEM_COLS / n_pad > 8 ? 8 : TC_TMEM_COLS / n_pad; }
 
 // ------------------------------------------------------------------------------------------- kernel
+// warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2..: epilogue (4 lane quadrants x column groups)
 template <int N_PAD, int ACT>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
-  constexpr int ACC_STAGES = TC_TMEM_COLS / N_PAD;  // 2 / 4 / 8 accumulator tiles in flight
-  constexpr int NCOL = N_PAD / 2;                   // columns per epilogue warp (two warps share a lane quadrant)
+__global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+  constexpr int ACC_STAGES = tc_acc_stages(N_PAD);       // accumulator tiles in flight
+  constexpr int EPI_WARPS = tc_epi_warps(N_PAD);
+  constexpr int NCOL = N_PAD / (EPI_WARPS / 4);          // columns per epilogue warp (8 or 16)
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_region = (p.w_bytes + 127u) & ~127u;
@@ -173,7 +231,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (lane == 0) {
       for (int i = 0; i < p.nslots; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
       mbar_init(bar_w, 1);
-      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * TC_EPI_WARPS); }
+      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * EPI_WARPS); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -188,83 +246,104 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (warp-uniform, one lane issues)
+    const bool leader = elect_one();
+    if (leader) {
       mbar_expect_tx(bar_w, p.w_bytes);
       bulk_load(smem_u32(smem), p.w_packed, p.w_bytes, bar_w);
-      int slot = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int img = tile / p.tiles_per_image;
-        const int o0 = (tile - img * p.tiles_per_image) * p.tile_adv;
-        for (int s = 0; s < p.nseg; ++s) {
-          const TcSeg& sg = p.segs[s];
-          mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+    }
+    int slot = 0, ntr = 0;
+    uint32_t phase = 0;
+    const uint32_t slots_base = smem_u32(s_slots);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int img = tile / p.tiles_per_image;
+      const int c_tile = 2 * ((tile - img * p.tiles_per_image) * p.tile_adv + p.q_first);  // tensor-map inner unit = 8 B
+      for (int s = 0; s < p.nseg; ++s) {
+        mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+        if (leader) {
           const uint32_t fb = bar_full + 8u * slot;
-          mbar_expect_tx(fb, (uint32_t)TC_TILE_M * sg.nchunks * 16u);
-          const uint32_t dst = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
-          const int c0 = 2 * (o0 + p.q_first + sg.rel_start);  // tensor-map inner unit = 8 B (half a position)
-          if (!p.s2d_in) tma_load_3d(dst, &p.maps[sg.map], fb, c0, 0, img);
-          else tma_load_4d(dst, &p.maps[sg.map], fb, c0, sg.sub, 0, img);
-          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+          mbar_expect_tx(fb, p.segs[s].tx_bytes);
+          tma_load_4d(slots_base + (uint32_t)slot * p.slot_bytes, &p.maps[p.segs[s].map], fb, c_tile + p.segs[s].rel_start2,
+                      p.segs[s].c1, 0, img);
+          trace_ev(p.trace, ntr, 1);
         }
+        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
-      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_PAD >> 3) << 17) | ((128u >> 4) << 24);
-      mbar_wait(bar_w, 0);
+    // ===================================================================== MMA issuer (warp-uniform, one lane issues)
+    const bool leader = elect_one();
+    // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_PAD >> 3) << 17) | ((128u >> 4) << 24);
+    // smem descriptor = hi word (SBO = 128 B, version 1) : lo word (start >> 4 | LBO >> 4 << 16); offsets add into lo.
+    // A: K chunks of a segment are nrows * 128 positions apart; B: [chunk][N_PAD][8] -> N_PAD * 16 B apart
+    constexpr uint32_t b_lo_const = (uint32_t)N_PAD << 16;
+    mbar_wait(bar_w, 0);
+    tc_fence_after();
+    const uint32_t b_lo_base = b_lo_const + (smem_u32(smem) >> 4);
+    const uint32_t a_lo_base = smem_u32(s_slots) >> 4;
+    const uint32_t slot_units = p.slot_bytes >> 4;
+    int slot = 0, acc = 0, ntr = 0;
+    long long* tr = p.trace ? p.trace + 4000 : nullptr;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t w_base = smem_u32(smem);
-      int slot = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+      if (leader) trace_ev(tr, ntr, 11);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_PAD);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.nseg; ++s) {
+        const int nrows = p.segs[s].nrows, ntaps = p.segs[s].ntaps, ksteps = p.segs[s].nchunks >> 1;
+        const uint32_t a_lbo = (uint32_t)nrows * TC_TILE_M;  // 16 B units: K chunks of the segment image are nrows bands apart
+        const uint32_t a_step = p.segs[s].a_step, b_step = p.segs[s].b_step, b_row_step = p.segs[s].b_row_step;
+        const uint32_t a_row = a_lo_base + (uint32_t)slot * slot_units + (a_lbo << 16) + p.segs[s].a0;
+        const uint32_t b_row = b_lo_base + p.segs[s].b0;
+        mbar_wait(bar_full + 8u * slot, phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_PAD);
-        uint32_t accumulate = 0;
-        for (int s = 0; s < p.nseg; ++s) {
-          const TcSeg& sg = p.segs[s];
-          mbar_wait(bar_full + 8u * slot, phase);
-          tc_fence_after();
-          const uint32_t a_base = smem_u32(s_slots + (size_t)slot * p.slot_bytes);
-          constexpr uint32_t a_lbo = TC_TILE_M * 16u;  // one band = [chunk][128 positions][8 ch]
-          const int ksteps = sg.nchunks >> 1;
-          for (int t = sg.tap_begin; t < sg.tap_end; ++t) {
-            const uint32_t a0 = a_base + (uint32_t)p.taps[t].pix_off * 16u;
-            const uint32_t b0 = w_base + (uint32_t)p.taps[t].w_off;
-            for (int ks = 0; ks < ksteps; ++ks) {
-              const uint64_t ad = umma_desc(a0 + (uint32_t)ks * 2u * a_lbo, a_lbo, 128u);
-              const uint64_t bd = umma_desc(b0 + (uint32_t)ks * 2u * (N_PAD * 16u), N_PAD * 16u, 128u);
-              umma_bf16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
-            }
-          }
-          umma_commit(bar_empty + 8u * slot);  // frees the band slot once these MMAs have read it
-          if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        if (leader) trace_ev(tr, ntr, 12);
+        const int shape = (nrows << 8) | (ntaps << 4) | ksteps;
+#define HV_SEG(R, T, K)                                                                                                   \
+  case ((R) << 8) | ((T) << 4) | (K):                                                                                     \
+    issue_segment<N_PAD, R, T, K>(leader, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);           \
+    break;
+        switch (shape) {
+          HV_SEG(3, 3, 1) HV_SEG(3, 3, 2) HV_SEG(3, 3, 4) HV_SEG(5, 5, 1) HV_SEG(5, 5, 2)
+          HV_SEG(1, 3, 1) HV_SEG(1, 3, 2) HV_SEG(1, 3, 4) HV_SEG(1, 2, 1) HV_SEG(1, 2, 2) HV_SEG(1, 1, 1) HV_SEG(1, 1, 2)
+          HV_SEG(5, 1, 1) HV_SEG(5, 1, 2) HV_SEG(1, 5, 1)
+          default:
+            issue_segment_generic<N_PAD>(leader, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate, nrows, ntaps, ksteps);
         }
-        umma_commit(bar_tfull + 8u * acc);  // accumulator tile complete -> epilogue
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+#undef HV_SEG
+        accumulate = 1;
+        if (leader) { umma_commit(bar_empty + 8u * slot); trace_ev(tr, ntr, 13); }  // slot is free once these MMAs have read it
+        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(bar_tfull + 8u * acc);  // accumulator tile complete -> epilogue
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
+    __syncwarp();
   } else {
-    // ===================================================================== epilogue (warps 2..9)
+    // ===================================================================== epilogue (warps 2 .. 2 + EPI_WARPS)
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;        // which half of the N_PAD columns
-    const int col0 = half * NCOL;
+    const int group = (warp - 2) >> 2;       // which NCOL-wide column group
+    const int col0 = group * NCOL;
     float bias_r[NCOL];
 #pragma unroll
     for (int i = 0; i < NCOL; ++i) bias_r[i] = __ldg(p.bias + col0 + i);
-    int acc = 0;
+    int acc = 0, ntr = 0;
+    long long* tr = (p.trace && warp == 2 && lane == 0) ? p.trace + 8000 : nullptr;
     uint32_t acc_phase = 0;
+    const int m = quad * 32 + lane;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.tiles_per_image;
-      const int m = quad * 32 + lane;
-      const int o = (tile - img * p.tiles_per_image) * p.tile_adv + m;
+      const int q = (tile - img * p.tiles_per_image) * p.tile_adv + m + p.q_first;
+      const int qrow = (int)(((unsigned long long)q * p.pitch_magic) >> 40);
+      const int yy = qrow - p.in_border;
+      const int xx = q - qrow * p.in_pitch - p.in_border;
+      trace_ev(tr, ntr, 20);
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
+      trace_ev(tr, ntr, 21);
       float v[NCOL];
       tmem_ld<NCOL>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD + col0), v);
       tmem_ld_wait();
@@ -273,13 +352,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
 
       // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
-      const int q = o + p.q_first;
-      const int yy = q / p.in_pitch - p.in_border;
-      const int xx = q - (yy + p.in_border) * p.in_pitch - p.in_border;
       if (m >= p.tile_adv || yy < 0 || yy >= p.h_out || xx < 0 || xx >= p.w_out) continue;
 
       if (p.out_mode == TC_OUT_HEADS) {
-        if (half != 0) continue;
+        if (group != 0) continue;
         const float a0 = fminf(fmaxf(v[0] + bias_r[0], -1.f), 1.f);
         const float a1 = 1.f / (1.f + __expf(-(v[1] + bias_r[1])));
         const size_t pix = ((size_t)img * p.h_out + yy) * p.w_out + xx;
@@ -302,7 +378,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       else pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
 #pragma unroll
       for (int j = 0; j < NCOL / 8; ++j) {
-        const int c = half * (NCOL / 8) + j;
+        const int c = group * (NCOL / 8) + j;
         if (c >= p.out_nchunks) break;
         uint32_t pk[4];
 #pragma unroll
@@ -351,28 +427,22 @@ static PFN_encodeTiled get_encode() {
 // Tensor map over one chunked buffer.  The inner dimension is the contiguous run of positions of one
 // chunk, described in 8-byte units (two per position) so that one 128-position band is a single
 // 2 KB box row (box rows of 16 B make TMA ~20x slower and fetch half-empty sectors).
-static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks) {
+//   stride-1 sources : dims {positions*2, k rows, chunks, n}, dim 1 steps `dil` image rows, so ONE box of `box_rows`
+//                      rows brings the bands of `box_rows` kernel rows (the dims overlap in memory; TMA does not mind)
+//   s2d sources      : dims {sub-plane positions*2, 4 sub-planes, chunks, n}, box_rows = 1
+static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks, int k, int dil, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return HV_ERR_CUDA; }
   const cuuint64_t plane_b = (cuuint64_t)b.plane() * 16, sub_b = (cuuint64_t)b.sub_plane() * 16;
   CUresult r = CUDA_SUCCESS;
   const CUtensorMapDataType types[2] = {CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64};
   for (int attempt = 0; attempt < 2; ++attempt) {
-    if (!b.s2d) {
-      cuuint64_t dims[3] = {(cuuint64_t)b.sub_plane() * 2, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-      cuuint64_t strides[2] = {plane_b, plane_b * b.chunks};
-      cuuint32_t box[3] = {2 * TC_TILE_M, (cuuint32_t)box_chunks, 1};
-      cuuint32_t es[3] = {1, 1, 1};
-      r = enc(map, types[attempt], 3, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    } else {
-      cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, 4, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-      cuuint64_t strides[3] = {sub_b, plane_b, plane_b * b.chunks};
-      cuuint32_t box[4] = {2 * TC_TILE_M, 1, (cuuint32_t)box_chunks, 1};
-      cuuint32_t es[4] = {1, 1, 1, 1};
-      r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    }
+    cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, b.s2d ? 4u : (cuuint64_t)k, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+    cuuint64_t strides[3] = {b.s2d ? sub_b : (cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.chunks};
+    cuuint32_t box[4] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r == CUDA_SUCCESS) return HV_OK;
   }
   set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -390,6 +460,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
   const TcBuf& b0 = srcs[0].buf;
   const int half = (k - 1) / 2;
+  int max_chunks = 0, total_chunks = 0;
   for (int i = 0; i < nsrc; ++i) {
     const TcBuf& b = srcs[i].buf;
     HV_CHECK_ARG(b.ptr && (b.chunks % 2) == 0, "tc_conv: source %d needs an even number of channel chunks", i);
@@ -398,76 +469,74 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     HV_CHECK_ARG(b.s2d == (stride == 2), "tc_conv: a stride-2 conv reads a space-to-depth buffer (and only it does)");
     HV_CHECK_ARG(b.border >= (stride == 2 ? 1 : half * dil), "tc_conv: source border %d smaller than the conv padding", b.border);
     HV_CHECK_ARG(srcs[i].real_channels <= b.chunks * 8, "tc_conv: real_channels > buffer channels");
+    max_chunks = max(max_chunks, b.chunks);
+    total_chunks += b.chunks;
   }
   HV_CHECK_ARG(b0.n == n_images, "tc_conv: batch mismatch");
   HV_CHECK_ARG(stride == 1 || nsrc == 1, "tc_conv: stride-2 layers take a single source");
   TcParams& p = c.p;
   const int pitch = b0.pitch();
+  HV_CHECK_ARG((long long)b0.plane() < (1ll << 20), "tc_conv: plane too large for the fast row division");
   p.s2d_in = stride == 2;
   p.in_pitch = pitch; p.in_border = b0.border;
+  p.pitch_magic = ((1ull << 40) + (unsigned long long)pitch - 1) / (unsigned long long)pitch;
   p.h_out = b0.sub_h(); p.w_out = b0.sub_w();
   p.q_first = b0.border * pitch + b0.border;
-  int seg = 0, tap = 0, woff = 0, max_shift = 0;
+  p.w_bytes = (uint32_t)(k * k * total_chunks * c.n_pad * 16);
+  const size_t budget = 227 * 1024 - 2048;
+  const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
+  // all k kernel rows of a source in one TMA load when at least 3 such slots fit beside the weights
+  const size_t band_bytes = (size_t)TC_TILE_M * max_chunks * 16u;
+  const bool multirow = stride == 1 && fixed + 3 * (size_t)k * band_bytes <= budget;
+  const int box_rows = multirow ? k : 1;
+  p.slot_bytes = (uint32_t)(band_bytes * box_rows);
+  HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
+  int seg = 0, max_shift = 0;
+  uint32_t woff16 = 0;
   for (int s = 0; s < nsrc; ++s) {
     const int nch = srcs[s].buf.chunks;
+    const uint32_t slab = (uint32_t)nch * c.n_pad;  // one tap's weights, 16 B units
     if (stride == 1) {
-      for (int ky = 0; ky < k; ++ky) {
+      max_shift = (k - 1) * dil;
+      for (int ky = 0; ky < (multirow ? 1 : k); ++ky) {
         HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
         TcSeg& sg = p.segs[seg++];
-        sg.map = s; sg.sub = 0; sg.nchunks = nch;
-        sg.rel_start = (ky - half) * dil * pitch - half * dil;
-        sg.tap_begin = tap;
-        for (int kx = 0; kx < k; ++kx) {
-          HV_CHECK_ARG(tap < TC_MAX_TAPS, "tc_conv: too many taps");
-          p.taps[tap].pix_off = kx * dil;
-          p.taps[tap].w_off = woff + (ky * k + kx) * nch * c.n_pad * 16;
-          max_shift = max(max_shift, kx * dil);
-          ++tap;
-        }
-        sg.tap_end = tap;
+        sg.map = s; sg.nchunks = nch; sg.nrows = box_rows; sg.ntaps = k;
+        sg.c1 = ky;  // kernel row selected through the row dimension of the tensor map
+        sg.rel_start2 = 2 * (-half * dil * pitch - half * dil);
+        sg.a0 = 0; sg.a_step = (uint32_t)dil;
+        sg.b0 = woff16 + (uint32_t)(ky * k) * slab; sg.b_step = slab; sg.b_row_step = (uint32_t)k * slab;
       }
     } else {
       // input pixel (2y+ky-1, 2x+kx-1) lives in sub-plane ((ky+1)&1, (kx+1)&1) at (y+dy, x+dx), dy/dx = -1 for k*=0
+      max_shift = 1;
       for (int ky = 0; ky < 3; ++ky)
         for (int px = 1; px >= 0; --px) {
           HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
           TcSeg& sg = p.segs[seg++];
           const int py = (ky + 1) & 1, dy = ky == 0 ? -1 : 0;
-          sg.map = s; sg.sub = py * 2 + px; sg.nchunks = nch;
-          sg.rel_start = dy * pitch + (px == 1 ? -1 : 0);
-          sg.tap_begin = tap;
-          for (int kx = 0; kx < 3; ++kx) {
-            if (((kx + 1) & 1) != px) continue;
-            const int dx = kx == 0 ? -1 : 0;
-            p.taps[tap].pix_off = dx - (px == 1 ? -1 : 0);
-            p.taps[tap].w_off = woff + (ky * 3 + kx) * nch * c.n_pad * 16;
-            max_shift = max(max_shift, p.taps[tap].pix_off);
-            ++tap;
-          }
-          sg.tap_end = tap;
+          sg.map = s; sg.c1 = py * 2 + px; sg.nchunks = nch; sg.nrows = 1;
+          sg.rel_start2 = 2 * (dy * pitch + (px == 1 ? -1 : 0));
+          sg.a0 = 0; sg.b_row_step = 0;
+          if (px == 1) { sg.ntaps = 2; sg.a_step = 1; sg.b0 = woff16 + (uint32_t)(ky * 3) * slab; sg.b_step = 2 * slab; }   // kx = 0, 2
+          else { sg.ntaps = 1; sg.a_step = 0; sg.b0 = woff16 + (uint32_t)(ky * 3 + 1) * slab; sg.b_step = 0; }              // kx = 1
         }
     }
-    woff += k * k * nch * c.n_pad * 16;
+    woff16 += (uint32_t)(k * k) * slab;
   }
-  p.nseg = seg; p.ntap = tap;
-  p.w_bytes = (uint32_t)woff;
+  p.nseg = seg;
+  for (int i = 0; i < seg; ++i) p.segs[i].tx_bytes = (uint32_t)TC_TILE_M * p.segs[i].nchunks * 16u * p.segs[i].nrows;
   p.tile_adv = TC_TILE_M - max_shift;
   const int span = p.h_out * pitch;  // positions from output (0,0) to the end of the last row (incl. side borders)
   p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
   p.total_tiles = p.tiles_per_image * n_images;
-  int max_chunks = 0;
-  for (int s = 0; s < nsrc; ++s) max_chunks = max(max_chunks, srcs[s].buf.chunks);
-  p.slot_bytes = (uint32_t)TC_TILE_M * max_chunks * 16u;
-  const size_t budget = 227 * 1024 - 2048;
-  const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
-  HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
   int nslots = (int)((budget - fixed) / p.slot_bytes);
   nslots = min(nslots, max(2 * seg, 4));
   nslots = min(nslots, 12);
   p.nslots = nslots;
   c.smem = fixed + (size_t)nslots * p.slot_bytes;
   for (int s = 0; s < nsrc; ++s) {
-    int rc = make_map(&p.maps[s], srcs[s].buf, srcs[s].buf.chunks);
+    int rc = make_map(&p.maps[s], srcs[s].buf, srcs[s].buf.chunks, k, dil, box_rows);
     if (rc) return rc;
   }
   if (nsrc == 1) p.maps[1] = p.maps[0];
@@ -552,6 +621,9 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
   return HV_OK;
 }
 
+static long long* g_trace = nullptr;
+void tc_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 template <int N_PAD, int ACT>
 static int tc_launch_na(const TcConv& c, cudaStream_t st) {
   static bool configured = false;  // per instantiation; the attribute is sticky for the process
@@ -559,7 +631,13 @@ static int tc_launch_na(const TcConv& c, cudaStream_t st) {
     HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv_tc_kernel<N_PAD, ACT><<<c.grid, TC_THREADS, c.smem, st>>>(c.p);
+  if (g_trace) {
+    TcParams q = c.p;
+    q.trace = g_trace;
+    conv_tc_kernel<N_PAD, ACT><<<c.grid, tc_threads(N_PAD), c.smem, st>>>(q);
+  } else {
+    conv_tc_kernel<N_PAD, ACT><<<c.grid, tc_threads(N_PAD), c.smem, st>>>(c.p);
+  }
   HV_LAUNCH_CHECK();
   return HV_OK;
 }

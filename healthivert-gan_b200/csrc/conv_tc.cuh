@@ -35,23 +35,27 @@ struct TcBuf {
   }
   size_t elems() const { return (size_t)n * chunks * plane() * 8; }
   size_t bytes() const { return elems() * sizeof(__nv_bfloat16); }
+  // multi-row TMA boxes of the last tiles of the last image read (and discard) up to 4 rows past the plane
+  static constexpr size_t kSlackBytes = 256 * 1024;
 };
 
-constexpr int TC_MAX_SEGS = 10;
-constexpr int TC_MAX_TAPS = 50;
+constexpr int TC_MAX_SEGS = 12;
 constexpr int TC_TILE_M = 128;
 
+// One TMA load of the producer = one "segment": `nrows` bands of 128 consecutive positions (one per kernel row ky,
+// `row pitch * dilation` positions apart, fetched by a single 4-D box) x all channel chunks of one source.
+// Shared-memory image of a segment: [chunk][row][128 positions][8 ch].  Every tap (row r, i-th kx of the segment) of the
+// segment is a shifted view of that image; offsets are affine, so the MMA issuer needs no per-tap table:
+//   A start (16 B units) = r * 128 + a0 + i * a_step          B start = b0 + r * b_row_step + i * b_step
 struct TcSeg {
-  int map;        // which tensor map (source)
-  int rel_start;  // start position of the 128-position band relative to the tile origin
-  int sub;        // sub-plane (s2d sources); 0 otherwise
-  int nchunks;    // channel chunks of this source
-  int tap_begin, tap_end;
-};
-
-struct TcTap {
-  int pix_off;   // shift (positions) inside the segment tile
-  int w_off;     // byte offset of this tap's weight slab [chunk][n_pad][8] in shared memory
+  int map;            // which tensor map (source)
+  int rel_start2;     // 2 * (start of row 0's band relative to the tile origin): tensor-map inner unit = 8 B
+  int c1;             // second box coordinate: sub-plane (s2d sources) or 0
+  int nchunks;        // channel chunks of this source
+  int nrows;          // kernel rows brought by this load
+  int ntaps;          // taps per row
+  uint32_t a0, a_step, b0, b_step, b_row_step;
+  uint32_t tx_bytes;  // bytes this load brings
 };
 
 enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2, TC_OUT_CHUNKED_S2D = 3 };
@@ -64,8 +68,7 @@ struct TcAux {  // optional bf16 side output of a head: one channel of a chunked
 struct TcParams {
   CUtensorMap maps[2];
   TcSeg segs[TC_MAX_SEGS];
-  TcTap taps[TC_MAX_TAPS];
-  int nseg, ntap;
+  int nseg;
   const void* w_packed;
   uint32_t w_bytes;
   const float* bias;  // [n_pad]
@@ -73,6 +76,7 @@ struct TcParams {
   int tile_adv;   // valid output positions per 128-row MMA tile (128 - widest tap shift)
   int tiles_per_image, total_tiles;
   int in_pitch, in_border, q_first;
+  unsigned long long pitch_magic;  // ceil(2^40 / in_pitch): q / in_pitch == (q * magic) >> 40 for q < 2^20
   int h_out, w_out;
   int act;
   int out_mode;
@@ -83,6 +87,7 @@ struct TcParams {
   TcAux aux0, aux1;
   uint32_t slot_bytes;
   int nslots;
+  long long* trace;  // debug event trace (device buffer of 12000 int64) or null
 };
 
 struct TcSource {
@@ -113,6 +118,7 @@ int tc_conv_pack_weights(TcConv& c, const float* w_eff_a, const float* bias_a, i
 void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act);
 void tc_conv_set_output_heads(TcConv& c, float* head0, float* head1, const TcAux* aux0, const TcAux* aux1);
 int tc_conv_launch(const TcConv& c, cudaStream_t st);
+void tc_set_trace(long long* dev_buf);  // debug: CTA 0 of every subsequent launch records its event timeline
 void tc_conv_free(TcConv& c);
 
 // fp32 NCHW <-> chunked bf16 converters (channel c of the source lands in chunk c/8, lane c%8)

@@ -10,8 +10,8 @@ namespace hv {
 
 static int alloc_buf(TcBuf& b, int n, int channels, int h, int w, int border, bool s2d, cudaStream_t st) {
   b.n = n; b.chunks = ((channels + 15) / 16) * 2; b.h = h; b.w = w; b.border = border; b.s2d = s2d;
-  HV_CUDA(cudaMallocAsync((void**)&b.ptr, b.bytes(), st));
-  HV_CUDA(cudaMemsetAsync(b.ptr, 0, b.bytes(), st));
+  HV_CUDA(cudaMallocAsync((void**)&b.ptr, b.bytes() + TcBuf::kSlackBytes, st));
+  HV_CUDA(cudaMemsetAsync(b.ptr, 0, b.bytes() + TcBuf::kSlackBytes, st));
   return HV_OK;
 }
 
@@ -82,4 +82,10 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
 extern "C" int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int up2_out,
                               hv_stream_t stream) {
   return hv::conv2d_bf16(d, w, bias, y, y2, up2_out, hv::as_stream(stream));
+}
+
+// debug hook (not part of the drop-in surface): dev_buf = 12000 int64 on the device, or NULL to switch tracing off
+extern "C" int hv_debug_conv_trace(void* dev_buf) {
+  hv::tc_set_trace(reinterpret_cast<long long*>(dev_buf));
+  return HV_OK;
 }

@@ -290,6 +290,7 @@ static int tc_plan_create(hv_generator* g) {
     b.s2d = (i == B_C1 || i == B_C3 || i == B_F1 || i == B_F3 || i == B_P1 || i == B_P3);
     total += (b.bytes() + 255) & ~(size_t)255;
   }
+  total += TcBuf::kSlackBytes;
   HV_CUDA(cudaMalloc((void**)&t->blob, total));
   HV_CUDA(cudaMemset(t->blob, 0, total));  // zero borders and padding channels, once
   size_t off = 0;

@@ -1,0 +1,57 @@
+"""Per-CTA event timeline of one tcgen05 conv layer (CTA 0): where do the producer / MMA issuer / epilogue wait?
+usage (GPU box): python tools/trace_conv.py <layer idx> [batch]"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import healthivert_gan_b200 as hv
+from healthivert_gan_b200 import _lib
+from oracle import synth
+
+
+def main():
+    layer = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 16
+    sd = synth.synthetic_generator_state_dict()
+    g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    g.load_state_dict(sd)
+    g = g.cuda().eval()
+    g.precision = "bf16"
+    x, mask, cam, ratio = (t.cuda() for t in synth.synthetic_slices(n, seed=1))
+    with torch.no_grad():
+        g(x, mask, cam, ratio)
+    L = _lib.lib()
+    L.hv_debug_conv_trace.argtypes = [ctypes.c_void_p]
+    for _ in range(2):
+        g.run_layer(layer, n)
+    torch.cuda.synchronize()
+    buf = torch.zeros(12000, dtype=torch.int64, device="cuda")
+    L.hv_debug_conv_trace(buf.data_ptr())
+    g.run_layer(layer, n)
+    torch.cuda.synchronize()
+    L.hv_debug_conv_trace(None)
+    b = buf.cpu().tolist()
+    ev = []
+    for base, who in ((0, "tma"), (4000, "mma"), (8000, "epi")):
+        for i in range(2000):
+            tag, clk = b[base + 2 * i], b[base + 2 * i + 1]
+            if tag == 0:
+                break
+            ev.append((clk, who, tag))
+    ev.sort()
+    t0 = ev[0][0]
+    names = {1: "tma issued", 10: "weights ready wait start", 11: "acc stage free", 12: "band full", 13: "band MMAs issued+commit",
+             20: "epi tile start", 21: "acc full"}
+    print(f"layer {layer} batch {n}: {len(ev)} events, span {ev[-1][0] - t0} cycles")
+    for clk, who, tag in ev[:140]:
+        print(f"{clk - t0:8d} {who} {names.get(tag, tag)}")
+    if len(ev) > 140:
+        print("...")
+        for clk, who, tag in ev[-30:]:
+            print(f"{clk - t0:8d} {who} {names.get(tag, tag)}")
+
+
+if __name__ == "__main__":
+    main()
