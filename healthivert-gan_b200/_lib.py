@@ -42,6 +42,8 @@ SIGNATURES = {
     "hv_ctx_attn_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "hv_ctx_attn_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                 c_float, c_int, c_int, c_void_p, c_void_p]),
+    "hv_ctx_attn_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     c_float, c_int, c_int, c_void_p]),
     "hv_stitch": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
                           c_int, c_int, c_int, c_void_p]),
     "hv_threshold": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_size_t, c_void_p]),

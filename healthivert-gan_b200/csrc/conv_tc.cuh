@@ -127,4 +127,9 @@ int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, c
 int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st);
 int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, cudaStream_t st);
 
+// contextual attention on tensor cores (ctx_attn_tc.cu): f and y are 64-channel 64x64 chunked buffers
+size_t ctx_attn_tc_workspace_bytes(int n);
+int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
+                    int per_sample_mask, void* workspace, cudaStream_t st);
+
 }  // namespace hv

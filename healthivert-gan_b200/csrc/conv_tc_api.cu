@@ -84,6 +84,32 @@ extern "C" int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float
   return hv::conv2d_bf16(d, w, bias, y, y2, up2_out, hv::as_stream(stream));
 }
 
+// bf16 tensor-core variant of hv_ctx_attn_fwd on fp32 NCHW tensors: pack -> ctx_attn_fwd_tc -> unpack
+extern "C" int hv_ctx_attn_fwd_bf16(const float* f, const float* mask, float* y, int32_t* offsets, float* flow, int n, int c,
+                                    int h, int w, float softmax_scale, int fuse, int per_sample_mask, hv_stream_t stream) {
+  using namespace hv;
+  cudaStream_t st = as_stream(stream);
+  HV_CHECK_ARG(f && mask && y, "ctx_attn_fwd_bf16: null argument");
+  HV_CHECK_ARG(c == 64 && h == 64 && w == 64 && n >= 1, "ctx_attn_fwd_bf16: built for [n,64,64,64] features (got c=%d h=%d w=%d)", c, h, w);
+  TcBuf fb, yb;
+  int rc = alloc_buf(fb, n, 64, 64, 64, 1, false, st);
+  if (rc) return rc;
+  rc = alloc_buf(yb, n, 64, 64, 64, 1, false, st);
+  if (rc) return rc;
+  rc = tc_pack_nchw(f, 64, HV_SRC_DIRECT, fb, 0, st);
+  if (rc) return rc;
+  void* ws = nullptr;
+  HV_CUDA(cudaMallocAsync(&ws, ctx_attn_tc_workspace_bytes(n), st));
+  rc = ctx_attn_fwd_tc(fb, mask, yb, offsets, flow, softmax_scale, fuse, per_sample_mask, ws, st);
+  if (rc) return rc;
+  rc = tc_unpack_nchw(yb, 0, 64, y, st);
+  if (rc) return rc;
+  HV_CUDA(cudaFreeAsync(ws, st));
+  HV_CUDA(cudaFreeAsync(fb.ptr, st));
+  HV_CUDA(cudaFreeAsync(yb.ptr, st));
+  return HV_OK;
+}
+
 // debug hook (not part of the drop-in surface): dev_buf = 12000 int64 on the device, or NULL to switch tracing off
 extern "C" int hv_debug_conv_trace(void* dev_buf) {
   hv::tc_set_trace(reinterpret_cast<long long*>(dev_buf));

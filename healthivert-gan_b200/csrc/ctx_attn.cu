@@ -263,60 +263,95 @@ static void make_wheel(unsigned char wheel[55][3]) {  // models/inpaint_tools.py
   for (int i = 0; i < MR; ++i) { wheel[col + i][2] = (unsigned char)(255 - 255 * i / MR); wheel[col + i][0] = 255; }
 }
 
-// one CTA per sample: offsets = argmax (row, col) - own (row, col); flow colour uses the running
-// maximum radius over samples 0..n (the reference carries maxrad across the batch).
-__global__ void __launch_bounds__(256) ca_offsets_flow_kernel(const int32_t* __restrict__ argmax,
-                                                              int32_t* __restrict__ offsets,
-                                                              float* __restrict__ flow, int side, int up) {
+// offsets = argmax (row, col) - own (row, col) (:368-374, :389-397); smax[n] = max squared offset length of sample n
+__global__ void __launch_bounds__(256) ca_offsets_kernel(const int32_t* __restrict__ argmax, int32_t* __restrict__ offsets,
+                                                         int* __restrict__ smax, int side) {
   const int L = side * side, n = blockIdx.x;
-  __shared__ int s_max[256];
+  __shared__ int s_max[8];
   int mx = 0;
-  for (int s = 0; s <= n; ++s)
-    for (int l = threadIdx.x; l < L; l += blockDim.x) {
-      const int am = argmax[(size_t)s * L + l];
-      const int du = am / side - l / side, dv = am % side - l % side;
-      mx = max(mx, du * du + dv * dv);
-    }
-  s_max[threadIdx.x] = mx;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) s_max[threadIdx.x] = max(s_max[threadIdx.x], s_max[threadIdx.x + o]);
-    __syncthreads();
-  }
-  const double maxrad = sqrt((double)s_max[0]) + 2.220446049250313e-16;
-  const int W = side * up;
   for (int l = threadIdx.x; l < L; l += blockDim.x) {
     const int am = argmax[(size_t)n * L + l];
     const int du = am / side - l / side, dv = am % side - l % side;
+    mx = max(mx, du * du + dv * dv);
     if (offsets) {
       offsets[((size_t)n * 2 + 0) * L + l] = du;
       offsets[((size_t)n * 2 + 1) * L + l] = dv;
     }
-    if (!flow) continue;
-    const double u = du / maxrad, v = dv / maxrad;
-    const double rad = sqrt(u * u + v * v);
-    const double a = atan2(-v, -u) / 3.141592653589793;
-    const double fk = (a + 1.0) / 2.0 * 54.0 + 1.0;
-    int k0 = (int)floor(fk), k1 = k0 + 1;
-    if (k1 == 56) k1 = 1;
-    const double fr = fk - k0;
-    for (int ch = 0; ch < 3; ++ch) {
-      const double c0 = c_wheel[k0 - 1][ch] / 255.0, c1 = c_wheel[k1 - 1][ch] / 255.0;
-      double col = (1.0 - fr) * c0 + fr * c1;
-      if (rad <= 1.0) col = 1.0 - rad * (1.0 - col); else col *= 0.75;
-      const float px = (float)(unsigned char)floor(255.0 * col) / 255.f;
-      const int y0 = (l / side) * up, x0 = (l % side) * up;
-      float* dst = flow + ((size_t)n * 3 + ch) * W * W;
-      for (int yy = 0; yy < up; ++yy)
-        for (int xx = 0; xx < up; ++xx) dst[(size_t)(y0 + yy) * W + x0 + xx] = px;
-    }
   }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) mx = max(mx, s_max[i]);
+    smax[n] = mx;
+  }
+}
+
+// flow colouring (models/inpaint_tools.py:73-100,:178-208): the reference carries the maximum radius across the
+// batch (maxrad of sample n = max over samples 0..n).  One thread = (cell, channel, pixel row of the up x up block).
+__global__ void __launch_bounds__(256) ca_flow_kernel(const int32_t* __restrict__ argmax, const int* __restrict__ smax,
+                                                      float* __restrict__ flow, int side, int up) {
+  const int L = side * side, n = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= L * 3 * up) return;
+  const int yy = i % up, ch = (i / up) % 3, l = i / (3 * up);
+  int m2 = 0;
+  for (int s = 0; s <= n; ++s) m2 = max(m2, smax[s]);
+  const double maxrad = sqrt((double)m2) + 2.220446049250313e-16;
+  const int am = argmax[(size_t)n * L + l];
+  const int du = am / side - l / side, dv = am % side - l % side;
+  const double u = du / maxrad, v = dv / maxrad;
+  const double rad = sqrt(u * u + v * v);
+  const double a = atan2(-v, -u) / 3.141592653589793;
+  const double fk = (a + 1.0) / 2.0 * 54.0 + 1.0;
+  int k0 = (int)floor(fk), k1 = k0 + 1;
+  if (k1 == 56) k1 = 1;
+  const double fr = fk - k0;
+  const double c0 = c_wheel[k0 - 1][ch] / 255.0, c1 = c_wheel[k1 - 1][ch] / 255.0;
+  double col = (1.0 - fr) * c0 + fr * c1;
+  if (rad <= 1.0) col = 1.0 - rad * (1.0 - col); else col *= 0.75;
+  const float px = (float)(unsigned char)floor(255.0 * col) / 255.f;
+  const int W = side * up;
+  float* dst = flow + (((size_t)n * 3 + ch) * W + (size_t)(l / side) * up + yy) * W + (size_t)(l % side) * up;
+  for (int xx = 0; xx < up; ++xx) dst[xx] = px;
+}
+
+static int ensure_wheel() {
+  if (!g_wheel_ready) {
+    unsigned char wheel[55][3];
+    make_wheel(wheel);
+    HV_CUDA(cudaMemcpyToSymbol(c_wheel, wheel, sizeof(wheel)));
+    g_wheel_ready = true;
+  }
+  return HV_OK;
+}
+
+// scratch: n ints
+int ca_offsets_flow_launch(const int32_t* argmax, int32_t* offsets, float* flow, int n, int side, int up, int* scratch,
+                           cudaStream_t st) {
+  int rc = ensure_wheel();
+  if (rc) return rc;
+  ca_offsets_kernel<<<n, 256, 0, st>>>(argmax, offsets, scratch, side);
+  HV_LAUNCH_CHECK();
+  if (flow) {
+    ca_flow_kernel<<<dim3((side * side * 3 * up + 255) / 256, n), 256, 0, st>>>(argmax, scratch, flow, side, up);
+    HV_LAUNCH_CHECK();
+  }
+  return HV_OK;
+}
+
+int ca_mask_launch(const float* mask, float* mm, int n, int side, int mh, int mw, int per_sample, cudaStream_t st) {
+  ca_mask_kernel<<<(n * side * side + 255) / 256, 256, 0, st>>>(mask, mm, n, side, side, mh, mw, mh / side, per_sample);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
 }
 
 // ------------------------------------------------------------------ host orchestration
 struct CaWorkspace {
   float *P, *R, *inv_norm, *mm, *S, *U, *cols;
   int32_t* argmax;
+  int* scratch;
 };
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -334,6 +369,7 @@ static size_t ca_layout(int n, int c, int h, int w, char* base, CaWorkspace* ws)
   p = take(sizeof(float) * n * L * L);      if (ws) ws->U = (float*)p;
   p = take(sizeof(float) * n * L * c * 16); if (ws) ws->cols = (float*)p;
   p = take(sizeof(int32_t) * n * L);        if (ws) ws->argmax = (int32_t*)p;
+  p = take(sizeof(int) * (n + 1));          if (ws) ws->scratch = (int*)p;
   return off;
 }
 
@@ -348,12 +384,6 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
   HV_CHECK_ARG(L % 128 == 0 && c % 8 == 0, "ctx_attn_fwd: needs (h/2)^2 %% 128 == 0 and c %% 8 == 0");
   CaWorkspace ws;
   ca_layout(n, c, h, w, (char*)workspace, &ws);
-  if (!g_wheel_ready) {
-    unsigned char wheel[55][3];
-    make_wheel(wheel);
-    HV_CUDA(cudaMemcpyToSymbol(c_wheel, wheel, sizeof(wheel)));
-    g_wheel_ready = true;
-  }
   ca_patches_kernel<<<dim3(L, n), 256, 0, st>>>(f, ws.P, ws.R, ws.inv_norm, c, h, w);
   HV_LAUNCH_CHECK();
   ca_mask_kernel<<<(n * L + 255) / 256, 256, 0, st>>>(mask, ws.mm, n, side, side, 4 * h, 4 * w, 8, per_sample_mask);
@@ -377,8 +407,8 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
   ca_fold_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(ws.cols, y, c, h, w);
   HV_LAUNCH_CHECK();
   if (offsets || flow) {
-    ca_offsets_flow_kernel<<<n, 256, 0, st>>>(ws.argmax, offsets, flow, side, 8);
-    HV_LAUNCH_CHECK();
+    rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, side, 8, ws.scratch, st);
+    if (rc) return rc;
   }
   return HV_OK;
 }

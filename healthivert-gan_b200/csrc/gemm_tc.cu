@@ -1,0 +1,235 @@
+// Batched bf16 "NT" GEMM on the 5th-generation tensor cores:  C[b][m][n] = sum_k A[b][m][k] * B[b][n][k]
+// (both operands K-major = row-major [rows][K]), fp32 accumulation in TMEM.
+//
+// It carries the two dense contractions of the contextual-attention module (reference
+// models/inpaint_networks.py:347-348 foreground-background similarity, :377-379 patch paste) in bf16 mode:
+//   scores  T[f][b]   = sum_k P[f][k] P[b][k] * inv_norm[b]          (M = N = 1024, K = 576, fp32 out, column scale)
+//   paste   cols[ck][f] = sum_b Rt[ck][b] A[f][b]                     (M = N = K = 1024, bf16 out)
+//
+// Kernel structure (persistent, one CTA per SM, 192 threads):
+//   warp 0    : TMA producer, 128B-swizzled [rows][64] boxes of A and B into a 6-stage ring
+//   warp 1    : TMEM allocator + tcgen05.mma issuer (M = 128, N = BN, K = 16; 4 MMAs per stage), peeks the next
+//               stage's mbarrier before issuing so that the wait latency hides under the queued MMAs
+//   warps 2-5 : epilogue, one TMEM lane quadrant each; accumulators are ring-buffered in all 512 TMEM columns
+#include <cuda_bf16.h>
+#include "hv_common.cuh"
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace hv {
+
+constexpr int G_BM = 128, G_BK = 64, G_STAGES = 6, G_TMEM_COLS = 512;
+
+struct GemmParams {
+  CUtensorMap map_a, map_b;
+  void* c;                  // fp32 or bf16 [batch][M][N]
+  const float* colscale;    // [batch][N] or null
+  int M, N, K, batch;
+  int tiles_m, tiles_n, total_tiles, kblocks;
+};
+
+template <int BN, bool OUT_BF16>
+__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int ACC_STAGES = G_TMEM_COLS / BN;
+  constexpr uint32_t A_BYTES = G_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)G_STAGES * STAGE_BYTES);
+  const uint32_t bar_full = smem_u32(bars);
+  const uint32_t bar_empty = bar_full + 8u * G_STAGES;
+  const uint32_t bar_tfull = bar_empty + 8u * G_STAGES;
+  const uint32_t bar_tempty = bar_tfull + 8u * ACC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * G_STAGES + 2 * ACC_STAGES);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&p.map_b) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < G_STAGES; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
+      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 128); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(G_TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int tiles_per_batch = p.tiles_m * p.tiles_n;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const bool leader = elect_one();
+    int slot = 0;
+    uint32_t phase = 0;
+    const uint32_t ring = smem_u32(smem);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+        if (leader) {
+          const uint32_t fb = bar_full + 8u * slot, dst = ring + (uint32_t)slot * STAGE_BYTES;
+          mbar_expect_tx(fb, STAGE_BYTES);
+          tma_load_3d(dst, &p.map_a, fb, kb * G_BK, mt * G_BM, b);
+          tma_load_3d(dst + A_BYTES, &p.map_b, fb, kb * G_BK, nt * BN, b);
+        }
+        if (++slot == G_STAGES) { slot = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t ring_lo = kDescLoSw128 + (smem_u32(smem) >> 4);
+    int slot = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    bool ready = mbar_peek(bar_full, 0);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait_peeked(ready, bar_full + 8u * slot, phase);
+        tc_fence_after();
+        const uint32_t a_lo = ring_lo + (uint32_t)slot * (STAGE_BYTES >> 4);
+        const uint32_t b_lo = a_lo + (A_BYTES >> 4);
+        const uint32_t cur_empty = bar_empty + 8u * slot;
+        if (++slot == G_STAGES) { slot = 0; phase ^= 1u; }
+        ready = mbar_peek(bar_full + 8u * slot, phase);  // next stage (possibly of the next tile)
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < G_BK / 16; ++ks)  // 32 B per K step inside the 128 B swizzle row
+            umma_bf16(d_tmem, ((uint64_t)kDescHiSw128 << 32) | (a_lo + 2u * ks), ((uint64_t)kDescHiSw128 << 32) | (b_lo + 2u * ks),
+                      idesc, (kb | ks) != 0 ? 1u : 0u);
+          umma_commit(cur_empty);
+        }
+      }
+      if (leader) umma_commit(bar_tfull + 8u * acc);
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
+      const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
+      const size_t out_row = ((size_t)b * p.M + (size_t)mt * G_BM + row) * p.N + (size_t)nt * BN;
+      const float* cs = p.colscale ? p.colscale + (size_t)b * p.N + (size_t)nt * BN : nullptr;
+      mbar_wait(bar_tfull + 8u * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tmem_ld<32>(t_addr + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 == BN) {  // all columns of this accumulator stage are in registers
+          tc_fence_before();
+          mbar_arrive(bar_tempty + 8u * acc);
+        }
+        if (cs) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + c0 + j);
+        }
+        if (OUT_BF16) {
+          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row + c0;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(out)[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+          float* out = reinterpret_cast<float*>(p.c) + out_row + c0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+      }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G_TMEM_COLS) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled gemm_get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int batch, long long batch_stride_elems, int box_rows) {
+  PFN_encodeTiled enc = gemm_get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return HV_ERR_CUDA; }
+  cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
+  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)batch_stride_elems * 2};
+  cuuint32_t box[3] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (gemm operand) failed with CUresult %d", (int)r); return HV_ERR_CUDA; }
+  return HV_OK;
+}
+
+template <int BN, bool OUT_BF16>
+static int gemm_launch(const GemmParams& p, int grid, cudaStream_t st) {
+  constexpr size_t smem = (size_t)G_STAGES * (G_BM * 128 + BN * 128) + 256;
+  static bool configured = false;
+  if (!configured) {
+    HV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  gemm_tc_kernel<BN, OUT_BF16><<<grid, 192, smem, st>>>(p);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const float* colscale, int M, int N, int K, int batch,
+               long long strideA, long long strideB, int out_bf16, cudaStream_t st) {
+  HV_CHECK_ARG(A && B && C, "gemm_tc: null argument");
+  HV_CHECK_ARG(M % G_BM == 0 && N % 128 == 0 && K % G_BK == 0 && batch >= 1, "gemm_tc: M %% 128, N %% 128, K %% 64 must be 0 (got %d,%d,%d)", M, N, K);
+  GemmParams p;
+  int rc = gemm_map(&p.map_a, A, M, K, batch, strideA, G_BM);
+  if (rc) return rc;
+  rc = gemm_map(&p.map_b, B, N, K, batch, strideB, 128);
+  if (rc) return rc;
+  p.c = C; p.colscale = colscale; p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.tiles_m = M / G_BM; p.tiles_n = N / 128; p.total_tiles = p.tiles_m * p.tiles_n * batch; p.kblocks = K / G_BK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  return out_bf16 ? gemm_launch<128, true>(p, grid, st) : gemm_launch<128, false>(p, grid, st);
+}
+
+}  // namespace hv

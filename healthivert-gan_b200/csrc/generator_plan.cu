@@ -259,7 +259,7 @@ struct TcPlan {
   bool has[kNumLayers] = {};
   int out_buf[kNumLayers];
   bool out_up2[kNumLayers] = {};
-  float* pm6_f32 = nullptr;  // attention bridge (fp32 NCHW)
+  void* ca_ws = nullptr;     // workspace of the tensor-core attention
   __nv_bfloat16* blob = nullptr;
 };
 
@@ -273,7 +273,7 @@ static TcAux make_aux(const TcBuf& b, int channel) {
 static void tc_plan_destroy(hv_generator* g) {
   if (!g->tc) return;
   for (int i = 0; i < kNumLayers; ++i) if (g->tc->has[i]) tc_conv_free(g->tc->conv[i]);
-  cudaFree(g->tc->blob); cudaFree(g->tc->pm6_f32);
+  cudaFree(g->tc->blob); cudaFree(g->tc->ca_ws);
   delete g->tc;
   g->tc = nullptr;
 }
@@ -298,7 +298,7 @@ static int tc_plan_create(hv_generator* g) {
     t->buf[i].ptr = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(t->blob) + off);
     off += (t->buf[i].bytes() + 255) & ~(size_t)255;
   }
-  HV_CUDA(cudaMalloc((void**)&t->pm6_f32, (size_t)n * 64 * 64 * 64 * sizeof(float)));
+  HV_CUDA(cudaMalloc(&t->ca_ws, ctx_attn_tc_workspace_bytes(n)));
   for (int i = 0; i < kNumLayers; ++i) t->out_buf[i] = -1;
   for (int i = 0; i < kNumTcLayers; ++i) {
     const TcLayerSpec& s = kTcLayers[i];
@@ -376,9 +376,7 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
   HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
   cudaStream_t sa = g->side;
   for (int l : {PM1, PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
-  RC(tc_unpack_nchw(view(B_P6), 0, 64, t->pm6_f32, sa));
-  RC(ctx_attn_fwd_fp32(t->pm6_f32, mask, g->ca_out, offsets, flow, n, 64, 64, 64, 10.f, 1, per_sample_mask, g->ca_ws, sa));
-  RC(tc_pack_nchw(g->ca_out, 64, HV_SRC_DIRECT, view(B_CA), 0, sa));
+  RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa));
   RC(run(PM9, sa));
   RC(run(PM10, sa));
   HV_CUDA(cudaEventRecord(g->ev_join, sa));
@@ -452,8 +450,10 @@ int hv_generator_create(hv_generator** out, int max_batch, int precision) {
     if (precision == HV_PREC_BF16) continue;                     // bf16 plan keeps chunked bf16 activations
     GEN_TRY(cudaMalloc(&g->act[i], act_elems(i, max_batch) * sizeof(float)));
   }
-  GEN_TRY(cudaMalloc(&g->ca_out, (size_t)max_batch * 64 * 64 * 64 * sizeof(float)));
-  GEN_TRY(cudaMalloc(&g->ca_ws, ctx_attn_workspace_bytes(max_batch, 64, 64, 64)));
+  if (precision == HV_PREC_FP32) {
+    GEN_TRY(cudaMalloc(&g->ca_out, (size_t)max_batch * 64 * 64 * 64 * sizeof(float)));
+    GEN_TRY(cudaMalloc(&g->ca_ws, ctx_attn_workspace_bytes(max_batch, 64, 64, 64)));
+  }
   GEN_TRY(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
@@ -534,6 +534,13 @@ long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_
   HV_CHECK_ARG(g->last_n > 0, "generator_read_tap: no forward has run");
   const float* src = nullptr;
   size_t count = 0;
+  if (idx == kTapAttention && g->tc) {
+    TcBuf v = g->tc->buf[B_CA];
+    v.n = g->last_n;
+    int rc = tc_unpack_nchw(v, 0, 64, out, as_stream(stream));
+    if (rc) return rc;
+    return (long long)g->last_n * 64 * 64 * 64;
+  }
   if (idx == kTapAttention) { src = g->ca_out; count = (size_t)g->last_n * 64 * 64 * 64; }
   else {
     HV_CHECK_ARG(idx >= 0 && idx < kNumLayers, "generator_read_tap: index %d out of range", idx);

@@ -268,6 +268,7 @@ class ContextualAttention(nn.Module):
         self.ksize, self.stride, self.rate, self.fuse_k = ksize, stride, rate, fuse_k
         self.softmax_scale, self.fuse, self.use_cuda = softmax_scale, fuse, use_cuda
         self.per_sample_mask = False  # False == the reference (mask of sample 0 for the whole batch)
+        self.precision = "fp32"       # 'bf16': similarity / paste contractions on tcgen05 (hv_ctx_attn_fwd_bf16)
         self.last_offsets = None
 
     def forward(self, f, b, mask=None):
@@ -284,10 +285,15 @@ class ContextualAttention(nn.Module):
         offsets = torch.empty(n, 2, h // 2, w // 2, device=f.device, dtype=torch.int32)
         flow = torch.empty(n, 3, 4 * h, 4 * w, device=f.device, dtype=torch.float32)
         L = _lib.lib()
-        ws = torch.empty(L.hv_ctx_attn_workspace_bytes(n, c, h, w), device=f.device, dtype=torch.uint8)
-        check(L.hv_ctx_attn_fwd(ptr(f), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w,
-                                float(self.softmax_scale), int(bool(self.fuse)), int(self.per_sample_mask), ptr(ws),
-                                _lib.stream()))
+        if self.precision == "bf16":
+            check(L.hv_ctx_attn_fwd_bf16(ptr(f), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w,
+                                         float(self.softmax_scale), int(bool(self.fuse)), int(self.per_sample_mask),
+                                         _lib.stream()))
+        else:
+            ws = torch.empty(L.hv_ctx_attn_workspace_bytes(n, c, h, w), device=f.device, dtype=torch.uint8)
+            check(L.hv_ctx_attn_fwd(ptr(f), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w,
+                                    float(self.softmax_scale), int(bool(self.fuse)), int(self.per_sample_mask), ptr(ws),
+                                    _lib.stream()))
         self.last_offsets = offsets
         return y, flow
 

@@ -102,6 +102,12 @@ int hv_ctx_attn_fwd(const float* f, const float* mask, float* y, int32_t* offset
                     int n, int c, int h, int w, float softmax_scale, int fuse,
                     int per_sample_mask, void* workspace, hv_stream_t stream);
 
+/* bf16 tensor-core variant (tcgen05 similarity and paste contractions, fused fuse+softmax): same arguments, c = h = w = 64;
+ * the workspace is taken from the stream-ordered allocator.                                                   */
+int hv_ctx_attn_fwd_bf16(const float* f, const float* mask, float* y, int32_t* offsets, float* flow,
+                         int n, int c, int h, int w, float softmax_scale, int fuse,
+                         int per_sample_mask, hv_stream_t stream);
+
 /* ---- A4: threshold + height-adaptive stitch -------------------------------------------
  * replaces models/pix2pix_model.py:201-252 and eval_3d_sagittal_twostage.py:103-118.
  * For sample i: pred = ceil(pred_h[i]*maxheight); hgt = max(pred, height[i]);

@@ -115,6 +115,32 @@ def test_contextual_attention_against_oracle():
     assert float((y3.cpu() - y3_ref).abs().max()) <= 1e-4
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_contextual_attention_bf16_tensor_core_path(fuse):
+    """tcgen05 similarity/paste GEMMs + fused fuse/softmax vs the fp32 oracle on bf16-representable features."""
+    g = torch.Generator().manual_seed(5)
+    f = torch.relu(torch.randn(3, 64, 64, 64, generator=g)).to(torch.bfloat16).float()
+    mask = torch.zeros(3, 1, 256, 256)
+    mask[0, :, 100:141] = 1
+    mask[1, :, 30:71] = 1
+    mask[2, :, 180:221] = 1
+    ca = hv.ContextualAttention(True, ksize=3, stride=1, rate=2, fuse_k=3, softmax_scale=10, fuse=fuse)
+    ca.precision = "bf16"
+    ca.per_sample_mask = True
+    fc = f.cuda()
+    y, flow = ca(fc, fc, mask.cuda())
+    torch.cuda.synchronize()
+    agree = []
+    for i in range(3):
+        yi, oi = gr.contextual_attention(f[i:i + 1], mask[i:i + 1], fuse=fuse)
+        err = float((y[i:i + 1].cpu() - yi).abs().max())
+        scale = float(yi.abs().max())
+        assert err <= 0.02 * scale + 1e-3, (i, err, scale)   # bf16 attention weights and bf16 output rounding
+        agree.append((ca.last_offsets[i:i + 1].cpu().long() == oi).float().mean().item())
+    assert min(agree) >= 0.98, agree
+    assert flow.shape == (3, 3, 256, 256) and float(flow.min()) >= 0.0 and float(flow.max()) <= 1.0
+
+
 def test_threshold_and_stitch_bit_exact():
     rng = np.random.Generator(np.random.PCG64(11))
     n = 6
