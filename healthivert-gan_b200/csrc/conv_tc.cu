@@ -81,18 +81,25 @@ __device__ __forceinline__ void issue_segment_generic(bool leader, uint32_t d_tm
 }
 
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_BAR_BYTES = 512;
-__host__ __device__ constexpr int tc_epi_warps(int n_pad) { return n_pad == 16 ? 8 : 16; }
+constexpr int TC_BAR_BYTES = 1024;  // mbarriers + TMEM slot + bias vector
+// 16 epilogue warps, 16 accumulator columns each: N_PAD/16*4 warps cover one tile (4 TMEM lane quadrants x column groups), so
+// 16/that many tiles are in the epilogue concurrently (4 / 2 / 1 for N_PAD = 16 / 32 / 64); group g owns tiles j % groups == g
+__host__ __device__ constexpr int tc_epi_warps(int) { return 16; }
+__host__ __device__ constexpr int tc_warps_per_tile(int n_pad) { return n_pad / 16 * 4; }
 __host__ __device__ constexpr int tc_threads(int n_pad) { return 64 + 32 * tc_epi_warps(n_pad); }
 __host__ __device__ constexpr int tc_acc_stages(int n_pad) { return TC_TMEM_COLS / n_pad > 8 ? 8 : TC_TMEM_COLS / n_pad; }
 
 // ------------------------------------------------------------------------------------------- kernel
-// warp 0: TMA producer, warp 1: TMEM allocator + MMA issuer, warps 2..: epilogue (4 lane quadrants x column groups)
+// warps 0..15: epilogue, warp 16: TMA producer, warp 17: TMEM allocator + MMA issuer.  The single-lane roles sit on the
+// HIGHEST warp ids on purpose: the SM's warp arbiter favours high warp ids, and an issuer starved by busy epilogue warps
+// stalls the tensor pipe.
 template <int N_PAD, int ACT>
 __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ACC_STAGES = tc_acc_stages(N_PAD);       // accumulator tiles in flight
   constexpr int EPI_WARPS = tc_epi_warps(N_PAD);
-  constexpr int NCOL = N_PAD / (EPI_WARPS / 4);          // columns per epilogue warp (8 or 16)
+  constexpr int WPT = tc_warps_per_tile(N_PAD), GROUPS = EPI_WARPS / WPT;
+  constexpr int NCOL = 16;                               // accumulator columns per epilogue warp
+  constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_region = (p.w_bytes + 127u) & ~127u;
@@ -105,16 +112,17 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
   const uint32_t bar_tfull = bar_w + 8u;
   const uint32_t bar_tempty = bar_tfull + 8u * ACC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 1 + 2 * ACC_STAGES);
+  float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_PRODUCER && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[1]) : "memory");
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     if (lane == 0) {
       for (int i = 0; i < p.nslots; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
       mbar_init(bar_w, 1);
-      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * EPI_WARPS); }
+      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * WPT); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -123,12 +131,13 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (threadIdx.x < N_PAD) s_bias[threadIdx.x] = __ldg(p.bias + threadIdx.x);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == W_PRODUCER) {
     // ===================================================================== TMA producer (warp-uniform, one lane issues)
     const bool leader = elect_one();
     if (leader) {
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
         if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // ===================================================================== MMA issuer (warp-uniform, one lane issues)
     const bool leader = elect_one();
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
@@ -169,21 +178,33 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
     int slot = 0, acc = 0, ntr = 0;
     long long* tr = p.trace ? p.trace + 4000 : nullptr;
     uint32_t phase = 0, acc_phase = 0;
+    // peek-ahead: the next barrier is probed BEFORE the current batch of MMAs is issued, so the probe latency
+    // hides under the queued MMAs (the tensor pipe accepts only a few MMAs ahead of execution)
+    bool ready_full = mbar_peek(bar_full, 0), ready_acc = mbar_peek(bar_tempty, 1);
+    const int nseg = p.nseg;
+    TcSeg sg = p.segs[0];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
+      mbar_wait_peeked(ready_acc, bar_tempty + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
       if (leader) trace_ev(tr, ntr, 11);
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_PAD);
+      const uint32_t cur_tfull = bar_tfull + 8u * acc;
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
       uint32_t accumulate = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const int nrows = p.segs[s].nrows, ntaps = p.segs[s].ntaps, ksteps = p.segs[s].nchunks >> 1;
+      for (int s = 0; s < nseg; ++s) {
+        if (nseg > 1) sg = p.segs[s];  // single-segment layers keep the descriptor recipe in registers
+        const int nrows = sg.nrows, ntaps = sg.ntaps, ksteps = sg.nchunks >> 1;
         const uint32_t a_lbo = (uint32_t)nrows * TC_TILE_M;  // 16 B units: K chunks of the segment image are nrows bands apart
-        const uint32_t a_step = p.segs[s].a_step, b_step = p.segs[s].b_step, b_row_step = p.segs[s].b_row_step;
-        const uint32_t a_row = a_lo_base + (uint32_t)slot * slot_units + (a_lbo << 16) + p.segs[s].a0;
-        const uint32_t b_row = b_lo_base + p.segs[s].b0;
-        mbar_wait(bar_full + 8u * slot, phase);
+        const uint32_t a_step = sg.a_step, b_step = sg.b_step, b_row_step = sg.b_row_step;
+        const uint32_t a_row = a_lo_base + (uint32_t)slot * slot_units + (a_lbo << 16) + sg.a0;
+        const uint32_t b_row = b_lo_base + sg.b0;
+        mbar_wait_peeked(ready_full, bar_full + 8u * slot, phase);
         tc_fence_after();
         if (leader) trace_ev(tr, ntr, 12);
+        const uint32_t cur_empty = bar_empty + 8u * slot;
+        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        ready_full = mbar_peek(bar_full + 8u * slot, phase);
+        if (s == nseg - 1) ready_acc = mbar_peek(bar_tempty + 8u * acc, acc_phase ^ 1u);
         const int shape = (nrows << 8) | (ntaps << 4) | ksteps;
 #define HV_SEG(R, T, K)                                                                                                   \
   case ((R) << 8) | ((T) << 4) | (K):                                                                                     \
@@ -198,49 +219,47 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
         }
 #undef HV_SEG
         accumulate = 1;
-        if (leader) { umma_commit(bar_empty + 8u * slot); trace_ev(tr, ntr, 13); }  // slot is free once these MMAs have read it
-        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }  // slot is free once these MMAs have read it
       }
-      if (leader) umma_commit(bar_tfull + 8u * acc);  // accumulator tile complete -> epilogue
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      if (leader) umma_commit(cur_tfull);  // accumulator tile complete -> epilogue
     }
     __syncwarp();
   } else {
-    // ===================================================================== epilogue (warps 2 .. 2 + EPI_WARPS)
+    // ===================================================================== epilogue (warps 0 .. 15)
+    // group g owns the CTA's tiles j = g, g + GROUPS, ...; inside a group a warp reads TMEM lane quadrant warp % 4 and one
+    // 16-column slice.  With GROUPS tiles in flight the per-tile latency (tcgen05.ld -> math -> stores) is off the critical path.
     const int quad = warp & 3;               // TMEM lane quadrant this warp may access
-    const int group = (warp - 2) >> 2;       // which NCOL-wide column group
-    const int col0 = group * NCOL;
-    float bias_r[NCOL];
-#pragma unroll
-    for (int i = 0; i < NCOL; ++i) bias_r[i] = __ldg(p.bias + col0 + i);
-    int acc = 0, ntr = 0;
-    long long* tr = (p.trace && warp == 2 && lane == 0) ? p.trace + 8000 : nullptr;
-    uint32_t acc_phase = 0;
+    const int group = warp / WPT;
+    const int col0 = ((warp % WPT) >> 2) * NCOL;
+    int ntr = 0;
+    long long* tr = (p.trace && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
     const int m = quad * 32 + lane;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int j = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
+      if (j % GROUPS != group) continue;
+      const int acc = j % ACC_STAGES;
+      const uint32_t acc_phase = (uint32_t)(j / ACC_STAGES) & 1u;
       const int img = tile / p.tiles_per_image;
       const int q = (tile - img * p.tiles_per_image) * p.tile_adv + m + p.q_first;
       const int qrow = (int)(((unsigned long long)q * p.pitch_magic) >> 40);
       const int yy = qrow - p.in_border;
       const int xx = q - qrow * p.in_pitch - p.in_border;
+      // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
+      const bool valid = m < p.tile_adv && yy >= 0 && yy < p.h_out && xx >= 0 && xx < p.w_out;
       trace_ev(tr, ntr, 20);
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
       trace_ev(tr, ntr, 21);
-      float v[NCOL];
-      tmem_ld<NCOL>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD + col0), v);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive(bar_tempty + 8u * acc);  // accumulator stage may be overwritten by a later tile
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
-
-      // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
-      if (m >= p.tile_adv || yy < 0 || yy >= p.h_out || xx < 0 || xx >= p.w_out) continue;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD);
 
       if (p.out_mode == TC_OUT_HEADS) {
-        if (group != 0) continue;
-        const float a0 = fminf(fmaxf(v[0] + bias_r[0], -1.f), 1.f);
-        const float a1 = 1.f / (1.f + __expf(-(v[1] + bias_r[1])));
+        float v[NCOL];
+        if (col0 == 0) { tmem_ld<NCOL>(t_addr, v); tmem_ld_wait(); }
+        tc_fence_before();
+        mbar_arrive(bar_tempty + 8u * acc);
+        if (!valid || col0 != 0) continue;
+        const float a0 = fminf(fmaxf(v[0] + s_bias[0], -1.f), 1.f);
+        const float a1 = 1.f / (1.f + __expf(-(v[1] + s_bias[1])));
         const size_t pix = ((size_t)img * p.h_out + yy) * p.w_out + xx;
         p.head0[pix] = a0;
         p.head1[pix] = a1;
@@ -259,32 +278,39 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
       else if (p.out_mode == TC_OUT_CHUNKED_S2D)  // consumer is a stride-2 conv: scatter by pixel parity
         pos = (size_t)((yy & 1) * 2 + (xx & 1)) * p.out_sub_plane + (size_t)((yy >> 1) + p.out_border) * p.out_pitch + (xx >> 1) + p.out_border;
       else pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
+      __nv_bfloat16* out0 = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off) * p.out_plane * 8 + pos * 8;
+      float v[NCOL];
+      tmem_ld<NCOL>(t_addr + col0, v);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(bar_tempty + 8u * acc);  // this warp's slice is in registers: release its share of the TMEM stage
+      if (!valid) continue;
 #pragma unroll
-      for (int j = 0; j < NCOL / 8; ++j) {
-        const int c = group * (NCOL / 8) + j;
+      for (int jj = 0; jj < NCOL / 8; ++jj) {
+        const int c = col0 / 8 + jj;
         if (c >= p.out_nchunks) break;
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float f0 = act_fast<ACT>(v[j * 8 + 2 * e] + bias_r[j * 8 + 2 * e], p.act);
-          const float f1 = act_fast<ACT>(v[j * 8 + 2 * e + 1] + bias_r[j * 8 + 2 * e + 1], p.act);
+          const float f0 = act_fast<ACT>(v[jj * 8 + 2 * e] + s_bias[col0 + jj * 8 + 2 * e], p.act);
+          const float f1 = act_fast<ACT>(v[jj * 8 + 2 * e + 1] + s_bias[col0 + jj * 8 + 2 * e + 1], p.act);
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
           pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        __nv_bfloat16* plane = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off + c) * p.out_plane * 8;
-        *reinterpret_cast<uint4*>(plane + pos * 8) = val;
+        __nv_bfloat16* plane = out0 + (size_t)c * p.out_plane * 8;
+        *reinterpret_cast<uint4*>(plane) = val;
         if (p.out_mode == TC_OUT_CHUNKED_UP2) {  // nearest x2 upsample fused into the store (inpaint_networks.py:97,:105,:219,:222)
-          *reinterpret_cast<uint4*>(plane + (pos + 1) * 8) = val;
-          *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch) * 8) = val;
-          *reinterpret_cast<uint4*>(plane + (pos + p.out_pitch + 1) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + 8) = val;
+          *reinterpret_cast<uint4*>(plane + (size_t)p.out_pitch * 8) = val;
+          *reinterpret_cast<uint4*>(plane + (size_t)(p.out_pitch + 1) * 8) = val;
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
   }
@@ -321,7 +347,7 @@ static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks, int k, int
   const CUtensorMapDataType types[2] = {CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64};
   for (int attempt = 0; attempt < 2; ++attempt) {
     cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, b.s2d ? 4u : (cuuint64_t)k, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-    cuuint64_t strides[3] = {b.s2d ? sub_b : (cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.chunks};
+    cuuint64_t strides[3] = {b.s2d ? sub_b : (cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.image_chunks()};
     cuuint32_t box[4] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -351,7 +377,8 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
                  "tc_conv: concat sources must share geometry");
     HV_CHECK_ARG(b.s2d == (stride == 2), "tc_conv: a stride-2 conv reads a space-to-depth buffer (and only it does)");
     HV_CHECK_ARG(b.border >= (stride == 2 ? 1 : half * dil), "tc_conv: source border %d smaller than the conv padding", b.border);
-    HV_CHECK_ARG(srcs[i].real_channels <= b.chunks * 8, "tc_conv: real_channels > buffer channels");
+    HV_CHECK_ARG(srcs[i].real_channels * (srcs[i].kxpack ? k : 1) <= b.chunks * 8, "tc_conv: real_channels > buffer channels");
+    HV_CHECK_ARG(!srcs[i].kxpack || stride == 1, "tc_conv: kx-packed sources feed stride-1 convs only");
     max_chunks = max(max_chunks, b.chunks);
     total_chunks += b.chunks;
   }
@@ -365,7 +392,8 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.pitch_magic = ((1ull << 40) + (unsigned long long)pitch - 1) / (unsigned long long)pitch;
   p.h_out = b0.sub_h(); p.w_out = b0.sub_w();
   p.q_first = b0.border * pitch + b0.border;
-  p.w_bytes = (uint32_t)(k * k * total_chunks * c.n_pad * 16);
+  p.w_bytes = 0;
+  for (int i = 0; i < nsrc; ++i) p.w_bytes += (uint32_t)((srcs[i].kxpack ? k : k * k) * srcs[i].buf.chunks * c.n_pad * 16);
   const size_t budget = 227 * 1024 - 2048;
   const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
   // all k kernel rows of a source in one TMA load when at least 3 such slots fit beside the weights
@@ -380,15 +408,17 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     const int nch = srcs[s].buf.chunks;
     const uint32_t slab = (uint32_t)nch * c.n_pad;  // one tap's weights, 16 B units
     if (stride == 1) {
-      max_shift = (k - 1) * dil;
+      const bool kxp = srcs[s].kxpack;
+      if (!kxp) max_shift = max(max_shift, (k - 1) * dil);
       for (int ky = 0; ky < (multirow ? 1 : k); ++ky) {
         HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
         TcSeg& sg = p.segs[seg++];
-        sg.map = s; sg.nchunks = nch; sg.nrows = box_rows; sg.ntaps = k;
+        sg.map = s; sg.nchunks = nch; sg.nrows = box_rows; sg.ntaps = kxp ? 1 : k;
         sg.c1 = ky;  // kernel row selected through the row dimension of the tensor map
-        sg.rel_start2 = 2 * (-half * dil * pitch - half * dil);
-        sg.a0 = 0; sg.a_step = (uint32_t)dil;
-        sg.b0 = woff16 + (uint32_t)(ky * k) * slab; sg.b_step = slab; sg.b_row_step = (uint32_t)k * slab;
+        sg.rel_start2 = 2 * (-half * dil * pitch - (kxp ? 0 : half * dil));
+        sg.a0 = 0; sg.a_step = kxp ? 0u : (uint32_t)dil;
+        if (kxp) { sg.b0 = woff16 + (uint32_t)ky * slab; sg.b_step = 0; sg.b_row_step = slab; }
+        else { sg.b0 = woff16 + (uint32_t)(ky * k) * slab; sg.b_step = slab; sg.b_row_step = (uint32_t)k * slab; }
       }
     } else {
       // input pixel (2y+ky-1, 2x+kx-1) lives in sub-plane ((ky+1)&1, (kx+1)&1) at (y+dy, x+dx), dy/dx = -1 for k*=0
@@ -405,7 +435,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
           else { sg.ntaps = 1; sg.a_step = 0; sg.b0 = woff16 + (uint32_t)(ky * 3 + 1) * slab; sg.b_step = 0; }              // kx = 1
         }
     }
-    woff16 += (uint32_t)(k * k) * slab;
+    woff16 += (uint32_t)(srcs[s].kxpack ? k : k * k) * slab;
   }
   p.nseg = seg;
   for (int i = 0; i < seg; ++i) p.segs[i].tx_bytes = (uint32_t)TC_TILE_M * p.segs[i].nchunks * 16u * p.segs[i].nrows;
@@ -439,7 +469,7 @@ void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int 
   p.out_mode = up2 ? TC_OUT_CHUNKED_UP2 : (out.s2d ? TC_OUT_CHUNKED_S2D : TC_OUT_CHUNKED);
   p.out = out.ptr; p.out_pitch = out.pitch(); p.out_border = out.border; p.out_plane = out.plane();
   p.out_sub_plane = out.sub_plane();
-  p.out_chunks_total = out.chunks; p.out_chunk_off = chunk_off; p.out_nchunks = nchunks;
+  p.out_chunks_total = out.image_chunks(); p.out_chunk_off = chunk_off; p.out_nchunks = nchunks;
   p.act = act;
 }
 
@@ -459,7 +489,8 @@ void tc_conv_free(TcConv& c) {
 
 // ------------------------------------------------------------------------------------------- weight packing
 // dst[(tap entry e = (source, ky, kx))][chunk][n_pad][8] bf16; padded channels / filters are zero.
-struct PackSrc { int ch_off, real, chunks; };
+// kx-packed sources have one entry per kernel row: channel ch of the entry = (kx = ch / real, c = ch % real).
+struct PackSrc { int ch_off, real, chunks, kxpack; };
 __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* __restrict__ ba, int cout_a,
                                     const float* __restrict__ wb, const float* __restrict__ bb, int cout_b, int cin_total,
                                     int k, int n_pad, PackSrc s0, PackSrc s1, int nsrc, __nv_bfloat16* __restrict__ dst,
@@ -476,15 +507,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
   int rem = i;
   const int c8 = rem & 7; rem >>= 3;
   const int n = rem % n_pad; rem /= n_pad;
-  // rem = linear (entry, chunk) index with per-source chunk counts
-  const int per0 = kk * s0.chunks;
+  // rem = linear (entry, chunk) index with per-source entry / chunk counts
+  const int per0 = (s0.kxpack ? k : kk) * s0.chunks;
   PackSrc s = s0;
   if (rem >= per0) { rem -= per0; s = s1; }
-  const int chunk = rem % s.chunks, tap = rem / s.chunks;
+  const int chunk = rem % s.chunks, entry = rem / s.chunks;
   const int ch = chunk * 8 + c8;
+  int c = ch, tap = entry;
+  bool real = ch < s.real;
+  if (s.kxpack) { const int kx = ch / s.real; c = ch - kx * s.real; tap = entry * k + kx; real = kx < k; }
   float v = 0.f;
-  if (ch < s.real) {
-    const int cin = s.ch_off + ch;
+  if (real) {
+    const int cin = s.ch_off + c;
     if (n < cout_a) v = wa[((size_t)n * cin_total + cin) * kk + tap];
     else if (n < cout_a + cout_b) v = wb[((size_t)(n - cout_a) * cin_total + cin) * kk + tap];
   }
@@ -494,9 +528,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
 int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a, const float* wb, const float* bb,
                          int cout_b, cudaStream_t st) {
   HV_CHECK_ARG(cout_a + cout_b == c.cout_real, "tc_conv_pack_weights: filter count mismatch");
-  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks}, s1{0, 0, 1};
+  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks, c.src[0].kxpack ? 1 : 0}, s1{0, 0, 1, 0};
   int cin_total = c.src[0].real_channels;
-  if (c.nsrc == 2) { s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks}; cin_total += c.src[1].real_channels; }
+  if (c.nsrc == 2) {
+    s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks, c.src[1].kxpack ? 1 : 0};
+    cin_total += c.src[1].real_channels;
+  }
   const int total = (int)(c.p.w_bytes / 2);
   pack_weights_kernel<<<(max(total, c.n_pad) + 255) / 256, 256, 0, st>>>(wa, ba, cout_a, wb, bb, cout_b, cin_total, c.k, c.n_pad, s0,
                                                                           s1, c.nsrc, (__nv_bfloat16*)c.w_packed, c.bias_pad, total);
@@ -552,7 +589,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels
   else if (mode == HV_SRC_UP2) v = src[(((size_t)n * src_channels + c) * (h / 2) + y / 2) * (w / 2) + x / 2];
   else v = src[(((size_t)n * src_channels + c) * h + y) * w + x];
   const int ch = ch0 + c;
-  dst.ptr[(((size_t)n * dst.chunks + (ch >> 3)) * dst.plane() + dst.pos(y, x)) * 8 + (ch & 7)] = __float2bfloat16(v);
+  dst.ptr[dst.chunk_base(n, ch >> 3) + dst.pos(y, x) * 8 + (ch & 7)] = __float2bfloat16(v);
 }
 
 int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst, int ch0, cudaStream_t st) {
@@ -563,13 +600,48 @@ int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst,
   return HV_OK;
 }
 
+// kx-packed input planes: one thread = (position, chunk) assembles 8 channels and stores 16 B
+struct PackKxArgs { const float* ptr[4]; int mode[4]; int nsrc, k, dil; };
+__global__ void __launch_bounds__(256) pack_kx_kernel(PackKxArgs a, TcBuf dst) {
+  const int n = blockIdx.z, chunk = blockIdx.y, h = dst.h, w = dst.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w, half = a.k / 2;
+  __align__(16) __nv_bfloat16 o[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = chunk * 8 + j, kx = ch / a.nsrc, c = ch - kx * a.nsrc;
+    float v = 0.f;
+    const int xs = x + (kx - half) * a.dil;
+    if (kx < a.k && xs >= 0 && xs < w) {
+      const float* src = a.ptr[c];
+      if (a.mode[c] == HV_SRC_SCALAR) v = src[n];
+      else if (a.mode[c] == HV_SRC_SUB2) v = src[((size_t)n * (2 * h) + 2 * y) * (2 * w) + 2 * xs];
+      else v = src[((size_t)n * h + y) * w + xs];
+    }
+    o[j] = __float2bfloat16(v);
+  }
+  *reinterpret_cast<uint4*>(dst.ptr + dst.chunk_base(n, chunk) + dst.pos(y, x) * 8) = *reinterpret_cast<const uint4*>(o);
+}
+
+int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& dst, cudaStream_t st) {
+  HV_CHECK_ARG(srcs && nsrc >= 1 && nsrc <= 4 && dst.ptr && !dst.s2d && k * nsrc <= dst.chunks * 8, "tc_pack_kx: bad argument");
+  PackKxArgs a;
+  a.nsrc = nsrc; a.k = k; a.dil = dil;
+  for (int i = 0; i < 4; ++i) { a.ptr[i] = i < nsrc ? srcs[i].ptr : nullptr; a.mode[i] = i < nsrc ? srcs[i].mode : 0; }
+  dim3 grid((dst.h * dst.w + 255) / 256, dst.chunks, dst.n);
+  pack_kx_kernel<<<grid, 256, 0, st>>>(a, dst);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 __global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst) {
   const int n = blockIdx.z, c = blockIdx.y, h = src.h, w = src.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int y = i / w, x = i - y * w, ch = ch0 + c;
   dst[((size_t)n * channels + c) * h * w + i] =
-      __bfloat162float(src.ptr[(((size_t)n * src.chunks + (ch >> 3)) * src.plane() + src.pos(y, x)) * 8 + (ch & 7)]);
+      __bfloat162float(src.ptr[src.chunk_base(n, ch >> 3) + src.pos(y, x) * 8 + (ch & 7)]);
 }
 
 int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st) {
@@ -581,37 +653,48 @@ int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStre
 }
 
 // SHRM height head on a chunked buffer: sigmoid(fc(mean_HW(x)))  (inpaint_networks.py:90-93,:211-214)
+// grid (chunks, n): every CTA reduces one 8-channel chunk plane to its share of the dot product; the last CTA of a
+// sample (self-resetting ticket counter) adds the shares in a fixed order and applies bias + sigmoid.
 __global__ void __launch_bounds__(256) tc_gap_fc_kernel(TcBuf x, const float* __restrict__ fw, const float* __restrict__ fb,
-                                                        float* __restrict__ out) {
-  const int n = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+                                                        float* __restrict__ out, float* __restrict__ partial,
+                                                        unsigned int* __restrict__ ticket) {
+  const int c = blockIdx.x, n = blockIdx.y;
   const int h = x.h, w = x.w;
-  __shared__ float red[8];
-  float dot = 0.f;
-  for (int c = warp; c < x.chunks; c += nw) {
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const __nv_bfloat16* pl = x.ptr + ((size_t)n * x.chunks + c) * x.plane() * 8;
-    for (int i = lane; i < h * w; i += 32) {
-      const int y = i / w, xx = i - y * w;
-      const uint4 raw = *reinterpret_cast<const uint4*>(pl + x.pos(y, xx) * 8);
-      const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  __shared__ float red[32];
+  __shared__ bool last;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __nv_bfloat16* pl = x.ptr + x.chunk_base(n, c);
+  for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+    const int y = i / w, xx = i - y * w;
+    const uint4 raw = *reinterpret_cast<const uint4*>(pl + x.pos(y, xx) * 8);
+    const __nv_bfloat162* hp = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(hp[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dot += (warp_sum(acc[j]) / (float)(h * w)) * fw[c * 8 + j];
+    for (int j = 0; j < 4; ++j) { float2 f = __bfloat1622float2(hp[j]); acc[2 * j] += f.x; acc[2 * j + 1] += f.y; }
   }
-  if (lane == 0) red[warp] = dot;
-  __syncthreads();
+  float dot = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dot += acc[j] * fw[c * 8 + j];
+  dot = block_sum(dot, red) / (float)(h * w);
   if (threadIdx.x == 0) {
+    partial[n * x.chunks + c] = dot;
+    __threadfence();
+    last = atomicAdd(&ticket[n], 1u) == (unsigned)x.chunks - 1;
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
     float t = 0.f;
-    for (int i = 0; i < nw; ++i) t += red[i];
+    for (int i = 0; i < x.chunks; ++i) t += __ldcg(&partial[n * x.chunks + i]);
     out[n] = 1.f / (1.f + expf(-(t + fb[0])));
+    ticket[n] = 0;
   }
 }
 
-int tc_gap_fc_sigmoid(const TcBuf& x, const float* fw, const float* fb, float* out, cudaStream_t st) {
-  HV_CHECK_ARG(x.ptr && fw && fb && out && !x.s2d, "tc_gap_fc_sigmoid: bad argument");
-  tc_gap_fc_kernel<<<x.n, 256, 0, st>>>(x, fw, fb, out);
+// scratch: (max_batch * chunks) floats + max_batch zero-initialised uints
+int tc_gap_fc_sigmoid(const TcBuf& x, const float* fw, const float* fb, float* out, float* partial, unsigned int* ticket,
+                      cudaStream_t st) {
+  HV_CHECK_ARG(x.ptr && fw && fb && out && partial && ticket && !x.s2d, "tc_gap_fc_sigmoid: bad argument");
+  tc_gap_fc_kernel<<<dim3(x.chunks, x.n), 256, 0, st>>>(x, fw, fb, out, partial, ticket);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }

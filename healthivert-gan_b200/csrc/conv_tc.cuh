@@ -23,6 +23,18 @@ struct TcBuf {
   __nv_bfloat16* ptr = nullptr;
   int n = 0, chunks = 0, h = 0, w = 0, border = 0;
   bool s2d = false;
+  int img_chunks = 0;  // chunks per image in memory when this is a view of a chunk range of a wider buffer (0: == chunks)
+  __host__ __device__ int image_chunks() const { return img_chunks ? img_chunks : chunks; }
+  // element offset of chunk plane c of image i
+  __host__ __device__ size_t chunk_base(int i, int c) const { return ((size_t)i * image_chunks() + c) * (size_t)plane() * 8; }
+  // view of chunks [c0, c0 + count)
+  TcBuf chunk_view(int c0, int count) const {
+    TcBuf v = *this;
+    v.img_chunks = image_chunks();
+    v.ptr = ptr + (size_t)c0 * plane() * 8;
+    v.chunks = count;
+    return v;
+  }
   __host__ __device__ int sub_h() const { return s2d ? h / 2 : h; }
   __host__ __device__ int sub_w() const { return s2d ? w / 2 : w; }
   __host__ __device__ int pitch() const { return sub_w() + 2 * border; }
@@ -33,7 +45,7 @@ struct TcBuf {
     if (!s2d) return (size_t)(y + border) * pitch() + x + border;
     return (size_t)((y & 1) * 2 + (x & 1)) * sub_plane() + (size_t)((y >> 1) + border) * pitch() + (x >> 1) + border;
   }
-  size_t elems() const { return (size_t)n * chunks * plane() * 8; }
+  size_t elems() const { return (size_t)n * image_chunks() * plane() * 8; }
   size_t bytes() const { return elems() * sizeof(__nv_bfloat16); }
   // multi-row TMA boxes of the last tiles of the last image read (and discard) up to 4 rows past the plane
   static constexpr size_t kSlackBytes = 256 * 1024;
@@ -93,6 +105,10 @@ struct TcParams {
 struct TcSource {
   TcBuf buf;
   int real_channels;  // channels of this source that carry weights (<= buf.chunks*8)
+  // kx-packed source: channel kx*real_channels + c of the buffer holds input channel c shifted by (kx - k/2)*dil pixels
+  // along x, so the conv needs one tap (and one MMA K-step set) per kernel ROW instead of per tap.  Pays off for
+  // sources with few channels (network inputs, the CAM plane): k*real_channels must fit the buffer.
+  bool kxpack = false;
 };
 
 struct TcConv {
@@ -124,8 +140,13 @@ void tc_conv_free(TcConv& c);
 // fp32 NCHW <-> chunked bf16 converters (channel c of the source lands in chunk c/8, lane c%8)
 int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, const TcBuf& dst, int dst_channel0,
                  cudaStream_t st);
+// kx-packed variant for up to 4 single-channel sources (planes [n,1,h,w] / [n,1,2h,2w] (SUB2) / scalars [n]):
+// dst channel kx*nsrc + c at (y, x) = source c at (y, x + (kx - k/2)*dil), zero outside the image
+struct TcPlaneSrc { const float* ptr; int mode; };
+int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& dst, cudaStream_t st);
 int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st);
-int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, cudaStream_t st);
+int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, float* partial /*[n*chunks]*/,
+                      unsigned int* ticket /*[n], zero-initialised, left zero*/, cudaStream_t st);
 
 // contextual attention on tensor cores (ctx_attn_tc.cu): f and y are 64-channel 64x64 chunked buffers
 size_t ctx_attn_tc_workspace_bytes(int n);

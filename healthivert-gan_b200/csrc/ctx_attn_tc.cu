@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) ca_tc_patches_kernel(TcBuf f, __nv_bfloat
     const int y = lh + ky - 1, x = lw + kx - 1;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < CA_SIDE && x >= 0 && x < CA_SIDE)
-      v = *reinterpret_cast<const uint4*>(f.ptr + (((size_t)n * f.chunks + ch) * f.plane() + f.pos(2 * y, 2 * x)) * 8);
+      v = *reinterpret_cast<const uint4*>(f.ptr + f.chunk_base(n, ch) + f.pos(2 * y, 2 * x) * 8);
     dst[i] = v;
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) ca_tc_raw_kernel(TcBuf f, __nv_bfloat16* 
     const int x = 2 * (8 * g + j) - 1 + kx;
     uint4 raw = make_uint4(0, 0, 0, 0);
     if (y >= 0 && y < CA_H && x >= 0 && x < CA_H)
-      raw = *reinterpret_cast<const uint4*>(f.ptr + (((size_t)n * f.chunks + ch) * f.plane() + f.pos(y, x)) * 8);
+      raw = *reinterpret_cast<const uint4*>(f.ptr + f.chunk_base(n, ch) + f.pos(y, x) * 8);
     *reinterpret_cast<uint4*>(v[j]) = raw;
   }
 #pragma unroll
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(256) ca_tc_fold_kernel(const __nv_bfloat16* __
     __nv_bfloat162 h = __floats2bfloat162_rn(acc[2 * e] * 0.25f, acc[2 * e + 1] * 0.25f);
     pk[e] = *reinterpret_cast<uint32_t*>(&h);
   }
-  *reinterpret_cast<uint4*>(y.ptr + (((size_t)n * y.chunks + ch) * y.plane() + y.pos(oy, ox)) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  *reinterpret_cast<uint4*>(y.ptr + y.chunk_base(n, ch) + y.pos(oy, ox) * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
 }
 
 // ------------------------------------------------------------------ host orchestration

@@ -214,34 +214,38 @@ enum BufId {
 };
 struct BufSpec { int channels, extent, border; };
 static const BufSpec kBufs[B_COUNT] = {
+    // B_IN_C (kx-packed 5 x [x, ratio, mask]), C1 .. C12U, CAM128 (kx-packed 3 x CAM), C20 .. C14U, CAM256 (kx-packed), C19, C15, C16
     {16, 256, 2}, {16, 256, 1}, {32, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
     {64, 64, 8}, {64, 64, 16}, {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {16, 128, 1}, {64, 128, 1}, {32, 128, 1},
     {32, 256, 1}, {16, 256, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
-    {16, 256, 2}, {16, 256, 1}, {16, 128, 1}, {32, 128, 1}, {32, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
+    // B_IN_F (kx-packed 5 x [x, coarse_seg, mask, ratio]), B_F1 = conv1 | pmconv1 (merged layer, 16 + 16 channels), F2 ..
+    {32, 256, 2}, {32, 256, 1}, {16, 128, 1}, {32, 128, 1}, {32, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
     {64, 64, 8}, {64, 64, 16}, {64, 64, 1},
-    {16, 256, 1}, {16, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1},
+    // B_P1 is a chunk view of B_F1 (no storage of its own)
+    {0, 256, 1}, {16, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1},
     {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {32, 128, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
 };
 
 // layer -> (sources, output).  real = channels of the source that carry weights.
-struct TcLayerSpec { int layer; int src0, real0, src1, real1; int out; bool up2; int out_chunks; };
+struct TcLayerSpec { int layer; int src0, real0, src1, real1; int out; bool up2; int out_chunks; bool kx0, kx1; };
 static const TcLayerSpec kTcLayers[] = {
-    {C1, B_IN_C, 3, -1, 0, B_C1, false, 2},     {C2, B_C1, 16, -1, 0, B_C2, false, 4},
+    {C1, B_IN_C, 3, -1, 0, B_C1, false, 2, true, false},  {C2, B_C1, 16, -1, 0, B_C2, false, 4},
     {C3, B_C2, 32, -1, 0, B_C3, false, 4},      {C4, B_C3, 32, -1, 0, B_C4, false, 8},
     {C5, B_C4, 64, -1, 0, B_C5, false, 8},      {C6, B_C5, 64, -1, 0, B_C6, false, 8},
     {C7, B_C6, 64, -1, 0, B_C7, false, 8},      {C8, B_C7, 64, -1, 0, B_C8, false, 8},
     {C9, B_C8, 64, -1, 0, B_C9, false, 8},      {C10, B_C9, 64, -1, 0, B_C10, false, 8},
     {C11, B_C10, 64, -1, 0, B_C11, false, 8},   {C12, B_C11, 64, -1, 0, B_C12U, true, 8},
-    {C20, B_C12U, 64, B_CAM128, 1, B_C20, false, 8}, {C13, B_C20, 64, -1, 0, B_C13, false, 4},
-    {C14, B_C13, 32, -1, 0, B_C14U, true, 4},   {C19, B_C14U, 32, B_CAM256, 1, B_C19, false, 4},
+    {C20, B_C12U, 64, B_CAM128, 1, B_C20, false, 8, false, true}, {C13, B_C20, 64, -1, 0, B_C13, false, 4},
+    {C14, B_C13, 32, -1, 0, B_C14U, true, 4},   {C19, B_C14U, 32, B_CAM256, 1, B_C19, false, 4, false, true},
     {C15, B_C19, 32, -1, 0, B_C15, false, 2},   {C16, B_C15, 16, -1, 0, B_C16, false, 2},
     {C17, B_C16, 8, -1, 0, -1, false, 0},       // heads conv17 + conv18
-    {F1, B_IN_F, 4, -1, 0, B_F1, false, 2},     {F2, B_F1, 16, -1, 0, B_F2, false, 2},
+    // fine conv1 and pmconv1 read the same input: ONE conv with 16 + 16 filters writes B_F1 (chunks 0-1 | 2-3 = B_P1)
+    {F1, B_IN_F, 4, -1, 0, B_F1, false, 4, true, false},  {F2, B_F1, 16, -1, 0, B_F2, false, 2},
     {F3, B_F2, 16, -1, 0, B_F3, false, 4},      {F4, B_F3, 32, -1, 0, B_F4, false, 4},
     {F5, B_F4, 32, -1, 0, B_F5, false, 8},      {F6, B_F5, 64, -1, 0, B_F6, false, 8},
     {F7, B_F6, 64, -1, 0, B_F7, false, 8},      {F8, B_F7, 64, -1, 0, B_F8, false, 8},
     {F9, B_F8, 64, -1, 0, B_F9, false, 8},      {F10, B_F9, 64, -1, 0, B_F10, false, 8},
-    {PM1, B_IN_F, 4, -1, 0, B_P1, false, 2},    {PM2, B_P1, 16, -1, 0, B_P2, false, 2},
+    {PM2, B_P1, 16, -1, 0, B_P2, false, 2},
     {PM3, B_P2, 16, -1, 0, B_P3, false, 4},     {PM4, B_P3, 32, -1, 0, B_P4, false, 8},
     {PM5, B_P4, 64, -1, 0, B_P5, false, 8},     {PM6, B_P5, 64, -1, 0, B_P6, false, 8},
     {PM9, B_CA, 64, -1, 0, B_P9, false, 8},     {PM10, B_P9, 64, -1, 0, B_P10, false, 8},
@@ -260,6 +264,8 @@ struct TcPlan {
   int out_buf[kNumLayers];
   bool out_up2[kNumLayers] = {};
   void* ca_ws = nullptr;     // workspace of the tensor-core attention
+  float* gap_partial = nullptr;      // [2][max_batch * 8] shares of the two height heads
+  unsigned int* gap_ticket = nullptr;  // [2][max_batch]
   __nv_bfloat16* blob = nullptr;
 };
 
@@ -273,7 +279,7 @@ static TcAux make_aux(const TcBuf& b, int channel) {
 static void tc_plan_destroy(hv_generator* g) {
   if (!g->tc) return;
   for (int i = 0; i < kNumLayers; ++i) if (g->tc->has[i]) tc_conv_free(g->tc->conv[i]);
-  cudaFree(g->tc->blob); cudaFree(g->tc->ca_ws);
+  cudaFree(g->tc->blob); cudaFree(g->tc->ca_ws); cudaFree(g->tc->gap_partial); cudaFree(g->tc->gap_ticket);
   delete g->tc;
   g->tc = nullptr;
 }
@@ -298,23 +304,30 @@ static int tc_plan_create(hv_generator* g) {
     t->buf[i].ptr = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<char*>(t->blob) + off);
     off += (t->buf[i].bytes() + 255) & ~(size_t)255;
   }
+  t->buf[B_P1] = t->buf[B_F1].chunk_view(2, 2);   // pmconv1's half of the merged conv1 | pmconv1 output
   HV_CUDA(cudaMalloc(&t->ca_ws, ctx_attn_tc_workspace_bytes(n)));
+  HV_CUDA(cudaMalloc((void**)&t->gap_partial, sizeof(float) * 2 * n * 8));
+  HV_CUDA(cudaMalloc((void**)&t->gap_ticket, sizeof(unsigned int) * 2 * n));
+  HV_CUDA(cudaMemset(t->gap_ticket, 0, sizeof(unsigned int) * 2 * n));
   for (int i = 0; i < kNumLayers; ++i) t->out_buf[i] = -1;
+  t->out_buf[PM1] = B_P1;
   for (int i = 0; i < kNumTcLayers; ++i) {
     const TcLayerSpec& s = kTcLayers[i];
     const LayerSpec& L = kLayers[s.layer];
     TcSource srcs[2];
-    srcs[0].buf = t->buf[s.src0]; srcs[0].real_channels = s.real0;
+    srcs[0].buf = s.layer == F2 ? t->buf[B_F1].chunk_view(0, 2) : t->buf[s.src0];
+    srcs[0].real_channels = s.real0; srcs[0].kxpack = s.kx0;
     int nsrc = 1;
-    if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; nsrc = 2; }
+    if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; srcs[1].kxpack = s.kx1; nsrc = 2; }
     const bool heads = s.out < 0;
     TcConv& c = t->conv[s.layer];
-    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, heads ? 2 : L.cout, n);
+    const int cout = heads ? 2 : (s.layer == F1 ? kLayers[F1].cout + kLayers[PM1].cout : L.cout);
+    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, cout, n);
     if (rc) return rc;
     t->has[s.layer] = true;
     if (heads) {
-      TcAux a0 = make_aux(t->buf[B_A16CAT], 8), a1 = make_aux(t->buf[B_IN_F], 1);
-      tc_conv_set_output_heads(c, nullptr, nullptr, s.layer == C17 ? &a0 : nullptr, s.layer == C17 ? &a1 : nullptr);
+      TcAux a0 = make_aux(t->buf[B_A16CAT], 8);   // x_stage1 joins allconv16's output for the final heads (:225)
+      tc_conv_set_output_heads(c, nullptr, nullptr, s.layer == C17 ? &a0 : nullptr, nullptr);
     } else {
       tc_conv_set_output_chunked(c, t->buf[s.out], 0, s.out_chunks, s.up2, L.act);
       t->out_buf[s.layer] = s.out; t->out_up2[s.layer] = s.up2;
@@ -339,6 +352,8 @@ static int tc_plan_pack_weights(hv_generator* g, cudaStream_t st) {
     int rc;
     if (kTcLayers[i].out < 0)  // heads: conv17|conv18 and allconv17|allconv18 are adjacent layer ids
       rc = tc_conv_pack_weights(t->conv[l], g->w_eff[l], g->bias[l], 1, g->w_eff[l + 1], g->bias[l + 1], 1, st);
+    else if (l == F1)
+      rc = tc_conv_pack_weights(t->conv[l], g->w_eff[F1], g->bias[F1], kLayers[F1].cout, g->w_eff[PM1], g->bias[PM1], kLayers[PM1].cout, st);
     else
       rc = tc_conv_pack_weights(t->conv[l], g->w_eff[l], g->bias[l], kLayers[l].cout, nullptr, nullptr, 0, st);
     if (rc) return rc;
@@ -356,34 +371,39 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     tc_set_batch(c, n);
     return tc_conv_launch(c, s);
   };
-  // ---- pack the fp32 NCHW inputs into the chunked bf16 input buffers (torch.cat of :77 / :179)
-  RC(tc_pack_nchw(x, 1, HV_SRC_DIRECT, view(B_IN_C), 0, st));
-  RC(tc_pack_nchw(ratio, 1, HV_SRC_SCALAR, view(B_IN_C), 1, st));
-  RC(tc_pack_nchw(mask, 1, HV_SRC_DIRECT, view(B_IN_C), 2, st));
-  RC(tc_pack_nchw(x, 1, HV_SRC_DIRECT, view(B_IN_F), 0, st));
-  RC(tc_pack_nchw(mask, 1, HV_SRC_DIRECT, view(B_IN_F), 2, st));
-  RC(tc_pack_nchw(ratio, 1, HV_SRC_SCALAR, view(B_IN_F), 3, st));
-  RC(tc_pack_nchw(cam, 1, HV_SRC_SUB2, view(B_CAM128), 0, st));
-  RC(tc_pack_nchw(cam, 1, HV_SRC_DIRECT, view(B_CAM256), 0, st));
+  // ---- pack the fp32 NCHW inputs into kx-packed chunked bf16 buffers (torch.cat of :77 / :179, F.interpolate of :98)
+  {
+    const TcPlaneSrc in_c[3] = {{x, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}, {mask, HV_SRC_DIRECT}};
+    RC(tc_pack_kx(in_c, 3, 5, 1, view(B_IN_C), st));
+    const TcPlaneSrc cam128[1] = {{cam, HV_SRC_SUB2}}, cam256[1] = {{cam, HV_SRC_DIRECT}};
+    RC(tc_pack_kx(cam128, 1, 3, 1, view(B_CAM128), st));
+    RC(tc_pack_kx(cam256, 1, 3, 1, view(B_CAM256), st));
+  }
   // ---- coarse network
   for (int l : {C1, C2, C3, C4, C5, C6, C7, C8, C9, C10}) RC(run(l, st));
-  RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, st));
+  RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, t->gap_partial, t->gap_ticket, st));
   for (int l : {C11, C12, C20, C13, C14, C19, C15, C16}) RC(run(l, st));
   t->conv[C17].p.head0 = x_stage1; t->conv[C17].p.head1 = coarse_seg;
   RC(run(C17, st));
-  // ---- fine network: attention branch on the side stream
+  // ---- fine network: xnow = [xin, coarse_seg, mask, ratio]; conv1 | pmconv1 as one 32-filter conv, then the
+  // attention branch forks onto the side stream
+  {
+    const TcPlaneSrc in_f[4] = {{x, HV_SRC_DIRECT}, {coarse_seg, HV_SRC_DIRECT}, {mask, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}};
+    RC(tc_pack_kx(in_f, 4, 5, 1, view(B_IN_F), st));
+  }
+  RC(run(F1, st));
   HV_CUDA(cudaEventRecord(g->ev_fork, st));
   HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
   cudaStream_t sa = g->side;
-  for (int l : {PM1, PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
+  for (int l : {PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
   RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa));
   RC(run(PM9, sa));
   RC(run(PM10, sa));
   HV_CUDA(cudaEventRecord(g->ev_join, sa));
-  for (int l : {F1, F2, F3, F4, F5, F6, F7, F8, F9, F10}) RC(run(l, st));
+  for (int l : {F2, F3, F4, F5, F6, F7, F8, F9, F10}) RC(run(l, st));
   HV_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
   RC(run(A11, st));
-  RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, st));
+  RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, t->gap_partial + g->max_batch * 8, t->gap_ticket + g->max_batch, st));
   for (int l : {A12, A19, A13, A14, A15, A16}) RC(run(l, st));
   t->conv[A17].p.head0 = x_stage2; t->conv[A17].p.head1 = fine_seg;
   RC(run(A17, st));

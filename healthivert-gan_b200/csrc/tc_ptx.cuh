@@ -126,7 +126,17 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 
 // non-blocking probe of an mbarrier phase (peek-ahead: issue it before a batch of MMAs, consume the result after)
-__device__ __forceinline__ bool mbar_peek(uint32_t bar, uint32_t parity) { return mbar_try_wait(bar, parity); }
+// (test_wait, not try_wait: try_wait may suspend the thread up to a hardware time limit when the phase is still pending,
+// which costs ~10k cycles on a barrier that will never complete, e.g. the probe past the last tile)
+__device__ __forceinline__ bool mbar_peek(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_peeked(bool ready, uint32_t bar, uint32_t parity) {
   if (!ready) mbar_wait(bar, parity);
 }
