@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
         switch (shape) {
           HV_SEG(3, 3, 1) HV_SEG(3, 3, 2) HV_SEG(3, 3, 4) HV_SEG(5, 5, 1) HV_SEG(5, 5, 2)
           HV_SEG(1, 3, 1) HV_SEG(1, 3, 2) HV_SEG(1, 3, 4) HV_SEG(1, 2, 1) HV_SEG(1, 2, 2) HV_SEG(1, 1, 1) HV_SEG(1, 1, 2)
-          HV_SEG(5, 1, 1) HV_SEG(5, 1, 2) HV_SEG(1, 5, 1)
+          HV_SEG(5, 1, 1) HV_SEG(5, 1, 2) HV_SEG(1, 5, 1) HV_SEG(3, 1, 1) HV_SEG(1, 1, 4)
           default:
             issue_segment_generic<N_PAD>(leader, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate, nrows, ntaps, ksteps);
         }
@@ -600,37 +600,49 @@ int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst,
   return HV_OK;
 }
 
-// kx-packed input planes: one thread = (position, chunk) assembles 8 channels and stores 16 B
-struct PackKxArgs { const float* ptr[4]; int mode[4]; int nsrc, k, dil; };
+// kx-packed input planes: one thread = one position; all K * NSRC channels are built with compile-time indices
+struct PackKxArgs { const float* ptr[4]; int mode[4]; int dil; };
+template <int NSRC, int K>
 __global__ void __launch_bounds__(256) pack_kx_kernel(PackKxArgs a, TcBuf dst) {
-  const int n = blockIdx.z, chunk = blockIdx.y, h = dst.h, w = dst.w;
+  constexpr int NCH = (K * NSRC + 15) / 16 * 2;  // chunks written (even)
+  const int n = blockIdx.y, h = dst.h, w = dst.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
-  const int y = i / w, x = i - y * w, half = a.k / 2;
-  __align__(16) __nv_bfloat16 o[8];
+  const int y = i / w, x = i - y * w;
+  __align__(16) __nv_bfloat16 o[NCH * 8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = chunk * 8 + j, kx = ch / a.nsrc, c = ch - kx * a.nsrc;
-    float v = 0.f;
-    const int xs = x + (kx - half) * a.dil;
-    if (kx < a.k && xs >= 0 && xs < w) {
-      const float* src = a.ptr[c];
-      if (a.mode[c] == HV_SRC_SCALAR) v = src[n];
-      else if (a.mode[c] == HV_SRC_SUB2) v = src[((size_t)n * (2 * h) + 2 * y) * (2 * w) + 2 * xs];
-      else v = src[((size_t)n * h + y) * w + xs];
+  for (int j = 0; j < NCH * 8; ++j) o[j] = __float2bfloat16(0.f);
+#pragma unroll
+  for (int c = 0; c < NSRC; ++c) {
+    const float* src = a.ptr[c];
+    const int mode = a.mode[c];
+    const float* row = mode == HV_SRC_SUB2 ? src + ((size_t)n * (2 * h) + 2 * y) * (2 * w) : src + ((size_t)n * h + y) * w;
+    const float scalar = mode == HV_SRC_SCALAR ? src[n] : 0.f;
+#pragma unroll
+    for (int kx = 0; kx < K; ++kx) {
+      const int xs = x + (kx - K / 2) * a.dil;
+      float v = 0.f;
+      if (xs >= 0 && xs < w) v = mode == HV_SRC_SCALAR ? scalar : (mode == HV_SRC_SUB2 ? row[2 * xs] : row[xs]);
+      o[kx * NSRC + c] = __float2bfloat16(v);
     }
-    o[j] = __float2bfloat16(v);
   }
-  *reinterpret_cast<uint4*>(dst.ptr + dst.chunk_base(n, chunk) + dst.pos(y, x) * 8) = *reinterpret_cast<const uint4*>(o);
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch)
+    *reinterpret_cast<uint4*>(dst.ptr + dst.chunk_base(n, ch) + dst.pos(y, x) * 8) = *reinterpret_cast<const uint4*>(o + ch * 8);
 }
 
 int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& dst, cudaStream_t st) {
   HV_CHECK_ARG(srcs && nsrc >= 1 && nsrc <= 4 && dst.ptr && !dst.s2d && k * nsrc <= dst.chunks * 8, "tc_pack_kx: bad argument");
   PackKxArgs a;
-  a.nsrc = nsrc; a.k = k; a.dil = dil;
+  a.dil = dil;
   for (int i = 0; i < 4; ++i) { a.ptr[i] = i < nsrc ? srcs[i].ptr : nullptr; a.mode[i] = i < nsrc ? srcs[i].mode : 0; }
-  dim3 grid((dst.h * dst.w + 255) / 256, dst.chunks, dst.n);
-  pack_kx_kernel<<<grid, 256, 0, st>>>(a, dst);
+  dim3 grid((dst.h * dst.w + 255) / 256, dst.n);
+  const int need = (k * nsrc + 15) / 16 * 2;
+  HV_CHECK_ARG(need == dst.chunks, "tc_pack_kx: destination has %d chunks, the packed channels need %d", dst.chunks, need);
+  if (nsrc == 1 && k == 3) pack_kx_kernel<1, 3><<<grid, 256, 0, st>>>(a, dst);
+  else if (nsrc == 3 && k == 5) pack_kx_kernel<3, 5><<<grid, 256, 0, st>>>(a, dst);
+  else if (nsrc == 4 && k == 5) pack_kx_kernel<4, 5><<<grid, 256, 0, st>>>(a, dst);
+  else { set_error("tc_pack_kx: no instance for %d sources, k=%d", nsrc, k); return HV_ERR_UNSUPPORTED; }
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
