@@ -35,6 +35,16 @@ FLOP_PER_SLICE = 17.54e9          # 14.187 (47 convs) + 1.208 
 METRIC = "slices/sec two-stage gen fwd (256x256)"
 
 
+def _traffic(precision):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per launch, from the committed ncu capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        with open(path) as fh:
+            return json.load(fh).get(precision)
+    except (OSError, ValueError):
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -57,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "-i", str(self.index), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -172,28 +182,51 @@ def run_ours(args, rank, world, local_rank):
     dev_ms = sum(a.elapsed_time(b) for a, b in evs)
 
     # ---------------- end to end through the public API from pinned host buffers
-    outs_host = None
-    e2e_evs = []
+    # Every step copies its own inputs host->device and its results device->host; copies run on two extra streams
+    # (double-buffered) so that the H2D of step i+1 and the D2H of step i-1 overlap the forward of step i.  The timed
+    # region is one CUDA-event pair around the whole loop, closed after the last D2H has landed.
+    copy_in, copy_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(2)]
+    outs_host = [None, None]
+    ev_in = [torch.cuda.Event() for _ in range(2)]
+    ev_comp = [torch.cuda.Event() for _ in range(2)]
+    ev_out = [torch.cuda.Event() for _ in range(2)]
     barrier()
-    for _ in range(args.steps):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        dx, dm, dc, dr = (t.to(dev, non_blocking=True) for t in host)
+    e2e_start, e2e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_start.record(stream)
+    copy_in.wait_event(e2e_start)
+    for i in range(args.steps):
+        b = i % 2
+        with torch.cuda.stream(copy_in):
+            if i >= 2:
+                copy_in.wait_event(ev_comp[b])      # the forward that read this input buffer has finished
+            for d, h in zip(dev_in[b], host):
+                d.copy_(h, non_blocking=True)
+            ev_in[b].record(copy_in)
+        stream.wait_event(ev_in[b])
         with torch.no_grad():
-            out = g(dx, dm, dc, dr)
-        keep = [out[i] for i in (0, 1, 2, 3, 5, 6)]
-        if outs_host is None:
-            outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in keep]
-        for h, t in zip(outs_host, keep):
-            h.copy_(t, non_blocking=True)
-        e1.record(stream)
-        e1.synchronize()
-        e2e_evs.append((e0, e1))
+            out = g(*dev_in[b])
+        ev_comp[b].record(stream)
+        keep = [out[k] for k in (0, 1, 2, 3, 5, 6)]
+        with torch.cuda.stream(copy_out):
+            copy_out.wait_event(ev_comp[b])
+            if outs_host[b] is None:
+                outs_host[b] = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in keep]
+            elif i >= 2:
+                ev_out[b].synchronize()             # the host consumed (here: may overwrite) step i-2's results
+            for h, t in zip(outs_host[b], keep):
+                t.record_stream(copy_out)
+                h.copy_(t, non_blocking=True)
+            ev_out[b].record(copy_out)
+    stream.wait_event(ev_out[0])
+    stream.wait_event(ev_out[1])
+    e2e_end.record(stream)
+    e2e_end.synchronize()
     barrier()
-    e2e_ms = sum(a.elapsed_time(b) for a, b in e2e_evs)
+    e2e_ms = e2e_start.elapsed_time(e2e_end)
     clocks = sampler.stop() if rank == 0 else None
     h2d = sum(t.numel() * t.element_size() for t in host)
-    d2h = sum(t.numel() * t.element_size() for t in outs_host)
+    d2h = sum(t.numel() * t.element_size() for t in outs_host[0])
 
     # ---------------- dominant kernel alone (roofline): 64->64 3x3 conv on the batch's 64x64 maps
     # (19 of 47 layers; coarse conv5 = layer 4).  Timed live with CUDA events on the launch stream.
@@ -239,6 +272,7 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"batch-{BATCH} 256x256 two-stage generator inference (BASELINE.json configs[1])",
                        "batch": BATCH, "precision": args.precision, "l2": "flushed (256 MiB write) between steps",
                        "timing": "per-step CUDA-event pairs on the launch stream, summed; max over ranks",
+                       "e2e_timing": "one CUDA-event pair around all steps; per-step H2D/D2H on copy streams overlap the forward",
                        "parallelism": f"slice-sharded x{world}, no collective"},
             "e2e": {"value": e2e, "unit": "slices/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
@@ -246,7 +280,8 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "tensor", "kernel": "conv 64->64 3x3 (fp32 SIMT parity kernel)"
                          if args.precision == "fp32" else "conv 64->64 3x3 (tcgen05 bf16)",
                          "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_tflops"], "traffic": None,
+                         "frac": achieved / peaks["bf16_tflops"], "traffic": _traffic(args.precision),
+                         "algorithmic_flop_per_launch": k_flop, "launch_us": k_ms * 1e3,
                          "peak_source": peaks["source"] + " burst bf16 (kernel timed alone)",
                          "whole_forward_tensor_frac_sustained": value / world * FLOP_PER_SLICE / (peaks["bf16_tflops_sustained"] * 1e12)},
             "wall_s_timed_region": wall,
@@ -263,10 +298,11 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("HV_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("HV_PRECISION", "bf16"), choices=["fp32", "bf16"],
+                    help="bf16 = tcgen05 tensor-core mode (headline); fp32 = SIMT parity mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
