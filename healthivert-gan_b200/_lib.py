@@ -51,6 +51,30 @@ SIGNATURES = {
     "hv_edge_xor_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "hv_column_heights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                   c_void_p]),
+    "hv_conv2d_dgrad": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_conv2d_wgrad": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_act_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_size_t, c_void_p]),
+    "hv_upsample2_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "hv_stitch_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hv_axpby": (c_int, [c_float, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
+    "hv_affine": (c_int, [c_float, c_void_p, c_float, c_void_p, c_size_t, c_void_p]),
+    "hv_height_loss": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_masked_center": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_size_t, c_void_p]),
+    "hv_sn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p]),
+    "hv_gap_fc_sigmoid_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p,
+                                      c_int, c_int, c_int, c_void_p]),
+    "hv_ctx_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "hv_ctx_attn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                c_void_p]),
+    "hv_bn_lrelu_fwd": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
+    "hv_bn_lrelu_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "hv_reduce_scalar": (c_int, [c_void_p, c_void_p, c_float, c_int, c_size_t, c_float, c_void_p, c_void_p, c_void_p]),
+    "hv_loss_grad": (c_int, [c_void_p, c_void_p, c_float, c_int, c_float, c_void_p, c_int, c_void_p, c_int, c_size_t,
+                             c_void_p]),
+    "hv_dice_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float, c_void_p]),
+    "hv_dice_bwd": (c_int, [c_void_p, c_void_p, c_float, c_float, c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hv_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_float, c_float, c_float, c_float, c_int,
+                             c_void_p]),
     "hv_generator_num_layers": (c_int, []),
     "hv_generator_layer_info": (c_int, [c_int, c_char_p] + [POINTER(c_int)] * 7),
     "hv_generator_create": (c_int, [POINTER(c_void_p), c_int, c_int]),

@@ -12,6 +12,7 @@
 // thread: 4 pixels x CPT channels accumulators in registers.  Input channels are staged
 // through shared memory CI at a time together with the matching weight slab.
 #include "hv_common.cuh"
+#include "kernels.h"
 
 namespace hv {
 
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
         }
       } else {
         int sh, sw;
-        if (mode == HV_SRC_UP2) { sh = p.Hin >> 1; sw = p.Win >> 1; }
+        if (mode == HV_SRC_UP2 || mode == HV_SRC_ZEROINS2) { sh = p.Hin >> 1; sw = p.Win >> 1; }
         else if (mode == HV_SRC_SUB2) { sh = p.Hin << 1; sw = p.Win << 1; }
         else { sh = p.Hin; sw = p.Win; }
         const float* base = sp + ((size_t)n * sch + ch) * sh * sw;
@@ -84,9 +85,11 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
           float v = 0.f;
           if (gy >= 0 && gy < p.Hin && gx >= 0 && gx < p.Win) {
             int yy = gy, xx = gx;
+            bool hit = true;
             if (mode == HV_SRC_UP2) { yy >>= 1; xx >>= 1; }
             else if (mode == HV_SRC_SUB2) { yy <<= 1; xx <<= 1; }
-            v = __ldg(base + (size_t)yy * sw + xx);
+            else if (mode == HV_SRC_ZEROINS2) { hit = ((yy | xx) & 1) == 0; yy >>= 1; xx >>= 1; }
+            if (hit) v = __ldg(base + (size_t)yy * sw + xx);
           }
           dst[r * p.pitch + x] = v;
         }
@@ -181,12 +184,18 @@ static int launch_ks(ConvArgs& a, cudaStream_t st) {
 
 int conv2d_fwd_fp32(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2,
                     cudaStream_t st) {
+  return conv2d_fwd_fp32_ex(d, w, bias, y, y2, 0, 0, st);
+}
+
+// hout/wout > 0 override the output extent (reads beyond the virtual input are zero): used by the data gradient
+int conv2d_fwd_fp32_ex(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
+                       cudaStream_t st) {
   HV_CHECK_ARG(d && w && y, "conv2d_fwd: null argument");
   HV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= 4, "conv2d_fwd: nsrc=%d out of range", d->nsrc);
   int csum = 0;
   for (int i = 0; i < d->nsrc; ++i) {
     HV_CHECK_ARG(d->src[i].ptr && d->src[i].channels > 0, "conv2d_fwd: bad source %d", i);
-    HV_CHECK_ARG(d->src[i].mode >= 0 && d->src[i].mode <= 3, "conv2d_fwd: bad source mode %d", d->src[i].mode);
+    HV_CHECK_ARG(d->src[i].mode >= 0 && d->src[i].mode <= 4, "conv2d_fwd: bad source mode %d", d->src[i].mode);
     HV_CHECK_ARG(d->src[i].mode != HV_SRC_SCALAR || d->src[i].channels == 1, "conv2d_fwd: scalar source must have 1 channel");
     HV_CHECK_ARG(d->src[i].mode != HV_SRC_UP2 || ((d->hin | d->win) & 1) == 0, "conv2d_fwd: up2 source needs even extent");
     csum += d->src[i].channels;
@@ -203,6 +212,8 @@ int conv2d_fwd_fp32(const hv_conv_desc* d, const float* w, const float* bias, fl
   const int eff = (d->k - 1) * d->dil + 1;
   a.Hout = (d->hin + 2 * d->pad - eff) / d->stride + 1;
   a.Wout = (d->win + 2 * d->pad - eff) / d->stride + 1;
+  if (hout > 0) a.Hout = hout;
+  if (wout > 0) a.Wout = wout;
   HV_CHECK_ARG(a.Hout > 0 && a.Wout > 0, "conv2d_fwd: empty output");
   a.pad = d->pad; a.dil = d->dil; a.act = d->act;
   const int key = d->k * 10 + d->stride;

@@ -413,4 +413,206 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
   return HV_OK;
 }
 
+// =================================================================== backward (fp32)
+// Adjoint of ctx_attn_fwd_fp32 w.r.t. the feature map f (it enters as foreground, background and raw patches alike).
+// The FORWARD workspace must be passed unchanged: it still holds P, R, inv_norm, mm, S (raw scores) and A (in U).
+
+// dcols[n][c*16+ky*4+kx][l] = 0.25 * dy[n][c][2lh-1+ky][2lw-1+kx]   (adjoint of the overlap-add, :377-379)
+__global__ void __launch_bounds__(256) ca_unfold_dy_kernel(const float* __restrict__ dy, float* __restrict__ dcols, int c, int h, int w) {
+  const int hs = h >> 1, ws = w >> 1, L = hs * ws;
+  const size_t total = (size_t)c * 16 * L;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = blockIdx.y;
+  const int l = i % L, t = (i / L) % 16, ch = i / ((size_t)L * 16);
+  const int y = 2 * (l / ws) - 1 + (t >> 2), x = 2 * (l % ws) - 1 + (t & 3);
+  float v = 0.f;
+  if (y >= 0 && y < h && x >= 0 && x < w) v = 0.25f * dy[(((size_t)n * c + ch) * h + y) * w + x];
+  dcols[(size_t)n * total + i] = v;
+}
+
+// softmax adjoint per foreground column: dU[b][f] = scale * mm[b] * A[b][f] * (dA[b][f] - sum_b' A[b'][f] dA[b'][f]); in place on dA
+__global__ void __launch_bounds__(256) ca_softmax_bwd_kernel(const float* __restrict__ A, float* __restrict__ dA, const float* __restrict__ mm,
+                                                             int L, float scale, int mm_stride) {
+  const float* An = A + (size_t)blockIdx.y * L * L;
+  float* dn = dA + (size_t)blockIdx.y * L * L;
+  const float* m = mm + (size_t)blockIdx.y * mm_stride;
+  const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int f = blockIdx.x * 32 + lane;
+  __shared__ float s_red[8][32];
+  float dot = 0.f;
+  for (int b = g; b < L; b += 8) dot = fmaf(An[(size_t)b * L + f], dn[(size_t)b * L + f], dot);
+  s_red[g][lane] = dot;
+  __syncthreads();
+  dot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) dot += s_red[k][lane];
+  for (int b = g; b < L; b += 8) {
+    const size_t o = (size_t)b * L + f;
+    dn[o] = scale * m[b] * An[o] * (dn[o] - dot);
+  }
+}
+
+// adjoint of ca_fuse_kernel: dS[r][s] = sum_{a,cc} dU[cmi(cm(r+a)+cc)][cmi(cm(s+a)+cc)]  (the operator is symmetric up to the
+// order of the two passes; a, cc in -1..1, flat indices outside [0, L) contribute nothing)
+__global__ void __launch_bounds__(256) ca_fuse_bwd_kernel(const float* __restrict__ dU, float* __restrict__ dS, int side) {
+  const int L = side * side;
+  const float* Un = dU + (size_t)blockIdx.z * L * L;
+  float* Sn = dS + (size_t)blockIdx.z * L * L;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (s >= L) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int a = -1; a <= 1; ++a) {
+    const int p = r + a, q = s + a;
+    if (p < 0 || p >= L || q < 0 || q >= L) continue;
+    const int cp = (p % side) * side + p / side, cq = (q % side) * side + q / side;
+#pragma unroll
+    for (int cc = -1; cc <= 1; ++cc) {
+      const int pi = cp + cc, pj = cq + cc;
+      if (pi < 0 || pi >= L || pj < 0 || pj >= L) continue;
+      const int i = (pi % side) * side + pi / side, j = (pj % side) * side + pj / side;
+      acc += Un[(size_t)i * L + j];
+    }
+  }
+  Sn[(size_t)r * L + s] = acc;
+}
+
+// per background row b: dinv[b] = sum_f dS[b][f] * S[b][f] / inv[b];  dG[b][:] = dS[b][:] * inv[b]  (in place)
+__global__ void __launch_bounds__(256) ca_rowscale_bwd_kernel(float* __restrict__ dS, const float* __restrict__ S, const float* __restrict__ inv_norm,
+                                                              float* __restrict__ dinv, int L) {
+  __shared__ float red[32];
+  const int b = blockIdx.x, n = blockIdx.y;
+  float* row = dS + ((size_t)n * L + b) * L;
+  const float* srow = S + ((size_t)n * L + b) * L;
+  const float inv = inv_norm[(size_t)n * L + b];
+  float acc = 0.f;
+  for (int f = threadIdx.x; f < L; f += blockDim.x) { acc = fmaf(row[f], srow[f], acc); row[f] *= inv; }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) dinv[(size_t)n * L + b] = acc / inv;
+}
+
+// zero-padded copy of the patch matrix: Ppad[n][l][kpad]
+__global__ void ca_pad_rows_kernel(const float* __restrict__ P, float* __restrict__ Ppad, int k, int kpad, size_t rows) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * kpad) return;
+  const int c = i % kpad;
+  const size_t r = i / kpad;
+  Ppad[i] = c < k ? P[r * k + c] : 0.f;
+}
+
+// df[n][c][Y][X] = sum of dR entries whose 4x4 stride-2 patch covers (Y, X)
+//                + (Y, X both even) sum of dP entries whose 3x3 patch on the ::2 grid covers (Y/2, X/2), with
+//                  dP[l] = C1[l] + C2[l] - inv[l]^3 dinv[l] P[l]   (the last term only where |P_l| > 1e-4)
+__global__ void __launch_bounds__(256) ca_gather_df_kernel(const float* __restrict__ dR, const float* __restrict__ C1, const float* __restrict__ C2,
+                                                           const float* __restrict__ P, const float* __restrict__ inv_norm,
+                                                           const float* __restrict__ dinv, float* __restrict__ df, int c, int h, int w, int kpad) {
+  const int hs = h >> 1, ws = w >> 1, L = hs * ws;
+  const size_t total = (size_t)c * h * w;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = blockIdx.y;
+  const int X = i % w, Y = (i / w) % h, ch = i / ((size_t)w * h);
+  float acc = 0.f;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int ky = ((Y + 1) & 1) + 2 * a, hf = (Y + 1 - ky) >> 1;
+    if (Y + 1 - ky < 0 || hf >= hs) continue;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int kx = ((X + 1) & 1) + 2 * b, wf = (X + 1 - kx) >> 1;
+      if (X + 1 - kx < 0 || wf >= ws) continue;
+      acc += dR[((size_t)n * L + hf * ws + wf) * (c * 16) + ch * 16 + ky * 4 + kx];
+    }
+  }
+  if (((Y | X) & 1) == 0) {
+    const int y = Y >> 1, x = X >> 1;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int lh = y - ky + 1;
+      if (lh < 0 || lh >= hs) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int lw = x - kx + 1;
+        if (lw < 0 || lw >= ws) continue;
+        const size_t l = (size_t)n * L + lh * ws + lw;
+        const int col = ch * 9 + ky * 3 + kx;
+        float v = C1[l * kpad + col] + C2[l * kpad + col];
+        const float inv = inv_norm[l];
+        if (inv < 1e4f) v -= inv * inv * inv * dinv[l] * P[l * (c * 9) + col];
+        acc += v;
+      }
+    }
+  }
+  df[(size_t)n * total + i] = acc;
+}
+
+struct CaBwdWorkspace { float *X1, *X2, *dR, *Ppad, *C1, *C2, *dinv; };
+
+static size_t ca_bwd_layout(int n, int c, int h, int w, char* base, CaBwdWorkspace* ws) {
+  const size_t L = (size_t)(h / 2) * (w / 2);
+  const size_t kpad = ((size_t)c * 9 + 127) / 128 * 128;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes); return p; };
+  char* p;
+  p = take(sizeof(float) * n * L * L);        if (ws) ws->X1 = (float*)p;
+  p = take(sizeof(float) * n * L * L);        if (ws) ws->X2 = (float*)p;
+  p = take(sizeof(float) * n * L * c * 16);   if (ws) ws->dR = (float*)p;
+  p = take(sizeof(float) * n * L * kpad);     if (ws) ws->Ppad = (float*)p;
+  p = take(sizeof(float) * n * L * kpad);     if (ws) ws->C1 = (float*)p;
+  p = take(sizeof(float) * n * L * kpad);     if (ws) ws->C2 = (float*)p;
+  p = take(sizeof(float) * n * L);            if (ws) ws->dinv = (float*)p;
+  return off;
+}
+
+size_t ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w) { return ca_bwd_layout(n, c, h, w, nullptr, nullptr); }
+
+int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, float scale, int fuse, void* fwd_workspace,
+                      void* bwd_workspace, cudaStream_t st) {
+  HV_CHECK_ARG(dy && df && fwd_workspace && bwd_workspace, "ctx_attn_bwd: null argument");
+  HV_CHECK_ARG(h == w && (h % 2) == 0, "ctx_attn_bwd: square even feature maps only");
+  const int side = h / 2, L = side * side, kp = c * 9, kr = c * 16;
+  HV_CHECK_ARG(L % 128 == 0 && kr % 128 == 0 && c % 8 == 0, "ctx_attn_bwd: needs (h/2)^2 %% 128 == 0 and c %% 8 == 0");
+  const int kpad = (kp + 127) / 128 * 128;
+  CaWorkspace fw;
+  ca_layout(n, c, h, w, (char*)fwd_workspace, &fw);
+  CaBwdWorkspace bw;
+  ca_bwd_layout(n, c, h, w, (char*)bwd_workspace, &bw);
+  const float* A = fuse ? fw.U : fw.S;     // attention weights of the forward
+  float* dcols = fw.cols;                   // the pasted columns are no longer needed
+  const size_t per_cols = (size_t)kr * L;
+  ca_unfold_dy_kernel<<<dim3((unsigned)((per_cols + 255) / 256), n), 256, 0, st>>>(dy, dcols, c, h, w);
+  HV_LAUNCH_CHECK();
+  // dA[b][f] = sum_ck R[b][ck] dcols[ck][f]
+  int rc = sgemm_batched(fw.R, dcols, bw.X1, nullptr, L, L, kr, true, false, (long long)L * kr, (long long)kr * L, (long long)L * L, 0, n, st);
+  if (rc) return rc;
+  // dR[b][ck] = sum_f A[b][f] dcols[ck][f]
+  rc = sgemm_batched(A, dcols, bw.dR, nullptr, L, kr, L, true, true, (long long)L * L, (long long)kr * L, (long long)L * kr, 0, n, st);
+  if (rc) return rc;
+  ca_softmax_bwd_kernel<<<dim3(L / 32, n), 256, 0, st>>>(A, bw.X1, fw.mm, L, scale, L);
+  HV_LAUNCH_CHECK();
+  float* dS = bw.X1;
+  if (fuse) {
+    ca_fuse_bwd_kernel<<<dim3((L + 255) / 256, L, n), 256, 0, st>>>(bw.X1, bw.X2, side);
+    HV_LAUNCH_CHECK();
+    dS = bw.X2;
+    // the raw scores were overwritten by nothing: fw.S still holds inv * P P^T
+  }
+  HV_CHECK_ARG(fuse, "ctx_attn_bwd: the no-fuse variant overwrote its scores in the forward (not differentiable here)");
+  ca_rowscale_bwd_kernel<<<dim3(L, n), 256, 0, st>>>(dS, fw.S, fw.inv_norm, bw.dinv, L);
+  HV_LAUNCH_CHECK();
+  const size_t rows = (size_t)n * L;
+  ca_pad_rows_kernel<<<(unsigned)((rows * kpad + 255) / 256), 256, 0, st>>>(fw.P, bw.Ppad, kp, kpad, rows);
+  HV_LAUNCH_CHECK();
+  // C1[b][k] = sum_f dG[b][f] P[f][k];  C2[f][k] = sum_b dG[b][f] P[b][k]
+  rc = sgemm_batched(dS, bw.Ppad, bw.C1, nullptr, L, kpad, L, true, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
+  if (rc) return rc;
+  rc = sgemm_batched(dS, bw.Ppad, bw.C2, nullptr, L, kpad, L, false, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
+  if (rc) return rc;
+  const size_t per = (size_t)c * h * w;
+  ca_gather_df_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(bw.dR, bw.C1, bw.C2, fw.P, fw.inv_norm, bw.dinv, df, c, h, w, kpad);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 }  // namespace hv

@@ -55,6 +55,16 @@ int hv_ctx_attn_fwd(const float* f, const float* mask, float* y, int32_t* offset
                            as_stream(stream));
 }
 
+size_t hv_ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w) {
+  if (n <= 0 || c <= 0 || h <= 0 || w <= 0) return 0;
+  return ctx_attn_bwd_workspace_bytes(n, c, h, w);
+}
+
+int hv_ctx_attn_bwd(const float* dy, float* df, int n, int c, int h, int w, float softmax_scale, int fuse, void* fwd_workspace,
+                    void* bwd_workspace, hv_stream_t stream) {
+  return ctx_attn_bwd_fp32(dy, df, n, c, h, w, softmax_scale, fuse, fwd_workspace, bwd_workspace, as_stream(stream));
+}
+
 int hv_stitch(const float* gen, const float* real, const float* pred_h, const int32_t* x1, const int32_t* x2,
               const int32_t* height, int maxheight, float* out, int32_t* rows_out, int n, int h, int w,
               hv_stream_t stream) {

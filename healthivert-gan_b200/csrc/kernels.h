@@ -21,6 +21,10 @@ int sn_prepare_single(const SnJob& job, int training, cudaStream_t st);
 
 int conv2d_fwd_fp32(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2,
                     cudaStream_t st);
+int conv2d_fwd_fp32_ex(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
+                       cudaStream_t st);
+// internal source mode: [N,ch,H/2,W/2] read through zero insertion (value at even (y,x) only) - stride-2 data gradient
+#define HV_SRC_ZEROINS2 4
 
 int gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* out, int n, int c,
                    int hw, cudaStream_t st);
@@ -35,6 +39,10 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
 int sgemm_batched(const float* A, const float* B, float* C, const float* rowscale, int M, int N, int K,
                   bool a_kmajor, bool b_kmajor, long long strideA, long long strideB, long long strideC,
                   long long strideScale, int batch, cudaStream_t st);
+
+size_t ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w);
+int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, float scale, int fuse, void* fwd_workspace,
+                      void* bwd_workspace, cudaStream_t st);
 
 int stitch(const float* gen, const float* real, const float* pred_h, const int32_t* x1, const int32_t* x2,
            const int32_t* height, int maxheight, float* out, int32_t* rows_out, int n, int h, int w,

@@ -126,6 +126,24 @@ class Conv2dBlock(nn.Module):
                             self.activation_name, hin, win)
 
 
+def _conv_run(block, tape, sources, extent, act=None):
+    """Tape-aware Conv2dBlock forward: spectral-norm prepare (one power iteration in train mode), fused conv, and a
+    recorded backward = act' -> wgrad/dgrad -> spectral-norm adjoint into ``weight_orig.grad`` / ``bias.grad``."""
+    from . import train_ops as T
+    c = block.conv
+    w_eff, sigma = c.effective_weight(block.training)
+
+    def on_grad(dw_eff, db):
+        dw = torch.empty_like(dw_eff)
+        check(_lib.lib().hv_sn_bwd(ptr(dw_eff), ptr(w_eff), ptr(c.weight_u), ptr(c.weight_v), ptr(sigma), ptr(dw),
+                                   c.out_channels, w_eff[0].numel(), _lib.stream()))
+        T.accumulate_param(c.weight_orig, dw)
+        T.accumulate_param(c.bias, db)
+
+    return T.conv2d(tape, sources, w_eff, c.bias.detach(), c.kernel_size, c.stride, c.padding, c.dilation,
+                    act or block.activation_name, extent, on_grad)
+
+
 def gen_conv(input_dim, output_dim, kernel_size=3, stride=1, padding=0, rate=1, activation="elu"):
     """reference models/inpaint_networks.py:413-417"""
     return Conv2dBlock(input_dim, output_dim, kernel_size, stride, conv_padding=padding, dilation=rate,
@@ -192,6 +210,71 @@ class CoarseGenerator(nn.Module):
         x_stage1 = torch.clamp(self.conv17(t), -1.0, 1.0)
         coarse_seg_sigmoid = self.conv18(t)
         return coarse_seg_sigmoid, x_stage1, pred1_h
+
+
+def _coarse_forward_tape(self, tape, x, mask, CAM, slice_ratio):
+    """CoarseGenerator.forward on the tape (training path).  x, mask, CAM: tensors; returns Vars."""
+    from . import train_ops as T
+    ratio = _ratio(slice_ratio, x)
+    h, w = x.shape[2:]
+    run = lambda name, srcs, ext: _conv_run(getattr(self, name), tape, srcs, ext)
+    t = run("conv1", [(x, HV_SRC_DIRECT), (ratio, HV_SRC_SCALAR), (mask, HV_SRC_DIRECT)], (h, w))
+    ext = (h, w)
+    for name in ("conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6", "conv7_atrous",
+                 "conv8_atrous", "conv9_atrous", "conv10_atrous"):
+        t = run(name, [(t, HV_SRC_DIRECT)], ext)
+        ext = tuple(t.data.shape[2:])
+    pred1_h = T.gap_fc_sigmoid(tape, t, self.fc_height)
+    t = run("conv11", [(t, HV_SRC_DIRECT)], ext)
+    t = run("conv12", [(t, HV_SRC_DIRECT)], ext)
+    t = run("conv20", [(t, HV_SRC_UP2), (CAM, HV_SRC_SUB2)], (h // 2, w // 2))
+    t = run("conv13", [(t, HV_SRC_DIRECT)], (h // 2, w // 2))
+    t = run("conv14", [(t, HV_SRC_DIRECT)], (h // 2, w // 2))
+    t = run("conv19", [(t, HV_SRC_UP2), (CAM, HV_SRC_DIRECT)], (h, w))
+    t = run("conv15", [(t, HV_SRC_DIRECT)], (h, w))
+    t = run("conv16", [(t, HV_SRC_DIRECT)], (h, w))
+    # conv17 (activation 'none') followed by torch.clamp(-1, 1) (:115): fused as the clamp epilogue
+    x_stage1 = _conv_run(self.conv17, tape, [(t, HV_SRC_DIRECT)], (h, w), act="clamp1")
+    coarse_seg = run("conv18", [(t, HV_SRC_DIRECT)], (h, w))
+    return coarse_seg, x_stage1, pred1_h
+
+
+def _fine_forward_tape(self, tape, xin, x_stage1, mask, coarse_seg, slice_ratio):
+    """FineGenerator.forward on the tape (training path); x_stage1 / coarse_seg are Vars (gradients reach the coarse net)."""
+    from . import train_ops as T
+    ratio = _ratio(slice_ratio, xin)
+    h, w = xin.shape[2:]
+    run = lambda name, srcs, ext: _conv_run(getattr(self, name), tape, srcs, ext)
+    xnow = [(xin, HV_SRC_DIRECT), (coarse_seg, HV_SRC_DIRECT), (mask, HV_SRC_DIRECT), (ratio, HV_SRC_SCALAR)]
+    t = run("conv1", xnow, (h, w))
+    ext = (h, w)
+    for name in ("conv2_downsample", "conv3", "conv4_downsample", "conv5", "conv6", "conv7_atrous",
+                 "conv8_atrous", "conv9_atrous", "conv10_atrous"):
+        t = run(name, [(t, HV_SRC_DIRECT)], ext)
+        ext = tuple(t.data.shape[2:])
+    x_hallu = t
+    t = run("pmconv1", xnow, (h, w))
+    ext = (h, w)
+    for name in ("pmconv2_downsample", "pmconv3", "pmconv4_downsample", "pmconv5", "pmconv6"):
+        t = run(name, [(t, HV_SRC_DIRECT)], ext)
+        ext = tuple(t.data.shape[2:])
+    ca = self.contextul_attention
+    t, offset_flow, offsets = T.ctx_attention(tape, t, mask, ca.softmax_scale, ca.fuse, ca.per_sample_mask)
+    ca.last_offsets = offsets
+    t = run("pmconv9", [(t, HV_SRC_DIRECT)], ext)
+    pm = run("pmconv10", [(t, HV_SRC_DIRECT)], ext)
+    t = run("allconv11", [(x_hallu, HV_SRC_DIRECT), (pm, HV_SRC_DIRECT)], ext)
+    pred2_h = T.gap_fc_sigmoid(tape, t, self.fc_height)
+    t = run("allconv12", [(t, HV_SRC_DIRECT)], ext)
+    t = run("allconv19", [(t, HV_SRC_DIRECT)], ext)
+    t = run("allconv13", [(t, HV_SRC_UP2)], (h // 2, w // 2))
+    t = run("allconv14", [(t, HV_SRC_DIRECT)], (h // 2, w // 2))
+    t = run("allconv15", [(t, HV_SRC_UP2)], (h, w))
+    t = run("allconv16", [(t, HV_SRC_DIRECT)], (h, w))
+    cat = [(t, HV_SRC_DIRECT), (x_stage1, HV_SRC_DIRECT)]
+    x_stage2 = _conv_run(self.allconv17, tape, cat, (h, w), act="clamp1")   # :230
+    fine_seg = run("allconv18", cat, (h, w))
+    return fine_seg, x_stage2, offset_flow, pred2_h
 
 
 class FineGenerator(nn.Module):
@@ -409,6 +492,21 @@ class Generator(nn.Module):
         out = (coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h)
         self._last_out = out  # the head taps of read_tap() alias these buffers
         return out
+
+    def forward_tape(self, tape, x, mask, CAM, slice_ratio):
+        """Training-path forward (layer by layer, fp32) recorded on ``tape``: returns the reference's 7-tuple with tape
+        Vars in place of the differentiable outputs (coarse_seg, fine_seg, x_stage1, x_stage2, flow tensor, pred1_h, pred2_h)."""
+        if not x.is_cuda:
+            raise _lib.HvError("hv_b200 Generator needs CUDA tensors (no CPU fallback)")
+        dev = x.device
+        x = x.to(torch.float32).contiguous()
+        mask = mask.to(device=dev, dtype=torch.float32).contiguous()
+        CAM = CAM.to(device=dev, dtype=torch.float32).contiguous()
+        coarse_seg, x_stage1, pred1_h = _coarse_forward_tape(self.coarse_generator, tape, x, mask, CAM, slice_ratio)
+        fine_seg, x_stage2, flow, pred2_h = _fine_forward_tape(self.fine_generator, tape, x, x_stage1, mask, coarse_seg,
+                                                              slice_ratio)
+        self.last_offsets = self.fine_generator.contextul_attention.last_offsets
+        return coarse_seg, fine_seg, x_stage1, x_stage2, flow, pred1_h, pred2_h
 
     def run_layer(self, idx, n):
         """Measurement hook: launch the tensor-core conv kernel of layer ``idx`` alone (bf16 plan)."""

@@ -1,0 +1,311 @@
+"""Reverse-mode tape over the hand-written training kernels (C ABI: include/hv_b200.h, "Training step").
+
+The reference relies on torch.autograd (models/pix2pix_model.py:286,:300,:314,:354); here every forward op records a
+closure that calls the matching hand-written backward kernel, and ``Tape.backward()`` replays the closures in reverse.
+torch supplies device memory (``torch.empty``) and parameter containers only - no torch arithmetic on the gradient path.
+"""
+import torch
+
+from . import _lib
+from ._lib import HV_ACT, HV_SRC_DIRECT, HV_SRC_SCALAR, HV_SRC_SUB2, HV_SRC_UP2, check, ptr
+
+
+class Var:
+    """A tensor on the tape: ``data`` plus an accumulated gradient (None until something flows back)."""
+    __slots__ = ("data", "grad", "requires_grad")
+
+    def __init__(self, data, requires_grad=True):
+        self.data = data
+        self.grad = None
+        self.requires_grad = requires_grad
+
+    @property
+    def shape(self):
+        return self.data.shape
+
+
+def _L():
+    return _lib.lib()
+
+
+def accumulate(var, g):
+    """var.grad += g (first contribution is adopted without a copy)."""
+    if not var.requires_grad:
+        return
+    if var.grad is None:
+        var.grad = g
+    else:
+        check(_L().hv_axpby(1.0, ptr(g), 1.0, ptr(var.grad), g.numel(), _lib.stream()))
+
+
+def accumulate_param(p, g):
+    if p.grad is None:
+        p.grad = g
+    else:
+        check(_L().hv_axpby(1.0, ptr(g), 1.0, ptr(p.grad), g.numel(), _lib.stream()))
+
+
+class Tape:
+    def __init__(self):
+        self.ops = []
+        self.keep = []   # tensors that must outlive the enqueued kernels of the forward
+
+    def record(self, fn):
+        self.ops.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.ops):
+            fn()
+        self.ops = []
+        self.keep = []
+
+
+def _desc(sources, cin, cout, k, stride, pad, dil, act, hin, win, n):
+    d = _lib.hv_conv_desc()
+    keep = []
+    for i, (t, mode) in enumerate(sources):
+        t = t.contiguous()
+        keep.append(t)
+        d.src[i].ptr = ptr(t)
+        d.src[i].channels = 1 if mode == HV_SRC_SCALAR else t.shape[1]
+        d.src[i].mode = mode
+    d.n, d.cin, d.cout, d.hin, d.win = n, cin, cout, hin, win
+    d.k, d.stride, d.pad, d.dil, d.act, d.nsrc = k, stride, pad, dil, HV_ACT[act], len(sources)
+    return d, keep
+
+
+def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_weight_grad, param_grads=True):
+    """act(conv2d(cat(sources), weight) + bias) with the fused source gather of hv_conv2d_fwd.
+
+    sources: [(Var | tensor, hv_src_mode)]; plain tensors are constants.  weight: effective weight TENSOR [cout,cin,k,k];
+    on_weight_grad(dw, db): receives the gradients w.r.t. weight / bias (skipped when param_grads is False)."""
+    srcs = [((s.data if isinstance(s, Var) else s), m) for s, m in sources]
+    first = srcs[0][0]
+    n = first.shape[0]
+    hin, win = extent
+    cin = sum(1 if m == HV_SRC_SCALAR else t.shape[1] for t, m in srcs)
+    cout = weight.shape[0]
+    eff = (k - 1) * dil + 1
+    hout, wout = (hin + 2 * pad - eff) // stride + 1, (win + 2 * pad - eff) // stride + 1
+    d, keep = _desc(srcs, cin, cout, k, stride, pad, dil, act, hin, win, n)
+    y = torch.empty(n, cout, hout, wout, device=first.device, dtype=torch.float32)
+    check(_L().hv_conv2d_fwd(d, ptr(weight), ptr(bias), ptr(y), None, _lib.stream()))
+    out = Var(y)
+    if tape is None:
+        return out
+    tape.keep.append(keep)
+
+    def bwd():
+        if out.grad is None:
+            return
+        L = _L()
+        st = _lib.stream()
+        dpre = out.grad
+        if act != "none":
+            dpre = torch.empty_like(y)
+            check(L.hv_act_bwd(ptr(y), ptr(out.grad), ptr(dpre), HV_ACT[act], y.numel(), st))
+        dd, keep2 = _desc(srcs, cin, cout, k, stride, pad, dil, "none", hin, win, n)
+        if param_grads:
+            dw = torch.empty_like(weight)
+            db = torch.empty(cout, device=y.device, dtype=torch.float32) if bias is not None else None
+            check(L.hv_conv2d_wgrad(dd, ptr(dpre), ptr(dw), ptr(db), st))
+            on_weight_grad(dw, db)
+        need = [isinstance(s, Var) and s.requires_grad for s, _ in sources]
+        if any(need):
+            ws = torch.empty(cin * cout * k * k, device=y.device, dtype=torch.float32)
+            dx = torch.empty(n, cin, hin, win, device=y.device, dtype=torch.float32)
+            check(L.hv_conv2d_dgrad(dd, ptr(weight), ptr(dpre), ptr(dx), ptr(ws), st))
+            c0 = 0
+            for (s, m), (t, _), nd in zip(sources, srcs, need):
+                ch = 1 if m == HV_SRC_SCALAR else t.shape[1]
+                if nd:
+                    if m == HV_SRC_DIRECT:
+                        g = dx if (c0 == 0 and ch == cin) else dx[:, c0:c0 + ch].contiguous()
+                    elif m == HV_SRC_UP2:
+                        g = torch.empty_like(t)
+                        check(L.hv_upsample2_bwd(ptr(dx), ptr(g), n, ch, hin // 2, win // 2, cin, c0, st))
+                    else:
+                        raise NotImplementedError("gradient through a sub-sampled / scalar source")
+                    accumulate(s, g)
+                c0 += ch
+        del keep2
+
+    tape.record(bwd)
+    return out
+
+
+def gap_fc_sigmoid(tape, x, fc):
+    """sigmoid(fc(mean_HW(x))) (reference inpaint_networks.py:90-93,:211-214); fc: nn.Linear(c, 1)."""
+    n, c, h, w = x.data.shape
+    out = torch.empty(n, 1, device=x.data.device, dtype=torch.float32)
+    fw, fb = fc.weight.detach().contiguous(), fc.bias.detach().contiguous()
+    check(_L().hv_gap_fc_sigmoid(ptr(x.data), ptr(fw), ptr(fb), ptr(out), n, c, h * w, _lib.stream()))
+    res = Var(out)
+    if tape is None:
+        return res
+
+    def bwd():
+        if res.grad is None:
+            return
+        dx = torch.empty_like(x.data)
+        dfw = torch.empty_like(fw)
+        dfb = torch.empty_like(fb)
+        check(_L().hv_gap_fc_sigmoid_bwd(ptr(x.data), ptr(out), ptr(res.grad.contiguous()), ptr(fw), ptr(dx), 0, ptr(dfw),
+                                         ptr(dfb), n, c, h * w, _lib.stream()))
+        accumulate(x, dx)
+        accumulate_param(fc.weight, dfw.reshape(fc.weight.shape))
+        accumulate_param(fc.bias, dfb.reshape(fc.bias.shape))
+
+    tape.record(bwd)
+    return res
+
+
+def ctx_attention(tape, f, mask, scale, fuse, per_sample_mask, want_flow=True):
+    """ContextualAttention.forward(f, f, mask) with its hand-written adjoint (fp32)."""
+    n, c, h, w = f.data.shape
+    L = _L()
+    dev = f.data.device
+    y = torch.empty_like(f.data)
+    offsets = torch.empty(n, 2, h // 2, w // 2, device=dev, dtype=torch.int32)
+    flow = torch.empty(n, 3, 4 * h, 4 * w, device=dev, dtype=torch.float32) if want_flow else None
+    ws = torch.empty(L.hv_ctx_attn_workspace_bytes(n, c, h, w), device=dev, dtype=torch.uint8)
+    mask = mask.contiguous()
+    check(L.hv_ctx_attn_fwd(ptr(f.data), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w, float(scale), int(bool(fuse)),
+                            int(per_sample_mask), ptr(ws), _lib.stream()))
+    out = Var(y)
+    if tape is not None:
+        def bwd():
+            if out.grad is None:
+                return
+            bws = torch.empty(L.hv_ctx_attn_bwd_workspace_bytes(n, c, h, w), device=dev, dtype=torch.uint8)
+            df = torch.empty_like(f.data)
+            check(L.hv_ctx_attn_bwd(ptr(out.grad.contiguous()), ptr(df), n, c, h, w, float(scale), int(bool(fuse)), ptr(ws),
+                                    ptr(bws), _lib.stream()))
+            accumulate(f, df)
+
+        tape.record(bwd)
+    return out, flow, offsets
+
+
+def bn_lrelu(tape, x, bn, slope=0.2, param_grads=True):
+    """BatchNorm2d (batch statistics, running stats updated) + LeakyReLU(slope) (reference networks.py:583-597)."""
+    n, c, h, w = x.data.shape
+    dev = x.data.device
+    y = torch.empty_like(x.data)
+    mean = torch.empty(c, device=dev, dtype=torch.float32)
+    invstd = torch.empty(c, device=dev, dtype=torch.float32)
+    gamma, beta = bn.weight.detach(), bn.bias.detach()
+    check(_L().hv_bn_lrelu_fwd(ptr(x.data), ptr(gamma), ptr(beta), ptr(bn.running_mean), ptr(bn.running_var), ptr(y), ptr(mean),
+                               ptr(invstd), n, c, h * w, float(bn.momentum), float(bn.eps), float(slope), _lib.stream()))
+    bn.num_batches_tracked += 1
+    out = Var(y)
+    if tape is None:
+        return out
+
+    def bwd():
+        if out.grad is None:
+            return
+        dx = torch.empty_like(x.data)
+        dg = torch.empty_like(gamma)
+        db = torch.empty_like(beta)
+        check(_L().hv_bn_lrelu_bwd(ptr(x.data), ptr(y), ptr(out.grad.contiguous()), ptr(gamma), ptr(mean), ptr(invstd), ptr(dx),
+                                   ptr(dg), ptr(db), n, c, h * w, float(slope), _lib.stream()))
+        if param_grads:
+            accumulate_param(bn.weight, dg)
+            accumulate_param(bn.bias, db)
+        accumulate(x, dx)
+
+    tape.record(bwd)
+    return out
+
+
+# ------------------------------------------------------------------------------------------- scalar losses
+class Scratch:
+    """Per-device reduction scratch (1024 floats) and 0-dim outputs."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, dev):
+        key = (dev.type, dev.index)
+        if key not in cls._bufs:
+            cls._bufs[key] = torch.empty(1024, device=dev, dtype=torch.float32)
+        return cls._bufs[key]
+
+
+def reduce_scalar(a, b, kind, scale, t=0.0):
+    out = torch.empty(1, device=a.device, dtype=torch.float32)
+    check(_L().hv_reduce_scalar(ptr(a), ptr(b), float(t), int(kind), a.numel(), float(scale), ptr(out), ptr(Scratch.get(a.device)),
+                                _lib.stream()))
+    return out
+
+
+def l1_mean(a, b):
+    """nn.L1Loss()(a, b) as a device scalar."""
+    return reduce_scalar(a.contiguous(), b.contiguous(), 0, 1.0 / a.numel())
+
+
+def bce_logits_const(logits, target_is_real):
+    """GANLoss('vanilla')(logits, target_is_real) = BCEWithLogitsLoss vs a constant target (networks.py:237,:270-272)."""
+    return reduce_scalar(logits.contiguous(), None, 1, 1.0 / logits.numel(), 1.0 if target_is_real else 0.0)
+
+
+def bce_logits_const_grad(logits, target_is_real, g):
+    """d(g * BCE mean)/d logits."""
+    da = torch.empty_like(logits)
+    check(_L().hv_loss_grad(ptr(logits), None, 1.0 if target_is_real else 0.0, 1, float(g) / logits.numel(), None, 0, ptr(da), 0,
+                            logits.numel(), _lib.stream()))
+    return da
+
+
+def l1_grad(a, b, g, scale=None, reciprocal=False):
+    """d(g * S * mean|a-b|)/da with the optional device scalar S (or 1/S)."""
+    da = torch.empty_like(a)
+    check(_L().hv_loss_grad(ptr(a), ptr(b), 0.0, 0, float(g) / a.numel(), ptr(scale), int(reciprocal), ptr(da), 0, a.numel(),
+                            _lib.stream()))
+    return da
+
+
+def dice(pred, gt, eps=1e-5):
+    """diceCoeff(pred, gt, activation='none') (pix2pix_model.py:13-39): (mean dice as device scalar, sums for the backward)."""
+    n = pred.shape[0]
+    per = pred.numel() // n
+    sums = torch.empty(n, 3, device=pred.device, dtype=torch.float32)
+    dn = torch.empty(n, device=pred.device, dtype=torch.float32)
+    check(_L().hv_dice_fwd(ptr(pred), ptr(gt), ptr(sums), ptr(dn), n, per, float(eps), _lib.stream()))
+    mean = reduce_scalar(dn, None, 3, 1.0 / n)
+    return mean, sums
+
+
+def dice_grad(gt, sums, g_out, eps=1e-5):
+    n = gt.shape[0]
+    per = gt.numel() // n
+    d = torch.empty_like(gt)
+    check(_L().hv_dice_bwd(ptr(gt), ptr(sums), float(g_out), float(eps), ptr(d), n, per, 0, _lib.stream()))
+    return d
+
+
+class FusedAdam:
+    """torch.optim.Adam(lr, betas) semantics (pix2pix_model.py:127-130) on hv_adam_step; state keys mirror torch's."""
+
+    def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):
+        self.params = [p for p in params]
+        self.param_groups = [{"params": self.params, "lr": lr, "initial_lr": lr, "betas": betas, "eps": eps}]
+        self.state = {}
+
+    def zero_grad(self, set_to_none=True):
+        for p in self.params:
+            p.grad = None
+
+    @torch.no_grad()
+    def step(self):
+        g = self.param_groups[0]
+        for p in self.params:
+            if p.grad is None:
+                continue
+            st = self.state.get(p)
+            if st is None:
+                st = self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+            st["step"] += 1
+            grad = p.grad.contiguous()
+            check(_L().hv_adam_step(ptr(p.data), ptr(grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(g["lr"]),
+                                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), int(st["step"]), _lib.stream()))

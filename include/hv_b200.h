@@ -173,6 +173,83 @@ int hv_generator_run_layer(hv_generator* g, int idx, int n, hv_stream_t stream);
  * output) of the LAST forward into out; returns element count or negative status        */
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream);
 
+
+/* ======================================================================================
+ * Training step (SURVEY.md §8 rows A1/A3 backward, A6, A7, A8), fp32.
+ * The host side (healthivert_gan_b200.pix2pix_model) keeps the reference's sequencing
+ * (models/pix2pix_model.py:356-382) and calls these in the order autograd would.
+ * ==================================================================================== */
+
+/* data gradient of hv_conv2d_fwd: dx over the VIRTUAL concatenated input [n,cin,hin,win] of
+ * the forward descriptor d (autograd of F.conv2d w.r.t. input, models/inpaint_networks.py:487-489,
+ * models/networks.py:575-598).  dy is the gradient w.r.t. the pre-activation output.
+ * workspace: cin*cout*k*k floats.                                                        */
+int hv_conv2d_dgrad(const hv_conv_desc* d, const float* w, const float* dy, float* dx,
+                    float* workspace, hv_stream_t stream);
+/* weight / bias gradient (autograd of F.conv2d w.r.t. weight, bias): the sources of d are
+ * the forward inputs; dw [cout,cin,k,k] is overwritten, db [cout] may be NULL.            */
+int hv_conv2d_wgrad(const hv_conv_desc* d, const float* dy, float* dw, float* db, hv_stream_t stream);
+/* dx = dy * act'(.) through the activation OUTPUT (nn.ELU / ReLU / Sigmoid / LeakyReLU(0.2) /
+ * clamp(-1,1) backward, inpaint_networks.py:460-472,:115,:230)                            */
+int hv_act_bwd(const float* out, const float* dy, float* dx, int act, size_t count, hv_stream_t stream);
+/* adjoint of F.interpolate(scale_factor=2, mode='nearest') (:97,:105,:219,:222): channels
+ * [dy_ch0, dy_ch0+c) of dy [n,dy_channels,2h,2w] -> dx [n,c,h,w]                          */
+int hv_upsample2_bwd(const float* dy, float* dx, int n, int c, int h, int w, int dy_channels,
+                     int dy_ch0, hv_stream_t stream);
+/* adjoint of hv_stitch w.r.t. gen; rows = rows_out of the forward (pix2pix_model.py:206-252) */
+int hv_stitch_bwd(const float* dout, const int32_t* rows, float* dgen, int n, int h, int w, hv_stream_t stream);
+/* y = a*x + b*y (x may be NULL) : gradient accumulation */
+int hv_axpby(float a, const float* x, float b, float* y, size_t count, hv_stream_t stream);
+/* y = a*x + c  (e.g. 1 - CAM, pix2pix_model.py:184) */
+int hv_affine(float a, const float* x, float c, float* y, size_t count, hv_stream_t stream);
+/* loss_h = mean(40|m p1-h|/h + 40|m p2-h|/h) (pix2pix_model.py:191-192,:350) and its gradients w.r.t. the sigmoid
+ * outputs p1, p2 [n] (dp1 / dp2 may be NULL); h: heights as float [n]                      */
+int hv_height_loss(const float* p1, const float* p2, const float* h, float maxheight, int n, float* loss,
+                   float* dp1, float* dp2, hv_stream_t stream);
+/* out = x * mask * [c0 <= column < c1]  (fake_B_local / real_B_local, pix2pix_model.py:254-260; self-adjoint) */
+int hv_masked_center(const float* x, const float* mask, float* out, int w, int c0, int c1, size_t total, hv_stream_t stream);
+/* backward of the spectral-norm reparametrisation (torch/nn/utils/spectral_norm.py:92-114):
+ * dw_orig = (dw_eff - <dw_eff, w_eff> u v^T) / sigma                                      */
+int hv_sn_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
+              float* dw_orig, int cout, int kdim, hv_stream_t stream);
+/* backward of hv_gap_fc_sigmoid: s = forward output [n], ds = its gradient; dx [n,c,hw]
+ * (accumulate != 0 adds), dfc_w [c], dfc_b [1]                                            */
+int hv_gap_fc_sigmoid_bwd(const float* x, const float* s, const float* ds, const float* fc_w, float* dx, int accumulate,
+                          float* dfc_w, float* dfc_b, int n, int c, int hw, hv_stream_t stream);
+/* backward of hv_ctx_attn_fwd w.r.t. f (fuse != 0 only).  fwd_workspace = the forward's
+ * workspace, untouched since; bwd_workspace: hv_ctx_attn_bwd_workspace_bytes bytes.        */
+size_t hv_ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w);
+int hv_ctx_attn_bwd(const float* dy, float* df, int n, int c, int h, int w, float softmax_scale, int fuse,
+                    void* fwd_workspace, void* bwd_workspace, hv_stream_t stream);
+
+/* ---- A7: BatchNorm2d(train) + LeakyReLU(0.2) of NLayerDiscriminator (models/networks.py:583-597).
+ * running_mean / running_var may be NULL; save_mean / save_invstd [c] feed the backward.   */
+int hv_bn_lrelu_fwd(const float* x, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                    float* y, float* save_mean, float* save_invstd, int n, int c, int hw, float momentum, float eps,
+                    float slope, hv_stream_t stream);
+int hv_bn_lrelu_bwd(const float* x, const float* y, const float* dy, const float* gamma, const float* save_mean,
+                    const float* save_invstd, float* dx, float* dgamma, float* dbeta, int n, int c, int hw,
+                    float slope, hv_stream_t stream);
+
+/* ---- A6: scalar losses.  out[0] = scale * reduce; kind 0: sum|a-b| (nn.L1Loss), 1: BCE-with-logits
+ * against the constant target t (GANLoss vanilla, models/networks.py:237,:270-272), 2: count_nonzero(a)
+ * (pix2pix_model.py:336), 3: sum a, 4: sum a*b.  scratch: 1024 floats.  Deterministic.     */
+int hv_reduce_scalar(const float* a, const float* b, float t, int kind, size_t count, float scale, float* out,
+                     float* scratch, hv_stream_t stream);
+/* gradients: kind 0: da = g * S * sign(a-b); kind 1: da = g * S * (sigmoid(a) - t); S = 1, *scale or 1 / *scale
+ * (device scalar, e.g. count_nonzero(mask)); accumulate != 0 adds into da                  */
+int hv_loss_grad(const float* a, const float* b, float t, int kind, float g, const float* scale,
+                 int scale_is_reciprocal, float* da, int accumulate, size_t count, hv_stream_t stream);
+/* diceCoeff(activation='none') (pix2pix_model.py:13-39): dice_n [n], sums [n,3] kept for the backward;
+ * g_out = d loss / d dice_n                                                                 */
+int hv_dice_fwd(const float* pred, const float* gt, float* sums, float* dice_n, int n, int per, float eps, hv_stream_t stream);
+int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, float* dpred, int n, int per,
+                int accumulate, hv_stream_t stream);
+
+/* ---- A8: torch.optim.Adam step (pix2pix_model.py:127-130), fused, in place */
+int hv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
+                 float beta1, float beta2, float eps, int step, hv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,3 +156,39 @@ def synthetic_train_batch(n=16, seed=7):
         "h2": torch.full((n,), 40, dtype=torch.int64), "slice_ratio": t(ratio),
         "A_paths": ["synthetic"] * n, "B_paths": ["synthetic"] * n,
     }
+
+
+def synthetic_discriminator_state_dict(seed=1, input_nc=1, ndf=64):
+    """PatchGAN NLayerDiscriminator weights in the reference ``state_dict`` format
+    (models/networks.py:555-602 after init_weights 'normal', gain 0.02: conv ~ N(0, 0.02), bias 0,
+    BatchNorm gamma ~ N(1, 0.02), beta 0), drawn from numpy so both implementations share them."""
+    rng = np.random.Generator(np.random.PCG64(1000 + seed))
+    sd = {}
+    chans = [(input_nc, ndf, True, False), (ndf, ndf * 2, False, True), (ndf * 2, ndf * 4, False, True),
+             (ndf * 4, ndf * 8, False, True), (ndf * 8, 1, True, False)]
+    idx = 0
+    for cin, cout, bias, bn in chans:
+        sd[f"model.{idx}.weight"] = torch.from_numpy((0.02 * rng.standard_normal((cout, cin, 4, 4))).astype(np.float32))
+        if bias:
+            sd[f"model.{idx}.bias"] = torch.zeros(cout)
+        idx += 1
+        if bn:
+            sd[f"model.{idx}.weight"] = torch.from_numpy((1.0 + 0.02 * rng.standard_normal(cout)).astype(np.float32))
+            sd[f"model.{idx}.bias"] = torch.zeros(cout)
+            sd[f"model.{idx}.running_mean"] = torch.zeros(cout)
+            sd[f"model.{idx}.running_var"] = torch.ones(cout)
+            sd[f"model.{idx}.num_batches_tracked"] = torch.tensor(0, dtype=torch.int64)
+            idx += 1
+        idx += 1  # LeakyReLU slot (absent after the last conv)
+    return sd
+
+
+def train_options(**over):
+    """argparse.Namespace with the effective defaults of `train.py --model pix2pix --direction BtoA`."""
+    import argparse
+    o = dict(gpu_ids=[], isTrain=True, checkpoints_dir="/tmp/hv_ckpt", name="synthetic", preprocess="none", input_nc=1,
+             output_nc=1, ndf=64, netD="basic", n_layers_D=3, norm="batch", init_type="normal", init_gain=0.02,
+             gan_mode="vanilla", lr=2e-4, beta1=0.5, direction="BtoA", lambda_L1=200.0, lr_policy="linear", epoch_count=1,
+             n_epochs=200, n_epochs_decay=800, continue_train=False, verbose=False, load_iter=0, epoch="latest")
+    o.update(over)
+    return argparse.Namespace(**o)

@@ -1,0 +1,277 @@
+"""GPU parity of the training-step kernels (through the C ABI).
+
+* single operators vs plain PyTorch fp32 autograd of the same op on the CPU;
+* the generator backward vs autograd through the CPU oracle restatement;
+* two full optimize_parameters() steps vs the golden vectors written by the UNMODIFIED reference
+  Pix2PixModel (oracle/make_golden_train.py -> tests/golden/train_step_n2.npz).
+Tolerance for gradients: relative L2 <= 1e-4, observed ~1e-6.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+import healthivert_gan_b200 as hv
+from healthivert_gan_b200 import _lib, networks, train_ops as T
+from healthivert_gan_b200.pix2pix_model import Pix2PixModel
+from oracle import generator_ref as gr
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+PROBES = np.random.Generator(np.random.PCG64(5)).random(8)
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def probe(t):
+    t = t.detach().double().reshape(-1).cpu()
+    return t[torch.from_numpy((PROBES * t.numel()).astype(np.int64))].numpy()
+
+
+ACT = {"elu": F.elu, "relu": F.relu, "sigmoid": torch.sigmoid, "none": lambda t: t, "lrelu": lambda t: F.leaky_relu(t, 0.2),
+       "clamp1": lambda t: t.clamp(-1, 1)}
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,dil,h,w,act", [
+    (8, 16, 3, 1, 2, 2, 24, 40, "elu"),
+    (16, 32, 3, 2, 1, 1, 32, 64, "elu"),
+    (1, 64, 4, 2, 1, 1, 64, 64, "lrelu"),       # PatchGAN first layer
+    (32, 48, 4, 1, 1, 1, 31, 31, "none"),       # PatchGAN stride-1 layer, odd extent
+    (3, 16, 5, 1, 2, 1, 32, 32, "elu"),
+    (8, 1, 3, 1, 1, 1, 32, 32, "clamp1"),
+    (70, 20, 3, 1, 1, 1, 17, 33, "sigmoid"),    # ragged channel counts
+])
+def test_conv_dgrad_wgrad_against_autograd(cin, cout, k, stride, pad, dil, h, w, act):
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(2, cin, h, w, generator=g, requires_grad=True)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).requires_grad_()
+    b = torch.randn(cout, generator=g, requires_grad=True)
+    y = ACT[act](F.conv2d(x, wt, b, stride=stride, padding=pad, dilation=dil))
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    tape = T.Tape()
+    xv = T.Var(x.detach().cuda())
+    got = {}
+    out = T.conv2d(tape, [(xv, 0)], wt.detach().cuda(), b.detach().cuda(), k, stride, pad, dil, act, (h, w),
+                   lambda dw, db: got.update(dw=dw, db=db))
+    assert rel(out.data, y.detach()) <= 1e-5
+    out.grad = dy.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    assert rel(xv.grad, x.grad) <= 1e-4
+    assert rel(got["dw"], wt.grad) <= 1e-4
+    assert rel(got["db"], b.grad) <= 1e-4
+
+
+def test_conv_backward_through_fused_sources():
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(2, 6, 16, 16, generator=g, requires_grad=True)
+    c = torch.randn(2, 3, 32, 32, generator=g, requires_grad=True)
+    cam = torch.rand(2, 1, 64, 64, generator=g)
+    ratio = torch.rand(2, generator=g)
+    wt = (torch.randn(8, 11, 3, 3, generator=g) * 0.1).requires_grad_()
+    b = torch.randn(8, generator=g, requires_grad=True)
+    up = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    cat = torch.cat([up, c, cam[:, :, ::2, ::2], ratio.view(2, 1, 1, 1).expand(-1, -1, 32, 32)], 1)
+    y = F.elu(F.conv2d(cat, wt, b, padding=1))
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    tape = T.Tape()
+    av, cv = T.Var(a.detach().cuda()), T.Var(c.detach().cuda())
+    got = {}
+    out = T.conv2d(tape, [(av, 1), (cv, 0), (cam.cuda(), 2), (ratio.cuda(), 3)], wt.detach().cuda(), b.detach().cuda(), 3, 1, 1, 1,
+                   "elu", (32, 32), lambda dw, db: got.update(dw=dw, db=db))
+    out.grad = dy.cuda()
+    tape.backward()
+    assert rel(out.data, y.detach()) <= 1e-5
+    assert rel(av.grad, a.grad) <= 1e-4 and rel(cv.grad, c.grad) <= 1e-4
+    assert rel(got["dw"], wt.grad) <= 1e-4 and rel(got["db"], b.grad) <= 1e-4
+
+
+def test_spectral_norm_backward():
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(32, 16, 3, 3, generator=g, requires_grad=True)
+    u = F.normalize(torch.randn(32, generator=g), dim=0)
+    v = F.normalize(torch.randn(144, generator=g), dim=0)
+    sigma = torch.dot(u, torch.mv(w.reshape(32, -1), v))
+    weff = w / sigma
+    dweff = torch.randn(weff.shape, generator=g)
+    weff.backward(dweff)
+    dw = torch.empty(32, 16, 3, 3, device="cuda")
+    dev = [t.detach().cuda() for t in (dweff, weff, u, v, sigma.reshape(1))]   # keep the device copies alive across the launch
+    _lib.check(_lib.lib().hv_sn_bwd(dev[0].data_ptr(), dev[1].data_ptr(), dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
+                                    dw.data_ptr(), 32, 144, None))
+    torch.cuda.synchronize()
+    assert rel(dw, w.grad) <= 1e-5
+
+
+def _torch_patchgan(sd):
+    seq = [nn.Conv2d(1, 64, 4, 2, 1), nn.LeakyReLU(0.2), nn.Conv2d(64, 128, 4, 2, 1, bias=False), nn.BatchNorm2d(128),
+           nn.LeakyReLU(0.2), nn.Conv2d(128, 256, 4, 2, 1, bias=False), nn.BatchNorm2d(256), nn.LeakyReLU(0.2),
+           nn.Conv2d(256, 512, 4, 1, 1, bias=False), nn.BatchNorm2d(512), nn.LeakyReLU(0.2), nn.Conv2d(512, 1, 4, 1, 1)]
+    net = nn.Sequential(*seq)
+    net.load_state_dict({k.replace("model.", ""): v for k, v in sd.items()})
+    return net.train()
+
+
+def test_patchgan_forward_backward_against_torch():
+    sd = synth.synthetic_discriminator_state_dict(seed=1)
+    ref = _torch_patchgan(sd)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 1, 256, 256, generator=g, requires_grad=True)
+    y = ref(x)
+    loss = F.binary_cross_entropy_with_logits(y, torch.ones_like(y))
+    loss.backward()
+    net = networks.define_D(1, 64, "basic", 3, "batch", "normal", 0.02, [])
+    net.load_state_dict(sd)
+    net = net.cuda().train()
+    crit = networks.GANLoss("vanilla").cuda()
+    tape = T.Tape()
+    xv = T.Var(x.detach().cuda())
+    out = net.run(xv, tape)
+    assert out.data.shape == (2, 1, 30, 30)
+    assert rel(out.data, y.detach()) <= 1e-4
+    assert abs(float(crit(out.data, True)) - float(loss)) <= 1e-5
+    out.grad = crit.grad(out.data, True, 1.0)
+    tape.backward()
+    torch.cuda.synchronize()
+    assert rel(xv.grad, x.grad) <= 1e-3
+    got = dict(net.named_parameters())
+    for name, p in ref.named_parameters():
+        assert rel(got["model." + name].grad, p.grad) <= 1e-3, name
+    gsd, rsd = net.state_dict(), ref.state_dict()
+    for k in rsd:
+        if "running" in k:
+            assert rel(gsd["model." + k], rsd[k]) <= 1e-5, k
+
+
+def test_contextual_attention_backward_against_oracle_autograd():
+    g = torch.Generator().manual_seed(6)
+    f = torch.relu(torch.randn(2, 64, 64, 64, generator=g)).requires_grad_()
+    mask = torch.zeros(2, 1, 256, 256)
+    mask[:, :, 100:141] = 1
+    y_ref, _ = gr.contextual_attention(f, mask)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    tape = T.Tape()
+    fv = T.Var(f.detach().cuda())
+    y, flow, offs = T.ctx_attention(tape, fv, mask.cuda(), 10.0, True, False)
+    assert rel(y.data, y_ref.detach()) <= 1e-4
+    y.grad = dy.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    assert rel(fv.grad, f.grad) <= 2e-3
+
+
+def test_losses_and_adam_against_torch():
+    g = torch.Generator().manual_seed(9)
+    a = torch.randn(2, 1, 64, 64, generator=g, requires_grad=True)
+    b = torch.randn(2, 1, 64, 64, generator=g)
+    F.l1_loss(a, b).backward()
+    assert abs(float(T.l1_mean(a.detach().cuda(), b.cuda())) - float(F.l1_loss(a, b))) <= 1e-6
+    assert rel(T.l1_grad(a.detach().cuda(), b.cuda(), 1.0), a.grad) <= 1e-6
+    p = torch.rand(3, 1, 32, 32, generator=g, requires_grad=True)
+    gt = (torch.rand(3, 1, 32, 32, generator=g) > 0.5).float()
+    tp = (gt * p).flatten(1).sum(1)
+    dice_ref = ((2 * tp + 1e-5) / (p.flatten(1).sum(1) + gt.flatten(1).sum(1) + 1e-5)).sum() / 3
+    ((1 - dice_ref) * 15).backward()
+    dm, sums = T.dice(p.detach().cuda(), gt.cuda())
+    assert abs(float(dm) - float(dice_ref)) <= 1e-6
+    assert rel(T.dice_grad(gt.cuda(), sums, -15.0 / 3), p.grad) <= 1e-5
+    # Adam: three steps
+    w = torch.randn(1000, generator=g)
+    wr = w.clone().requires_grad_()
+    wg = nn.Parameter(w.clone().cuda())
+    ref = torch.optim.Adam([wr], lr=2e-4, betas=(0.5, 0.999))
+    ours = T.FusedAdam([wg], lr=2e-4, betas=(0.5, 0.999))
+    for i in range(3):
+        gr_ = torch.randn(1000, generator=g)
+        wr.grad = gr_.clone()
+        wg.grad = gr_.cuda()
+        ref.step()
+        ours.step()
+    assert float((wg.detach().cpu() - wr.detach()).abs().max()) <= 5e-7   # one fp32 ulp of O(1) weights
+
+
+def test_generator_backward_against_oracle_autograd(synthetic_sd):
+    sd = {k: v.clone().requires_grad_(v.dtype.is_floating_point and ("weight_orig" in k or "bias" in k or "fc_height" in k))
+          for k, v in synthetic_sd.items()}
+    x, mask, cam, ratio = synth.synthetic_slices(1, seed=21)
+    out = gr.generator_forward(sd, x, mask, cam, ratio, flow=False)
+    g = torch.Generator().manual_seed(2)
+    seeds = [torch.randn(out[i].shape, generator=g) for i in (0, 1, 2, 3, 5, 6)]
+    loss = sum((out[i] * s).sum() for i, s in zip((0, 1, 2, 3, 5, 6), seeds))
+    loss.backward()
+    gen = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    gen.load_state_dict(synthetic_sd)
+    gen = gen.cuda().eval()   # eval: no power iteration, same sigma as the oracle call above
+    tape = T.Tape()
+    outs = gen.forward_tape(tape, x.cuda(), mask.cuda(), cam.cuda(), ratio.cuda())
+    for i, s in zip((0, 1, 2, 3, 5, 6), seeds):
+        assert rel(outs[i].data, out[i].detach()) <= 1e-4
+        outs[i].grad = s.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    worst = 0.0
+    for name, p in gen.named_parameters():
+        r = sd[name].grad
+        assert r is not None and p.grad is not None, name
+        e = rel(p.grad, r)
+        worst = max(worst, e)
+        assert e <= 2e-3, (name, e)
+    print("worst relative gradient error", worst)
+
+
+def _build_model(n):
+    opt = synth.train_options(gpu_ids=[0])
+    torch.manual_seed(0)
+    m = Pix2PixModel(opt)
+    m.setup(opt)
+    m.netG.load_state_dict(synth.synthetic_generator_state_dict())
+    for k, net in enumerate((m.netD_1, m.netD_2, m.netD_3), start=1):
+        net.load_state_dict(synth.synthetic_discriminator_state_dict(seed=k))
+    m.train()
+    return m
+
+
+def test_two_training_steps_against_reference_golden(golden_dir):
+    gold = np.load(os.path.join(golden_dir, "train_step_n2.npz"))
+    m = _build_model(2)
+    batch = synth.synthetic_train_batch(n=2, seed=7)
+    m.set_input(batch)
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    names = [str(s) for s in gold["loss_names"]]
+    assert names == m.loss_names
+    got = np.array([m.get_current_losses()[k] for k in names])
+    ref = gold["losses_step1"]
+    assert np.abs(got - ref).max() <= 2e-3 * np.maximum(1.0, np.abs(ref)).max(), dict(zip(names, zip(got, ref)))
+    assert np.abs(probe(m.fake_B) - gold["fake_B_probe"]).max() <= 1e-4
+    for tag, net in (("D_1", m.netD_1), ("D_2", m.netD_2), ("D_3", m.netD_3), ("G", m.netG)):
+        pnames = [str(s) for s in gold[f"{tag}_names"]]
+        params = dict(net.named_parameters())
+        assert pnames == list(params.keys())
+        for i, name in enumerate(pnames):
+            p = params[name]
+            gn = float(p.grad.double().norm())
+            rn = float(gold[f"{tag}_grad_norm"][i])
+            assert abs(gn - rn) <= 5e-3 * rn + 1e-7, (tag, name, gn, rn)
+            assert np.abs(probe(p.grad) - gold[f"{tag}_grad_probe"][i]).max() <= 5e-3 * rn + 1e-7, (tag, name)
+            # Adam moves every weight by ~lr in the first step whatever the gradient's size: compare updated weights loosely
+            assert np.abs(probe(p) - gold[f"{tag}_param_probe"][i]).max() <= 4.5e-4, (tag, name)
+    u = np.stack([probe(v) for k, v in m.netG.state_dict().items() if k.endswith("weight_u")])
+    assert np.abs(u - gold["u_probe"]).max() <= 1e-5
+    bn = np.stack([probe(v.float()) for k, v in m.netD_1.state_dict().items() if "running" in k])
+    assert np.abs(bn - gold["bn_running"]).max() <= 1e-4
+    # second step: Adam state, BatchNorm running statistics and the power-iterated u / v carry over
+    m.set_input(batch)
+    m.optimize_parameters()
+    got2 = np.array([m.get_current_losses()[k] for k in names])
+    ref2 = gold["losses_step2"]
+    assert np.abs(got2 - ref2).max() <= 0.05 * np.maximum(1.0, np.abs(ref2)).max(), dict(zip(names, zip(got2, ref2)))
