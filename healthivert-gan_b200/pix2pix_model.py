@@ -167,12 +167,11 @@ class Pix2PixModel(BaseModel):
 
     # ------------------------------------------------------------------------------------------ D updates
     def _allreduce(self, params):
-        if self.world_size > 1:
-            import torch.distributed as dist
-            for p in params:
-                if p.grad is not None:
-                    dist.all_reduce(p.grad)
-                    check(_lib.lib().hv_axpby(0.0, None, 1.0 / self.world_size, ptr(p.grad), p.grad.numel(), _lib.stream()))
+        """Data-parallel gradient exchange: one all-reduce(mean) per parameter tensor after each net's backward
+        (4 per step: D_1, D_2, D_3, G), NCCL over NVLink when launched under torchrun."""
+        from . import sharding
+        scale = lambda t, f: check(_lib.lib().hv_axpby(0.0, None, float(f), ptr(t), t.numel(), _lib.stream()))
+        sharding.allreduce_mean_([p.grad for p in params if p.grad is not None], self.world_size, scale)
 
     def _backward_D(self, netD, fake, real, idx):
         """reference backward_D_k (:267-314): 0.5 * (BCE(D(fake.detach()), 0) + BCE(D(real), 1)), gradients into netD."""

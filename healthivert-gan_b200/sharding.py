@@ -42,3 +42,16 @@ def volume_slices(n_sagittal: int, n_coronal: int) -> List[Tuple[str, int]]:
     """The (orientation, index) work list of one straightened volume: sagittal slices [:, :, z]
     (eval_3d_sagittal_twostage.py:201) then coronal slices [:, z, :] (RHLV_quantification_coronal.py:51-54)."""
     return [("sagittal", z) for z in range(n_sagittal)] + [("coronal", z) for z in range(n_coronal)]
+
+
+def allreduce_mean_(tensors, world: int, scale_inplace) -> None:
+    """Gradient exchange of the data-parallel training step: ``all_reduce(SUM)`` every tensor in place, then
+    ``scale_inplace(t, 1 / world)``.  BatchNorm statistics stay per rank and the spectral-norm u / v buffers need no broadcast
+    (they are a deterministic function of the replicated weights).  ``scale_inplace`` is the device kernel on the GPU path
+    (hv_axpby) - the CPU tests pass a torch lambda; the collective itself is torch.distributed (NCCL over NVLink / gloo)."""
+    if world <= 1:
+        return
+    import torch.distributed as dist
+    for t in tensors:
+        dist.all_reduce(t)
+        scale_inplace(t, 1.0 / world)

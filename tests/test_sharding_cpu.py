@@ -63,3 +63,30 @@ def test_world_size_2_gloo_matches_single_process(tmp_path):
     want = torch.tensor([[v * 1000 + z + 1 for z in range(n_slices)] for v in range(n_volumes)])
     assert torch.equal(got["res"], want)       # every (volume, slice) produced exactly once
     assert got["tmax"] == 2.0
+
+
+def _grad_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(100 + rank)
+        grads = [torch.randn(7, 5, generator=g), torch.randn(11, generator=g)]
+        sharding.allreduce_mean_(grads, world, lambda t, f: t.mul_(f))
+        if rank == 0:
+            torch.save(grads, out)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_mean_world_size_2(tmp_path):
+    """The training step's only exchange: mean of the per-rank gradients, checked against a local mean."""
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_grad_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    want = None
+    for rank in range(2):
+        g = torch.Generator().manual_seed(100 + rank)
+        gs = [torch.randn(7, 5, generator=g), torch.randn(11, generator=g)]
+        want = gs if want is None else [a + b for a, b in zip(want, gs)]
+    for a, b in zip(got, want):
+        assert torch.allclose(a, b / 2, atol=1e-7)
