@@ -1,0 +1,114 @@
+"""Batched restatement of the reference's inference driver ``eval_3d_sagittal_twostage.py`` (process_nii_files :136-241 +
+run_model :46-133) on the device: per straightened volume, for every slice of the synthesis window, the iterative
+three-stage synthesis (upper neighbour -> lower neighbour -> target vertebra), **stage-major**: all slices of a stage
+run as one batch through the generator, slice preparation / stitching / uint8 hand-over between stages stay on the GPU
+(libhv_b200.so: hv_vol_to_u8, hv_slice_id_counts, hv_slice_prepare, hv_stitch, hv_slice_finish).
+
+The host only decides WHICH slices enter which stage (a [S, 3] int32 count table, one small D2H per volume), exactly the
+control decisions the reference takes at eval:186-197, :204, :213.  ``axis=2`` walks sagittal slices ``vol[:, :, z]`` like the
+reference driver; ``axis=1`` is the coronal twin (``vol[:, z, :]``, evaluation/RHLV_quantification_coronal.py:51-54) needed by
+the 2.5D RHLV features.  NIfTI I/O is out of scope: volumes come and go as arrays.
+"""
+import numpy as np
+import torch
+
+from . import _lib, mask_ops
+from ._lib import check, ptr
+
+
+class VolumeSynthesizer:
+    def __init__(self, generator, batch=64, maxheight=40):
+        """generator: healthivert_gan_b200.Generator on a CUDA device, eval mode (fp32 parity or bf16 tensor-core mode)."""
+        self.g = generator
+        self.batch = int(batch)
+        self.maxheight = int(maxheight)
+        self.dev = next(generator.parameters()).device
+        if self.dev.type != "cuda":
+            raise _lib.HvError("VolumeSynthesizer needs the generator on a CUDA device (no CPU fallback)")
+
+    # ---------------------------------------------------------------------------------------- helpers
+    def _to_u8_slices(self, vol, axis, scale):
+        v = torch.as_tensor(np.ascontiguousarray(vol, dtype=np.float64)).to(self.dev)
+        d0, d1, d2 = v.shape
+        s, ncol = (d2, d1) if axis == 2 else (d1, d2)
+        out = torch.empty(s, d0, ncol, device=self.dev, dtype=torch.uint8)
+        check(_lib.lib().hv_vol_to_u8(ptr(v), ptr(out), d0, d1, d2, axis, float(scale), _lib.stream()))
+        return out
+
+    def _stage(self, slices, vert_id, label_in, label_next, ct_u8, cam_u8, ratios, ct_out, label_out):
+        """One run_model() per entry of ``slices`` (all with the same vertebra id), batched."""
+        L = _lib.lib()
+        S, h, w = label_in.shape
+        dev = self.dev
+        for chunk in (slices[i:i + self.batch] for i in range(0, len(slices), self.batch)):
+            nb = len(chunk)
+            idx = torch.tensor(chunk, device=dev, dtype=torch.int32)
+            vid = torch.full((nb,), int(vert_id), device=dev, dtype=torch.int32)
+            scratch = torch.empty(2 * nb * h * w, device=dev, dtype=torch.int32)
+            keep = torch.empty(nb * h * w, device=dev, dtype=torch.uint8)
+            meta = torch.empty(nb, 8, device=dev, dtype=torch.int32)
+            f = lambda: torch.empty(nb, 1, h, w, device=dev, dtype=torch.float32)
+            ct, mask, cam1m, ori = f(), f(), f(), f()
+            x1, x2, hh = (torch.empty(nb, device=dev, dtype=torch.int32) for _ in range(3))
+            st = _lib.stream()
+            check(L.hv_slice_prepare(ptr(label_in), ptr(ct_u8), ptr(cam_u8), ptr(idx), ptr(vid), nb, h, w, self.maxheight, ptr(scratch),
+                                     ptr(keep), ptr(meta), ptr(ct), ptr(mask), ptr(cam1m), ptr(ori), ptr(x1), ptr(x2), ptr(hh), st))
+            ratio = torch.tensor([ratios[z] for z in chunk], device=dev, dtype=torch.float32)
+            with torch.no_grad():
+                _, fine_seg, _, x_stage2, _, _, pred2_h = self.g(ct, mask, cam1m, ratio)
+            fake_ct, rows = mask_ops.stitch(x_stage2, ori, pred2_h, x1, x2, hh, self.maxheight, return_rows=True)
+            check(L.hv_slice_finish(ptr(fake_ct), ptr(fine_seg), ptr(rows), ptr(meta), ptr(idx), ptr(vid), ptr(label_in), nb, h, w,
+                                    ptr(ct_out), ptr(label_out), ptr(ct_u8), ptr(label_next), _lib.stream()))
+            self.last_meta = meta
+
+    # ---------------------------------------------------------------------------------------- driver
+    @torch.no_grad()
+    def synthesize(self, ct_vol, label_vol, cam_vol, vert_id, axis=2, cam_scale=255.0, return_device=False):
+        """process_nii_files for ONE volume.  ct_vol / label_vol / cam_vol: [d0, d1, d2] arrays (the reference's get_fdata()
+        float64 volumes; cam in [0, 1], multiplied by ``cam_scale`` like eval:181).  Returns (ct_fake, label_fake) volumes of the
+        input shape (float32), zero outside the synthesis window exactly like the reference's np.zeros_like outputs."""
+        vert_id = int(vert_id)
+        prev_flags = (self.g.per_sample_mask, self.g.return_flow)
+        self.g.per_sample_mask, self.g.return_flow = True, False     # the reference driver is batch-1: every slice has its own mask
+        try:
+            ct_u8 = self._to_u8_slices(ct_vol, axis, 1.0)
+            lab_a = self._to_u8_slices(label_vol, axis, 1.0)
+            cam_u8 = self._to_u8_slices(cam_vol, axis, cam_scale)
+            S, h, w = lab_a.shape
+            counts = torch.empty(S, 3, device=self.dev, dtype=torch.int32)
+            check(_lib.lib().hv_slice_id_counts(ptr(lab_a), S, h * w, vert_id - 1, vert_id, vert_id + 1, ptr(counts), _lib.stream()))
+            cnt = counts.cpu().numpy()
+            ct_out = torch.zeros(S, h, w, device=self.dev, dtype=torch.float32)
+            label_out = torch.zeros(S, h, w, device=self.dev, dtype=torch.float32)
+            present = np.nonzero(cnt[:, 1] > 0)[0]
+            if present.size:
+                z0, z1 = int(present.min()), int(present.max())                      # eval:186-197
+                range_length = z1 - z0 + 1
+                new_len = int(range_length * 4 / 5)
+                new_z0 = z0 + (range_length - new_len) // 2
+                new_z1 = new_z0 + new_len - 1
+                center = (new_z0 + new_z1) // 2
+                zs = list(range(new_z0, new_z1 + 1))
+                ratios = {z: abs(z - center) / range_length * 2 for z in zs}         # eval:202-203
+                upper = [z for z in zs if vert_id > 8 and cnt[z, 0] > 200]           # eval:204
+                lower = [z for z in zs if vert_id < 24 and cnt[z, 2] > 200]          # eval:213
+                lab_b = lab_a.clone()
+                cur, nxt = lab_a, lab_b
+                for stage_slices, vid, final in ((upper, vert_id - 1, False), (lower, vert_id + 1, False), (zs, vert_id, True)):
+                    if not stage_slices:
+                        continue
+                    nxt.copy_(cur)                                                   # slices outside the stage pass through
+                    self._stage(stage_slices, vid, cur, nxt, ct_u8, cam_u8, ratios, ct_out if final else None,
+                                label_out if final else None)
+                    cur, nxt = nxt, cur
+            # back to the volume's own axis order
+            if axis == 2:
+                ct_f, lab_f = ct_out.permute(1, 2, 0), label_out.permute(1, 2, 0)
+            else:
+                ct_f, lab_f = ct_out.permute(1, 0, 2), label_out.permute(1, 0, 2)
+            ct_f, lab_f = ct_f.contiguous(), lab_f.contiguous()
+            if return_device:
+                return ct_f, lab_f
+            return ct_f.cpu().numpy(), lab_f.cpu().numpy()
+        finally:
+            self.g.per_sample_mask, self.g.return_flow = prev_flags

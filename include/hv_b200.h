@@ -250,6 +250,31 @@ int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, floa
 int hv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
                  float beta1, float beta2, float eps, int step, hv_stream_t stream);
 
+/* ======================================================================================
+ * A9 / N1: device-side slice preparation and post-processing of the iterative eval loop
+ * (run_model, eval_3d_sagittal_twostage.py:46-133), batched over the slices of a stage.
+ * Volumes are held as uint8 SLICE-MAJOR planes [S][h][w] (numpy astype(uint8) semantics).
+ * ==================================================================================== */
+/* out[s][r][c] = (uint8) trunc(vol * scale): vol float64 [d0][d1][d2]; axis 2: slices vol[:,:,s]
+ * (sagittal, eval:201), axis 1: vol[:,s,:] (coronal, RHLV_quantification_coronal.py:51-54)  */
+int hv_vol_to_u8(const double* vol, uint8_t* out, int d0, int d1, int d2, int axis, double scale, hv_stream_t stream);
+/* counts[s][j] = #pixels of slice s equal to id_j (np.sum(label[:,:,z]==id) > 200 tests, eval:204,:213; z range :186-197) */
+int hv_slice_id_counts(const uint8_t* label, int nslices, int hw, int id0, int id1, int id2, int32_t* counts, hv_stream_t stream);
+/* per batch entry b (slice slice_idx[b], vertebra vert_ids[b]): label==id, 8-connected components < 50 px removed
+ * (eval:16-30), bounds / window (:51-72) -> meta[b][8] = (valid, x1, x2, height, min_x, max_x, pixels, 0); then the
+ * generator inputs ct / mask / cam1m (= 1 - CAM) / ori_ct [nb,1,h,w] fp32 (:73-98) and x1 / x2 / height [nb].
+ * lab_scratch: 2*nb*h*w int32; keep_scratch: nb*h*w bytes.                                  */
+int hv_slice_prepare(const uint8_t* label_planes, const uint8_t* ct_planes, const uint8_t* cam_planes,
+                     const int32_t* slice_idx, const int32_t* vert_ids, int nb, int h, int w, int maxheight,
+                     int32_t* lab_scratch, uint8_t* keep_scratch, int32_t* meta, float* ct, float* mask, float* cam1m,
+                     float* ori, int32_t* x1, int32_t* x2, int32_t* height, hv_stream_t stream);
+/* after the forward and hv_stitch(x_stage2, ori, pred2_h, ...): (x+1)*127.5 -> ct_out (fp32 slice of the output volume,
+ * may be NULL) and its uint8 truncation ct_u8_next; thresholded seg * id stitched into the label map (eval:119-130) ->
+ * label_out (fp32, may be NULL) / label_next (uint8; must not alias label_in)               */
+int hv_slice_finish(const float* fake_ct, const float* fine_seg, const int32_t* rows, const int32_t* meta,
+                    const int32_t* slice_idx, const int32_t* vert_ids, const uint8_t* label_in, int nb, int h, int w,
+                    float* ct_out, float* label_out, uint8_t* ct_u8_next, uint8_t* label_next, hv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

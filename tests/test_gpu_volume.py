@@ -1,0 +1,144 @@
+"""GPU parity of the device-side slice preparation (A9) and the batched volume driver against the oracle restatement of
+run_model / process_nii_files and the golden vectors written by the unmodified reference (tests/golden/run_model.npz)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import healthivert_gan_b200 as hv
+from healthivert_gan_b200 import _lib
+from healthivert_gan_b200._lib import check, ptr
+from healthivert_gan_b200.volume import VolumeSynthesizer
+from oracle import generator_ref as gr
+from oracle import mask_ops_ref as mo
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def gen(synthetic_sd):
+    g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    g.load_state_dict(synthetic_sd)
+    return g.cuda().eval()
+
+
+def _prepare(vs, label_u8, ct_u8, cam_u8, slices, vid):
+    L = _lib.lib()
+    S, h, w = label_u8.shape
+    nb = len(slices)
+    dev = label_u8.device
+    idx = torch.tensor(slices, device=dev, dtype=torch.int32)
+    v = torch.full((nb,), vid, device=dev, dtype=torch.int32)
+    scratch = torch.empty(2 * nb * h * w, device=dev, dtype=torch.int32)
+    keep = torch.empty(nb * h * w, device=dev, dtype=torch.uint8)
+    meta = torch.empty(nb, 8, device=dev, dtype=torch.int32)
+    planes = [torch.empty(nb, 1, h, w, device=dev) for _ in range(4)]
+    ints = [torch.empty(nb, device=dev, dtype=torch.int32) for _ in range(3)]
+    check(L.hv_slice_prepare(ptr(label_u8), ptr(ct_u8), ptr(cam_u8), ptr(idx), ptr(v), nb, h, w, 40, ptr(scratch), ptr(keep), ptr(meta),
+                             *[ptr(p) for p in planes], *[ptr(i) for i in ints], None))
+    torch.cuda.synchronize()
+    return meta.cpu().numpy(), [p.cpu().numpy() for p in planes], keep.reshape(nb, h, w).cpu().numpy()
+
+
+def test_slice_prepare_bit_exact_against_oracle(gen):
+    label, ct, cam = synth.synthetic_volume(seed=3, depth=24)
+    rng = np.random.Generator(np.random.PCG64(1))
+    # specks (< 50 px, must be removed), a tall vertebra (height > 40 re-centring) and fractional CT values (uint8 truncation)
+    label[5:9, 200:206, :] = 20
+    label[60:130, 100:120, 5] = 21
+    ct = ct + rng.random(ct.shape) * 0.999
+    ct = np.clip(ct, 0, 255.999)
+    vs = VolumeSynthesizer(gen)
+    lab8, ct8, cam8 = vs._to_u8_slices(label, 2, 1.0), vs._to_u8_slices(ct, 2, 1.0), vs._to_u8_slices(cam, 2, 255.0)
+    assert np.array_equal(ct8.cpu().numpy(), np.transpose(ct.astype(np.uint8), (2, 0, 1)))
+    assert np.array_equal(cam8.cpu().numpy(), np.transpose((cam * 255).astype(np.uint8), (2, 0, 1)))
+    for vid in (19, 20, 21, 7):
+        slices = list(range(0, 24, 3)) + [5]
+        meta, planes, keep = _prepare(vs, lab8, ct8, cam8, slices, vid)
+        for b, z in enumerate(slices):
+            ref = mo.slice_prep(cam[:, :, z] * 255, label[:, :, z], ct[:, :, z], vid)
+            if ref is None:
+                assert meta[b, 0] == 0, (vid, z)
+                continue
+            assert meta[b, 0] == 1
+            assert tuple(meta[b, 1:6]) == (ref["x1"], ref["x2"], ref["height"], ref["min_x"], ref["max_x"]), (vid, z)
+            vert = mo.remove_small_components((label[:, :, z] == vid).astype(np.uint8), 50)
+            assert np.array_equal(keep[b], vert), (vid, z)
+            assert np.array_equal(planes[0][b, 0], ref["ct"]), (vid, z)
+            assert np.array_equal(planes[1][b, 0], ref["mask"]), (vid, z)
+            assert np.array_equal(planes[2][b, 0], np.float32(1) - ref["cam"]), (vid, z)
+            assert np.array_equal(planes[3][b, 0], ref["ori_ct"]), (vid, z)
+
+
+def test_single_stage_against_reference_golden(gen, golden_dir):
+    gold = np.load(os.path.join(golden_dir, "run_model.npz"))
+    label, ct, cam = synth.synthetic_volume(seed=0, depth=64)
+    vs = VolumeSynthesizer(gen)
+    gen.per_sample_mask, gen.return_flow = True, False
+    try:
+        for z, vid in ((32, 20), (20, 19), (40, 21)):
+            lab8, ct8, cam8 = vs._to_u8_slices(label, 2, 1.0), vs._to_u8_slices(ct, 2, 1.0), vs._to_u8_slices(cam, 2, 255.0)
+            nxt = lab8.clone()
+            ct_out = torch.zeros(64, 256, 256, device="cuda")
+            lab_out = torch.zeros(64, 256, 256, device="cuda")
+            vs._stage([z], vid, lab8, nxt, ct8, cam8, {z: abs(z - 32) / 50 * 2}, ct_out, lab_out)
+            torch.cuda.synchronize()
+            got_ct, got_seg = ct_out[z].cpu().numpy(), lab_out[z].cpu().numpy()
+            assert np.abs(got_ct - gold[f"ct_{z}_{vid}"]).max() <= 0.05, (z, vid)     # 1e-3-level generator noise * 127.5
+            assert (got_seg.astype(np.uint8) != gold[f"seg_{z}_{vid}"]).mean() <= 1e-4, (z, vid)
+            assert int(vs.last_meta[0, 3]) == int(gold[f"height_{z}_{vid}"])
+            assert np.array_equal(ct8[z].cpu().numpy(), got_ct.astype(np.uint8))      # hand-over plane of the next stage
+    finally:
+        gen.per_sample_mask, gen.return_flow = False, True
+
+
+def _oracle_volume(sd, ct, label, cam, vert_id):
+    """process_nii_files (eval:153-234) restated with the oracle pieces, batch 1, on the CPU."""
+    out_ct, out_seg = np.zeros_like(ct), np.zeros_like(ct)
+    loc = np.where(label == vert_id)
+    z0, z1 = loc[2].min(), loc[2].max()
+    rl = z1 - z0 + 1
+    nl = int(rl * 4 / 5)
+    nz0 = z0 + (rl - nl) // 2
+    nz1 = nz0 + nl - 1
+    center = (nz0 + nz1) // 2
+    cam255 = cam * 255
+
+    def run(lab2d, ct2d, z, vid, ratio):
+        p = mo.slice_prep(cam255[:, :, z], lab2d, ct2d, vid)
+        if p is None:
+            return None
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a))[None, None]
+        with torch.no_grad():
+            o = gr.generator_forward(sd, t(p["ct"]), t(p["mask"]), 1 - t(p["cam"]), torch.tensor([ratio], dtype=torch.float32), flow=False)
+        seg, fake = mo.eval_postprocess(o[1][0, 0].numpy(), o[3][0, 0].numpy(), float(o[6][0, 0]), p["ori_ct"], lab2d, p["x1"], p["x2"],
+                                        p["height"], vid)
+        return seg, fake
+
+    for z in range(nz0, nz1 + 1):
+        ratio = abs(z - center) / rl * 2
+        lab2d, ct2d = label[:, :, z], ct[:, :, z]
+        if vert_id > 8 and np.sum(label[:, :, z] == vert_id - 1) > 200:
+            lab2d, ct2d = run(lab2d, ct2d, z, vert_id - 1, ratio)
+        if vert_id < 24 and np.sum(label[:, :, z] == vert_id + 1) > 200:
+            lab2d, ct2d = run(lab2d, ct2d, z, vert_id + 1, ratio)
+        o = run(lab2d, ct2d, z, vert_id, ratio)
+        if o is not None:
+            out_seg[:, :, z], out_ct[:, :, z] = o
+    return out_ct, out_seg
+
+
+def test_volume_driver_three_stage_loop_against_oracle(gen, synthetic_sd):
+    label, ct, cam = synth.synthetic_volume(seed=5, depth=8)
+    ref_ct, ref_seg = _oracle_volume(synthetic_sd, ct, label, cam, 20)
+    vs = VolumeSynthesizer(gen, batch=4)
+    got_ct, got_seg = vs.synthesize(ct, label, cam, 20)
+    assert got_ct.shape == ct.shape
+    done = np.nonzero(ref_seg.any(axis=(0, 1)))[0]
+    assert done.size >= 3
+    assert np.array_equal(np.nonzero(got_seg.any(axis=(0, 1)))[0], done)
+    # three chained forwards: fp32 re-association noise can flip isolated threshold / truncation decisions
+    assert (got_seg != ref_seg).mean() <= 2e-4
+    assert np.abs(got_ct - ref_ct).max() <= 2.0 and np.abs(got_ct - ref_ct).mean() <= 0.01
