@@ -101,6 +101,8 @@ def synthetic_volume(seed=0, depth=64, target_id=20):
     label = np.zeros((256, 256, depth), np.float64)
     heights = rng.integers(22, 35, size=7)
     gaps = rng.integers(6, 9, size=7)
+    while int(heights.sum() + gaps.sum()) > 248:   # seeds whose stack would not fit 256 rows (used to raise): trim the tallest
+        heights[int(np.argmax(heights))] -= 1
     total = int(heights.sum() + gaps.sum())
     r = (256 - total) // 2
     yy, zz = np.meshgrid(np.arange(256), np.arange(depth), indexing="ij")
