@@ -62,6 +62,28 @@ __device__ __forceinline__ void issue_segment(bool leader, uint32_t d_tmem, uint
   }
 }
 
+// Stride-2 3x3 conv on a space-to-depth source, all 9 taps from ONE shared-memory image [chunk][sub-plane 4][row 2][128][8]:
+// input pixel (2y+ky-1, 2x+kx-1) lives in sub-plane ((ky+1)&1, (kx+1)&1) at (y+dy, x+dx), dy/dx = -1 for ky/kx = 0; row r = dy+1,
+// and the band starts one position early so that dx = -1 is offset 0.
+template <int N_PAD, int KSTEPS>
+__device__ __forceinline__ void issue_s2d(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t slab, uint32_t idesc) {
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  constexpr uint32_t a_lbo = 8u * TC_TILE_M;  // 4 sub-planes x 2 rows per chunk
+  if (leader) {
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t sub = (uint32_t)(((ky + 1) & 1) * 2 + ((kx + 1) & 1)), r = ky == 0 ? 0u : 1u, off = kx == 0 ? 0u : 1u;
+          const uint32_t a_lo = a_base + (sub * 2u + r) * TC_TILE_M + off + (uint32_t)ks * 2u * a_lbo;
+          const uint32_t b_lo = b_base + (uint32_t)(ky * 3 + kx) * slab + (uint32_t)ks * 2u * N_PAD;
+          umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (ky | kx | ks) == 0 ? 0u : 1u);
+        }
+  }
+}
+
 // generic (slow) fallback for shapes without an unrolled instance
 template <int N_PAD>
 __device__ __forceinline__ void issue_segment_generic(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t a_step,
@@ -81,7 +103,7 @@ __device__ __forceinline__ void issue_segment_generic(bool leader, uint32_t d_tm
 }
 
 constexpr int TC_TMEM_COLS = 256;
-constexpr int TC_BAR_BYTES = 1024;  // mbarriers + TMEM slot + bias vector
+constexpr int TC_BAR_BYTES = 1024;  // mbarriers + TMEM slot (512 B) + bias vector (512 B)
 // 16 epilogue warps, 16 accumulator columns each: N_PAD/16*4 warps cover one tile (4 TMEM lane quadrants x column groups), so
 // 16/that many tiles are in the epilogue concurrently (4 / 2 / 1 for N_PAD = 16 / 32 / 64); group g owns tiles j % groups == g
 __host__ __device__ constexpr int tc_epi_warps(int) { return 16; }
@@ -147,19 +169,26 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
     int slot = 0, ntr = 0;
     uint32_t phase = 0;
     const uint32_t slots_base = smem_u32(s_slots);
+    const int nseg = p.nseg, nslots = p.nslots;
+    const bool s2d = p.s2d_in != 0;
+    const uint32_t slot_bytes = p.slot_bytes;
+    int rel2 = p.segs[0].rel_start2, c1 = p.segs[0].c1;   // single-segment layers keep the load recipe in registers
+    uint32_t tx = p.segs[0].tx_bytes;
+    bool map1 = false;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.tiles_per_image;
       const int c_tile = 2 * ((tile - img * p.tiles_per_image) * p.tile_adv + p.q_first);  // tensor-map inner unit = 8 B
-      for (int s = 0; s < p.nseg; ++s) {
+      for (int s = 0; s < nseg; ++s) {
+        if (nseg > 1) { rel2 = p.segs[s].rel_start2; c1 = p.segs[s].c1; tx = p.segs[s].tx_bytes; map1 = p.segs[s].map != 0; }
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
         if (leader) {
-          const uint32_t fb = bar_full + 8u * slot;
-          mbar_expect_tx(fb, p.segs[s].tx_bytes);
-          tma_load_4d(slots_base + (uint32_t)slot * p.slot_bytes, &p.maps[p.segs[s].map], fb, c_tile + p.segs[s].rel_start2,
-                      p.segs[s].c1, 0, img);
+          const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_bytes;
+          mbar_expect_tx(fb, tx);
+          if (s2d) tma_load_5d(dst, &p.maps[0], fb, c_tile + rel2, 0, 0, 0, img);   // {positions, 2 rows, 4 sub-planes, chunks, image}
+          else tma_load_4d(dst, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, 0, img);
           trace_ev(p.trace, ntr, 1);
         }
-        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        if (++slot == nslots) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == W_MMA) {
@@ -182,6 +211,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
     // hides under the queued MMAs (the tensor pipe accepts only a few MMAs ahead of execution)
     bool ready_full = mbar_peek(bar_full, 0), ready_acc = mbar_peek(bar_tempty, 1);
     const int nseg = p.nseg;
+    const bool s2d = p.s2d_in != 0;
     TcSeg sg = p.segs[0];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait_peeked(ready_acc, bar_tempty + 8u * acc, acc_phase ^ 1u);
@@ -196,15 +226,24 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __g
         const int nrows = sg.nrows, ntaps = sg.ntaps, ksteps = sg.nchunks >> 1;
         const uint32_t a_lbo = (uint32_t)nrows * TC_TILE_M;  // 16 B units: K chunks of the segment image are nrows bands apart
         const uint32_t a_step = sg.a_step, b_step = sg.b_step, b_row_step = sg.b_row_step;
-        const uint32_t a_row = a_lo_base + (uint32_t)slot * slot_units + (a_lbo << 16) + sg.a0;
-        const uint32_t b_row = b_lo_base + sg.b0;
         mbar_wait_peeked(ready_full, bar_full + 8u * slot, phase);
         tc_fence_after();
         if (leader) trace_ev(tr, ntr, 12);
-        const uint32_t cur_empty = bar_empty + 8u * slot;
+        const uint32_t cur_slot = (uint32_t)slot, cur_empty = bar_empty + 8u * slot;
         if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         ready_full = mbar_peek(bar_full + 8u * slot, phase);
+        const uint32_t a_row = a_lo_base + cur_slot * slot_units + (a_lbo << 16) + sg.a0;
+        const uint32_t b_row = b_lo_base + sg.b0;
         if (s == nseg - 1) ready_acc = mbar_peek(bar_tempty + 8u * acc, acc_phase ^ 1u);
+        if (s2d) {
+          const uint32_t a_s2d = a_lo_base + cur_slot * slot_units + ((8u * TC_TILE_M) << 16);
+          if (ksteps == 1) issue_s2d<N_PAD, 1>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
+          else if (ksteps == 2) issue_s2d<N_PAD, 2>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
+          else issue_s2d<N_PAD, 4>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
+          accumulate = 1;
+          if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
+          continue;
+        }
         const int shape = (nrows << 8) | (ntaps << 4) | ksteps;
 #define HV_SEG(R, T, K)                                                                                                   \
   case ((R) << 8) | ((T) << 4) | (K):                                                                                     \
@@ -346,12 +385,22 @@ static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks, int k, int
   CUresult r = CUDA_SUCCESS;
   const CUtensorMapDataType types[2] = {CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64};
   for (int attempt = 0; attempt < 2; ++attempt) {
-    cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, b.s2d ? 4u : (cuuint64_t)k, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
-    cuuint64_t strides[3] = {b.s2d ? sub_b : (cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.image_chunks()};
-    cuuint32_t box[4] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
-    cuuint32_t es[4] = {1, 1, 1, 1};
-    r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (!b.s2d) {
+      cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, (cuuint64_t)k, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+      cuuint64_t strides[3] = {(cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.image_chunks()};
+      cuuint32_t box[4] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+      // space-to-depth source: {positions*2, 2 rows (dy = -1, 0), 4 parity sub-planes, chunks, n}: one box = everything a tile needs
+      cuuint64_t dims[5] = {(cuuint64_t)b.sub_plane() * 2, 2, 4, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+      cuuint64_t strides[4] = {(cuuint64_t)b.pitch() * 16, sub_b, plane_b, plane_b * b.image_chunks()};
+      cuuint32_t box[5] = {2 * TC_TILE_M, 2, 4, (cuuint32_t)box_chunks, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      r = enc(map, types[attempt], 5, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
     if (r == CUDA_SUCCESS) return HV_OK;
   }
   set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -400,7 +449,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   const size_t band_bytes = (size_t)TC_TILE_M * max_chunks * 16u;
   const bool multirow = stride == 1 && fixed + 3 * (size_t)k * band_bytes <= budget;
   const int box_rows = multirow ? k : 1;
-  p.slot_bytes = (uint32_t)(band_bytes * box_rows);
+  p.slot_bytes = (uint32_t)(band_bytes * (stride == 2 ? 8 : box_rows));
   HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
   int seg = 0, max_shift = 0;
   uint32_t woff16 = 0;
@@ -421,19 +470,13 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
         else { sg.b0 = woff16 + (uint32_t)(ky * k) * slab; sg.b_step = slab; sg.b_row_step = (uint32_t)k * slab; }
       }
     } else {
-      // input pixel (2y+ky-1, 2x+kx-1) lives in sub-plane ((ky+1)&1, (kx+1)&1) at (y+dy, x+dx), dy/dx = -1 for k*=0
+      // one segment = one 5-D box [chunk][4 sub-planes][2 rows][128 positions]; taps are enumerated by issue_s2d
       max_shift = 1;
-      for (int ky = 0; ky < 3; ++ky)
-        for (int px = 1; px >= 0; --px) {
-          HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
-          TcSeg& sg = p.segs[seg++];
-          const int py = (ky + 1) & 1, dy = ky == 0 ? -1 : 0;
-          sg.map = s; sg.c1 = py * 2 + px; sg.nchunks = nch; sg.nrows = 1;
-          sg.rel_start2 = 2 * (dy * pitch + (px == 1 ? -1 : 0));
-          sg.a0 = 0; sg.b_row_step = 0;
-          if (px == 1) { sg.ntaps = 2; sg.a_step = 1; sg.b0 = woff16 + (uint32_t)(ky * 3) * slab; sg.b_step = 2 * slab; }   // kx = 0, 2
-          else { sg.ntaps = 1; sg.a_step = 0; sg.b0 = woff16 + (uint32_t)(ky * 3 + 1) * slab; sg.b_step = 0; }              // kx = 1
-        }
+      HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
+      TcSeg& sg = p.segs[seg++];
+      sg.map = s; sg.c1 = 0; sg.nchunks = nch; sg.nrows = 8; sg.ntaps = 9;
+      sg.rel_start2 = 2 * (-pitch - 1);
+      sg.a0 = 0; sg.a_step = 0; sg.b0 = woff16; sg.b_step = slab; sg.b_row_step = 0;
     }
     woff16 += (uint32_t)(srcs[s].kxpack ? k : k * k) * slab;
   }
