@@ -110,13 +110,16 @@ __host__ __device__ constexpr int tc_epi_warps(int) { return 16; }
 __host__ __device__ constexpr int tc_warps_per_tile(int n_pad) { return n_pad / 16 * 4; }
 __host__ __device__ constexpr int tc_threads(int n_pad) { return 64 + 32 * tc_epi_warps(n_pad); }
 __host__ __device__ constexpr int tc_acc_stages(int n_pad) { return TC_TMEM_COLS / n_pad > 8 ? 8 : TC_TMEM_COLS / n_pad; }
+// thin layers (N_PAD <= 32) are bound by the single-lane issue / handshake latencies, not by the tensor pipe: two CTAs per SM
+// (2 x 256 TMEM columns, <= 56 registers per thread) interleave their MMA streams
+__host__ __device__ constexpr int tc_ctas_per_sm(int n_pad) { return n_pad <= 32 ? 2 : 1; }
 
 // ------------------------------------------------------------------------------------------- kernel
 // warps 0..15: epilogue, warp 16: TMA producer, warp 17: TMEM allocator + MMA issuer.  The single-lane roles sit on the
 // HIGHEST warp ids on purpose: the SM's warp arbiter favours high warp ids, and an issuer starved by busy epilogue warps
 // stalls the tensor pipe.
 template <int N_PAD, int ACT>
-__global__ void __launch_bounds__(tc_threads(N_PAD), 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ACC_STAGES = tc_acc_stages(N_PAD);       // accumulator tiles in flight
   constexpr int EPI_WARPS = tc_epi_warps(N_PAD);
   constexpr int WPT = tc_warps_per_tile(N_PAD), GROUPS = EPI_WARPS / WPT;
@@ -408,6 +411,12 @@ static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks, int k, int
 }
 
 // ------------------------------------------------------------------------------------------- host: setup
+static int max_chunks_of(const TcSource* srcs, int nsrc) {
+  int m = 0;
+  for (int i = 0; i < nsrc; ++i) m = max(m, srcs[i].buf.chunks);
+  return m;
+}
+
 int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images) {
   HV_CHECK_ARG(nsrc >= 1 && nsrc <= 2, "tc_conv: 1 or 2 sources supported");
   HV_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || (stride == 2 && k == 3 && dil == 1)), "tc_conv: unsupported k/stride");
@@ -443,8 +452,14 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.q_first = b0.border * pitch + b0.border;
   p.w_bytes = 0;
   for (int i = 0; i < nsrc; ++i) p.w_bytes += (uint32_t)((srcs[i].kxpack ? k : k * k) * srcs[i].buf.chunks * c.n_pad * 16);
-  const size_t budget = 227 * 1024 - 2048;
+  size_t budget = 227 * 1024 - 2048;
   const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
+  c.ctas_per_sm = 1;
+  {  // two co-resident CTAs when the layer is thin and three tile slots still fit in half the shared memory (measured: with
+     // only two slots per CTA the merged fine conv1|pmconv1 layer got 30 % slower)
+    const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k);
+    if (tc_ctas_per_sm(c.n_pad) == 2 && fixed + 3 * band <= half) { c.ctas_per_sm = 2; budget = half; }
+  }
   // all k kernel rows of a source in one TMA load when at least 3 such slots fit beside the weights
   const size_t band_bytes = (size_t)TC_TILE_M * max_chunks * 16u;
   const bool multirow = stride == 1 && fixed + 3 * (size_t)k * band_bytes <= budget;
@@ -503,7 +518,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c.grid = min(p.total_tiles, sms);
+  c.grid = min(p.total_tiles, sms * c.ctas_per_sm);
   return HV_OK;
 }
 

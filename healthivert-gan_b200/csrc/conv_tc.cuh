@@ -115,6 +115,7 @@ struct TcConv {
   TcParams p;
   int n_pad = 0;
   int grid = 0;
+  int ctas_per_sm = 1;
   size_t smem = 0;
   void* w_packed = nullptr;   // owned
   float* bias_pad = nullptr;  // owned

@@ -342,7 +342,7 @@ static void tc_set_batch(TcConv& c, int n) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c.grid = c.p.total_tiles < sms ? c.p.total_tiles : sms;
+  c.grid = c.p.total_tiles < sms * c.ctas_per_sm ? c.p.total_tiles : sms * c.ctas_per_sm;
 }
 
 static int tc_plan_pack_weights(hv_generator* g, cudaStream_t st) {
