@@ -12,6 +12,7 @@
 //   warps 2-5: epilogue       - tcgen05.ld (one TMEM lane quadrant each) -> bias/act -> bf16 -> global
 // Pipelines: smem band ring (full/empty mbarriers, tcgen05.commit frees a slot) and a 2-deep TMEM
 // accumulator ring so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "hv_common.cuh"
@@ -162,6 +163,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // PDL: let the next kernel of the stream start its own prologue as soon as SM resources free up ...
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp == W_PRODUCER) {
     // ===================================================================== TMA producer (warp-uniform, one lane issues)
     const bool leader = elect_one();
@@ -169,6 +172,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
       mbar_expect_tx(bar_w, p.w_bytes);
       bulk_load(smem_u32(smem), p.w_packed, p.w_bytes, bar_w);
     }
+    // ... and do not read the previous kernel's output (the activation bands) before it has completed and flushed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     int slot = 0, ntr = 0;
     uint32_t phase = 0;
     const uint32_t slots_base = smem_u32(s_slots);
@@ -600,6 +605,7 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
 }
 
 static long long* g_trace = nullptr;
+static bool g_pdl = getenv("HV_NO_PDL") == nullptr;
 void tc_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
 template <int N_PAD, int ACT>
@@ -609,13 +615,21 @@ static int tc_launch_na(const TcConv& c, cudaStream_t st) {
     HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  if (g_trace) {
-    TcParams q = c.p;
-    q.trace = g_trace;
-    conv_tc_kernel<N_PAD, ACT><<<c.grid, tc_threads(N_PAD), c.smem, st>>>(q);
-  } else {
-    conv_tc_kernel<N_PAD, ACT><<<c.grid, tc_threads(N_PAD), c.smem, st>>>(c.p);
-  }
+  // programmatic dependent launch: the kernel may start while its predecessor in the stream drains; it prefetches its
+  // weights / sets up barriers and TMEM, then griddepcontrol.wait's before touching the predecessor's output
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(c.grid);
+  cfg.blockDim = dim3(tc_threads(N_PAD));
+  cfg.dynamicSmemBytes = c.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  TcParams q = c.p;
+  q.trace = g_trace;
+  HV_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<N_PAD, ACT>, q));
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
