@@ -27,7 +27,7 @@ def main():
     for _ in range(2):
         g.run_layer(layer, n)
     torch.cuda.synchronize()
-    buf = torch.zeros(12000, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(12000 + 2 * 400, dtype=torch.int64, device="cuda")
     L.hv_debug_conv_trace(buf.data_ptr())
     g.run_layer(layer, n)
     torch.cuda.synchronize()
@@ -47,6 +47,15 @@ def main():
     print(f"layer {layer} batch {n}: {len(ev)} events, span {ev[-1][0] - t0} cycles")
     for clk, who, tag in ev[:140]:
         print(f"{clk - t0:8d} {who} {names.get(tag, tag)}")
+    ctas = [(b[12000 + 2 * i], b[12000 + 2 * i + 1]) for i in range(400) if b[12000 + 2 * i]]
+    if ctas:
+        g0 = min(c[0] for c in ctas)
+        starts = sorted(c[0] - g0 for c in ctas)
+        ends = sorted(c[1] - g0 for c in ctas)
+        durs = sorted(c[1] - c[0] for c in ctas)
+        q = lambda v, f: v[min(len(v) - 1, int(f * len(v)))]
+        print(f"CTAs {len(ctas)}: start ns p0/p50/p100 = {starts[0]}/{q(starts, .5)}/{starts[-1]}  end ns p0/p50/p100 = {ends[0]}/{q(ends, .5)}/{ends[-1]}"
+              f"  duration ns p0/p50/p100 = {durs[0]}/{q(durs, .5)}/{durs[-1]}")
     if len(ev) > 140:
         print("...")
         for clk, who, tag in ev[-30:]:
