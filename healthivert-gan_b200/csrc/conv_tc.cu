@@ -85,6 +85,30 @@ __device__ __forceinline__ void issue_s2d(bool leader, uint32_t d_tmem, uint32_t
   }
 }
 
+// 3x3 stride-1 conv on an x-phase (xp = 4) source: accumulator row = position (y, x/4), columns = 4 output phases x cp channels.
+// Output pixel x = 4q + j, tap kx reads input x + kx - 1 = 4q + d with d = j + kx - 1 in [-1, 4]: six "views" v = d + 1 of the
+// shared-memory image [chunk][phase][row][128]: phase = d mod 4, position shift = floor(d / 4) (+1: the band starts one early).
+// The weights of view v hold w[.][.][ky][kx = v - j] in the columns of phase j and zeros elsewhere.
+template <int N_PAD, int NROWS, int KSTEPS>
+__device__ __forceinline__ void issue_xp4(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t slab, uint32_t idesc,
+                                          uint32_t first_acc) {
+  constexpr uint32_t desc_hi = (128u >> 4) | (1u << 14);
+  constexpr uint32_t a_lbo = 4u * NROWS * TC_TILE_M;
+  if (leader) {
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+      for (int v = 0; v < 6; ++v)
+#pragma unroll
+        for (int ks = 0; ks < KSTEPS; ++ks) {
+          const uint32_t phase = (uint32_t)((v + 3) & 3), shift = v == 0 ? 0u : (v == 5 ? 2u : 1u);
+          const uint32_t a_lo = a_base + (phase * NROWS + (uint32_t)r) * TC_TILE_M + shift + (uint32_t)ks * 2u * a_lbo;
+          const uint32_t b_lo = b_base + (uint32_t)(r * 6 + v) * slab + (uint32_t)ks * 2u * N_PAD;
+          umma_bf16(d_tmem, ((uint64_t)desc_hi << 32) | a_lo, ((uint64_t)desc_hi << 32) | b_lo, idesc, (r | v | ks) == 0 ? first_acc : 1u);
+        }
+  }
+}
+
 // generic (slow) fallback for shapes without an unrolled instance
 template <int N_PAD>
 __device__ __forceinline__ void issue_segment_generic(bool leader, uint32_t d_tmem, uint32_t a_base, uint32_t b_base, uint32_t a_step,
@@ -178,7 +202,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     uint32_t phase = 0;
     const uint32_t slots_base = smem_u32(s_slots);
     const int nseg = p.nseg, nslots = p.nslots;
-    const bool s2d = p.s2d_in != 0;
+    const bool map5d = p.map5d != 0;
     const uint32_t slot_bytes = p.slot_bytes;
     int rel2 = p.segs[0].rel_start2, c1 = p.segs[0].c1;   // single-segment layers keep the load recipe in registers
     uint32_t tx = p.segs[0].tx_bytes;
@@ -192,7 +216,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         if (leader) {
           const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_bytes;
           mbar_expect_tx(fb, tx);
-          if (s2d) tma_load_5d(dst, &p.maps[0], fb, c_tile + rel2, 0, 0, 0, img);   // {positions, 2 rows, 4 sub-planes, chunks, image}
+          if (map5d) tma_load_5d(dst, &p.maps[0], fb, c_tile + rel2, c1, 0, 0, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
           else tma_load_4d(dst, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, 0, img);
           trace_ev(p.trace, ntr, 1);
         }
@@ -219,7 +243,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     // hides under the queued MMAs (the tensor pipe accepts only a few MMAs ahead of execution)
     bool ready_full = mbar_peek(bar_full, 0), ready_acc = mbar_peek(bar_tempty, 1);
     const int nseg = p.nseg;
-    const bool s2d = p.s2d_in != 0;
+    const bool s2d = p.s2d_in != 0, xp_in = p.in_xp > 1;
     TcSeg sg = p.segs[0];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       mbar_wait_peeked(ready_acc, bar_tempty + 8u * acc, acc_phase ^ 1u);
@@ -248,6 +272,19 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
           if (ksteps == 1) issue_s2d<N_PAD, 1>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
           else if (ksteps == 2) issue_s2d<N_PAD, 2>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
           else issue_s2d<N_PAD, 4>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
+          accumulate = 1;
+          if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
+          continue;
+        }
+        if (xp_in) {
+          const uint32_t a_xp = a_lo_base + cur_slot * slot_units + ((4u * (uint32_t)nrows * TC_TILE_M) << 16);
+          const int shape_xp = (nrows << 4) | ksteps;
+          switch (shape_xp) {
+            case (3 << 4) | 1: issue_xp4<N_PAD, 3, 1>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            case (3 << 4) | 2: issue_xp4<N_PAD, 3, 2>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            case (1 << 4) | 1: issue_xp4<N_PAD, 1, 1>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            default: issue_xp4<N_PAD, 1, 2>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+          }
           accumulate = 1;
           if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
           continue;
@@ -299,58 +336,73 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
       trace_ev(tr, ntr, 21);
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD);
 
+      // position of output pixel (y, x) inside one chunk plane of the output buffer (plain / space-to-depth / x-phase)
+      auto out_pos = [&](int y, int x) -> size_t {
+        if (p.out_mode == TC_OUT_CHUNKED_S2D)
+          return (size_t)((y & 1) * 2 + (x & 1)) * p.out_sub_plane + (size_t)((y >> 1) + p.out_border) * p.out_pitch + (x >> 1) + p.out_border;
+        if (p.out_xp > 1)
+          return (size_t)(x & (p.out_xp - 1)) * p.out_sub_plane + (size_t)(y + p.out_border) * p.out_pitch + x / p.out_xp + p.out_border;
+        return (size_t)(y + p.out_border) * p.out_pitch + x + p.out_border;
+      };
+      auto aux_store = [&](const TcAux& a, int y, int x, float val) {   // one bf16 channel of an (x-phase or plain) chunked buffer
+        const size_t pos = p.out_xp > 1 ? (size_t)(x & (p.out_xp - 1)) * a.sub_plane + (size_t)(y + a.border) * a.pitch + x / p.out_xp + a.border
+                                        : (size_t)(y + a.border) * a.pitch + x + a.border;
+        a.ptr[(((size_t)img * a.chunks + a.chunk) * a.plane + pos) * 8 + a.channel] = __float2bfloat16(val);
+      };
+
       if (p.out_mode == TC_OUT_HEADS) {
         float v[NCOL];
         if (col0 == 0) { tmem_ld<NCOL>(t_addr, v); tmem_ld_wait(); }
         tc_fence_before();
         mbar_arrive(bar_tempty + 8u * acc);
         if (!valid || col0 != 0) continue;
-        const float a0 = fminf(fmaxf(v[0] + s_bias[0], -1.f), 1.f);
-        const float a1 = 1.f / (1.f + __expf(-(v[1] + s_bias[1])));
-        const size_t pix = ((size_t)img * p.h_out + yy) * p.w_out + xx;
-        p.head0[pix] = a0;
-        p.head1[pix] = a1;
-        if (p.aux0.ptr) {
-          const TcAux& a = p.aux0;
-          a.ptr[(((size_t)img * a.chunks + a.chunk) * a.plane + (size_t)(yy + a.border) * a.pitch + xx + a.border) * 8 + a.channel] = __float2bfloat16(a0);
-        }
-        if (p.aux1.ptr) {
-          const TcAux& a = p.aux1;
-          a.ptr[(((size_t)img * a.chunks + a.chunk) * a.plane + (size_t)(yy + a.border) * a.pitch + xx + a.border) * 8 + a.channel] = __float2bfloat16(a1);
+        const int npix = p.in_xp > 1 ? p.in_xp : 1;   // x-phase source: columns j * cp + {0, 1} = heads of pixel 4 xx + j
+#pragma unroll
+        for (int jx = 0; jx < 4; ++jx) {
+          if (jx >= npix) break;
+          const int x = p.in_xp > 1 ? xx * p.in_xp + jx : xx;
+          const float a0 = fminf(fmaxf(v[jx * 4] + s_bias[jx * 4], -1.f), 1.f);
+          const float a1 = 1.f / (1.f + __expf(-(v[jx * 4 + 1] + s_bias[jx * 4 + 1])));
+          const size_t pix = ((size_t)img * p.h_out + yy) * p.w_img + x;
+          p.head0[pix] = a0;
+          p.head1[pix] = a1;
+          if (p.aux0.ptr) aux_store(p.aux0, yy, x, a0);
+          if (p.aux1.ptr) aux_store(p.aux1, yy, x, a1);
         }
         continue;
       }
-      size_t pos;
-      if (p.out_mode == TC_OUT_CHUNKED) pos = (size_t)(yy + p.out_border) * p.out_pitch + xx + p.out_border;
-      else if (p.out_mode == TC_OUT_CHUNKED_S2D)  // consumer is a stride-2 conv: scatter by pixel parity
-        pos = (size_t)((yy & 1) * 2 + (xx & 1)) * p.out_sub_plane + (size_t)((yy >> 1) + p.out_border) * p.out_pitch + (xx >> 1) + p.out_border;
-      else pos = (size_t)(2 * yy + p.out_border) * p.out_pitch + 2 * xx + p.out_border;
-      __nv_bfloat16* out0 = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off) * p.out_plane * 8 + pos * 8;
       float v[NCOL];
       tmem_ld<NCOL>(t_addr + col0, v);
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_tempty + 8u * acc);  // this warp's slice is in registers: release its share of the TMEM stage
       if (!valid) continue;
+      __nv_bfloat16* out_img = p.out + ((size_t)img * p.out_chunks_total + p.out_chunk_off) * p.out_plane * 8;
 #pragma unroll
       for (int jj = 0; jj < NCOL / 8; ++jj) {
-        const int c = col0 / 8 + jj;
-        if (c >= p.out_nchunks) break;
+        const int col = col0 + jj * 8;
+        // plain source: column = channel.  x-phase source: column = phase * cp + channel of output pixel in_xp * xx + phase
+        const int ph = p.in_xp > 1 ? col / p.cp : 0;
+        const int c = (p.in_xp > 1 ? col - ph * p.cp : col) >> 3;
+        if (c >= p.out_nchunks) continue;
+        const int x = p.in_xp > 1 ? xx * p.in_xp + ph : xx;
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float f0 = act_fast<ACT>(v[jj * 8 + 2 * e] + s_bias[col0 + jj * 8 + 2 * e], p.act);
-          const float f1 = act_fast<ACT>(v[jj * 8 + 2 * e + 1] + s_bias[col0 + jj * 8 + 2 * e + 1], p.act);
+          const float f0 = act_fast<ACT>(v[jj * 8 + 2 * e] + s_bias[col + 2 * e], p.act);
+          const float f1 = act_fast<ACT>(v[jj * 8 + 2 * e + 1] + s_bias[col + 2 * e + 1], p.act);
           __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
           pk[e] = *reinterpret_cast<uint32_t*>(&h);
         }
         const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        __nv_bfloat16* plane = out0 + (size_t)c * p.out_plane * 8;
-        *reinterpret_cast<uint4*>(plane) = val;
+        __nv_bfloat16* plane = out_img + (size_t)c * p.out_plane * 8;
         if (p.out_mode == TC_OUT_CHUNKED_UP2) {  // nearest x2 upsample fused into the store (inpaint_networks.py:97,:105,:219,:222)
-          *reinterpret_cast<uint4*>(plane + 8) = val;
-          *reinterpret_cast<uint4*>(plane + (size_t)p.out_pitch * 8) = val;
-          *reinterpret_cast<uint4*>(plane + (size_t)(p.out_pitch + 1) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + out_pos(2 * yy, 2 * x) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + out_pos(2 * yy, 2 * x + 1) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + out_pos(2 * yy + 1, 2 * x) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + out_pos(2 * yy + 1, 2 * x + 1) * 8) = val;
+        } else {
+          *reinterpret_cast<uint4*>(plane + out_pos(yy, x) * 8) = val;
         }
       }
     }
@@ -393,12 +445,20 @@ static int make_map(CUtensorMap* map, const TcBuf& b, int box_chunks, int k, int
   CUresult r = CUDA_SUCCESS;
   const CUtensorMapDataType types[2] = {CU_TENSOR_MAP_DATA_TYPE_UINT64, CU_TENSOR_MAP_DATA_TYPE_FLOAT64};
   for (int attempt = 0; attempt < 2; ++attempt) {
-    if (!b.s2d) {
+    if (!b.s2d && b.xp == 1) {
       cuuint64_t dims[4] = {(cuuint64_t)b.sub_plane() * 2, (cuuint64_t)k, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
       cuuint64_t strides[3] = {(cuuint64_t)dil * b.pitch() * 16, plane_b, plane_b * b.image_chunks()};
       cuuint32_t box[4] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
       cuuint32_t es[4] = {1, 1, 1, 1};
       r = enc(map, types[attempt], 4, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (b.xp > 1) {
+      // x-phase source: {positions*2, k rows, xp phases, chunks, n}; one box = `box_rows` kernel rows of all phases
+      cuuint64_t dims[5] = {(cuuint64_t)b.sub_plane() * 2, (cuuint64_t)k, (cuuint64_t)b.xp, (cuuint64_t)b.chunks, (cuuint64_t)b.n};
+      cuuint64_t strides[4] = {(cuuint64_t)dil * b.pitch() * 16, sub_b, plane_b, plane_b * b.image_chunks()};
+      cuuint32_t box[5] = {2 * TC_TILE_M, (cuuint32_t)box_rows, (cuuint32_t)b.xp, (cuuint32_t)box_chunks, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      r = enc(map, types[attempt], 5, b.ptr, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
       // space-to-depth source: {positions*2, 2 rows (dy = -1, 0), 4 parity sub-planes, chunks, n}: one box = everything a tile needs
@@ -429,14 +489,23 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   c.k = k; c.stride = stride; c.dil = dil; c.nsrc = nsrc; c.cout_real = cout_real;
   for (int i = 0; i < nsrc; ++i) c.src[i] = srcs[i];
   HV_CHECK_ARG(cout_real >= 1 && cout_real <= 64, "tc_conv: cout must be in 1..64");
-  c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
   const TcBuf& b0 = srcs[0].buf;
+  const int xp = b0.xp;
+  int cp = 0;   // accumulator columns per output pixel of an x-phase layer
+  if (xp > 1) {
+    HV_CHECK_ARG(xp == 4 && nsrc == 1 && stride == 1 && k == 3 && dil == 1 && !srcs[0].kxpack && cout_real <= 16 && (b0.w % 4) == 0,
+                 "tc_conv: x-phase sources feed single-source 3x3 stride-1 convs with <= 16 filters");
+    cp = cout_real <= 4 ? 4 : (cout_real <= 8 ? 8 : 16);
+    c.n_pad = 4 * cp;
+  } else {
+    c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
+  }
   const int half = (k - 1) / 2;
   int max_chunks = 0, total_chunks = 0;
   for (int i = 0; i < nsrc; ++i) {
     const TcBuf& b = srcs[i].buf;
     HV_CHECK_ARG(b.ptr && (b.chunks % 2) == 0, "tc_conv: source %d needs an even number of channel chunks", i);
-    HV_CHECK_ARG(b.h == b0.h && b.w == b0.w && b.border == b0.border && b.n == b0.n && b.s2d == b0.s2d,
+    HV_CHECK_ARG(b.h == b0.h && b.w == b0.w && b.border == b0.border && b.n == b0.n && b.s2d == b0.s2d && b.xp == b0.xp,
                  "tc_conv: concat sources must share geometry");
     HV_CHECK_ARG(b.s2d == (stride == 2), "tc_conv: a stride-2 conv reads a space-to-depth buffer (and only it does)");
     HV_CHECK_ARG(b.border >= (stride == 2 ? 1 : half * dil), "tc_conv: source border %d smaller than the conv padding", b.border);
@@ -451,32 +520,46 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   const int pitch = b0.pitch();
   HV_CHECK_ARG((long long)b0.plane() < (1ll << 20), "tc_conv: plane too large for the fast row division");
   p.s2d_in = stride == 2;
+  p.in_xp = xp; p.cp = cp; p.map5d = (stride == 2 || xp > 1) ? 1 : 0;
+  p.w_img = b0.w;
   p.in_pitch = pitch; p.in_border = b0.border;
   p.pitch_magic = ((1ull << 40) + (unsigned long long)pitch - 1) / (unsigned long long)pitch;
   p.h_out = b0.sub_h(); p.w_out = b0.sub_w();
   p.q_first = b0.border * pitch + b0.border;
   p.w_bytes = 0;
-  for (int i = 0; i < nsrc; ++i) p.w_bytes += (uint32_t)((srcs[i].kxpack ? k : k * k) * srcs[i].buf.chunks * c.n_pad * 16);
+  for (int i = 0; i < nsrc; ++i) p.w_bytes += (uint32_t)((xp > 1 ? k * (xp + 2) : (srcs[i].kxpack ? k : k * k)) * srcs[i].buf.chunks * c.n_pad * 16);
   size_t budget = 227 * 1024 - 2048;
   const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
   c.ctas_per_sm = 1;
   {  // two co-resident CTAs when the layer is thin and three tile slots still fit in half the shared memory (measured: with
      // only two slots per CTA the merged fine conv1|pmconv1 layer got 30 % slower)
-    const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k);
+    const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k * xp);
     if (tc_ctas_per_sm(c.n_pad) == 2 && fixed + 3 * band <= half) { c.ctas_per_sm = 2; budget = half; }
   }
   // all k kernel rows of a source in one TMA load when at least 3 such slots fit beside the weights
   const size_t band_bytes = (size_t)TC_TILE_M * max_chunks * 16u;
-  const bool multirow = stride == 1 && fixed + 3 * (size_t)k * band_bytes <= budget;
+  const bool multirow = stride == 1 && fixed + 3 * (size_t)k * xp * band_bytes <= budget;
   const int box_rows = multirow ? k : 1;
-  p.slot_bytes = (uint32_t)(band_bytes * (stride == 2 ? 8 : box_rows));
+  p.slot_bytes = (uint32_t)(band_bytes * (stride == 2 ? 8 : box_rows * xp));
   HV_CHECK_ARG(fixed + 2 * (size_t)p.slot_bytes <= budget, "tc_conv: weights (%u B) + 2 band slots do not fit in shared memory", p.w_bytes);
   int seg = 0, max_shift = 0;
   uint32_t woff16 = 0;
   for (int s = 0; s < nsrc; ++s) {
     const int nch = srcs[s].buf.chunks;
     const uint32_t slab = (uint32_t)nch * c.n_pad;  // one tap's weights, 16 B units
-    if (stride == 1) {
+    if (xp > 1) {
+      // x-phase source: image [chunk][4 phases][rows][128]; the six views of a row are enumerated by issue_xp4
+      max_shift = 2;
+      for (int ky = 0; ky < (multirow ? 1 : k); ++ky) {
+        HV_CHECK_ARG(seg < TC_MAX_SEGS, "tc_conv: too many segments");
+        TcSeg& sg = p.segs[seg++];
+        sg.map = s; sg.nchunks = nch; sg.nrows = box_rows; sg.ntaps = xp + 2;
+        sg.c1 = ky;
+        sg.rel_start2 = 2 * (-pitch - 1);
+        sg.a0 = 0; sg.a_step = 0;
+        sg.b0 = woff16 + (uint32_t)(ky * (xp + 2)) * slab; sg.b_step = slab; sg.b_row_step = (uint32_t)(xp + 2) * slab;
+      }
+    } else if (stride == 1) {
       const bool kxp = srcs[s].kxpack;
       if (!kxp) max_shift = max(max_shift, (k - 1) * dil);
       for (int ky = 0; ky < (multirow ? 1 : k); ++ky) {
@@ -498,10 +581,10 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
       sg.rel_start2 = 2 * (-pitch - 1);
       sg.a0 = 0; sg.a_step = 0; sg.b0 = woff16; sg.b_step = slab; sg.b_row_step = 0;
     }
-    woff16 += (uint32_t)(srcs[s].kxpack ? k : k * k) * slab;
+    woff16 += (uint32_t)(xp > 1 ? k * (xp + 2) : (srcs[s].kxpack ? k : k * k)) * slab;
   }
   p.nseg = seg;
-  for (int i = 0; i < seg; ++i) p.segs[i].tx_bytes = (uint32_t)TC_TILE_M * p.segs[i].nchunks * 16u * p.segs[i].nrows;
+  for (int i = 0; i < seg; ++i) p.segs[i].tx_bytes = (uint32_t)TC_TILE_M * p.segs[i].nchunks * 16u * p.segs[i].nrows * (xp > 1 ? xp : 1);
   p.tile_adv = TC_TILE_M - max_shift;
   const int span = p.h_out * pitch;  // positions from output (0,0) to the end of the last row (incl. side borders)
   p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
@@ -530,6 +613,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
 void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act) {
   TcParams& p = c.p;
   p.out_mode = up2 ? TC_OUT_CHUNKED_UP2 : (out.s2d ? TC_OUT_CHUNKED_S2D : TC_OUT_CHUNKED);
+  p.out_xp = out.xp;
   p.out = out.ptr; p.out_pitch = out.pitch(); p.out_border = out.border; p.out_plane = out.plane();
   p.out_sub_plane = out.sub_plane();
   p.out_chunks_total = out.image_chunks(); p.out_chunk_off = chunk_off; p.out_nchunks = nchunks;
@@ -539,6 +623,7 @@ void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int 
 void tc_conv_set_output_heads(TcConv& c, float* head0, float* head1, const TcAux* aux0, const TcAux* aux1) {
   TcParams& p = c.p;
   p.out_mode = TC_OUT_HEADS;
+  p.out_xp = c.src[0].buf.xp;   // the aux channels go into buffers of the source's layout
   p.head0 = head0; p.head1 = head1;
   memset(&p.aux0, 0, sizeof(TcAux)); memset(&p.aux1, 0, sizeof(TcAux));
   if (aux0) p.aux0 = *aux0;
@@ -553,16 +638,17 @@ void tc_conv_free(TcConv& c) {
 // ------------------------------------------------------------------------------------------- weight packing
 // dst[(tap entry e = (source, ky, kx))][chunk][n_pad][8] bf16; padded channels / filters are zero.
 // kx-packed sources have one entry per kernel row: channel ch of the entry = (kx = ch / real, c = ch % real).
-struct PackSrc { int ch_off, real, chunks, kxpack; };
+struct PackSrc { int ch_off, real, chunks, kxpack, xp, cp; };
 __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* __restrict__ ba, int cout_a,
                                     const float* __restrict__ wb, const float* __restrict__ bb, int cout_b, int cin_total,
                                     int k, int n_pad, PackSrc s0, PackSrc s1, int nsrc, __nv_bfloat16* __restrict__ dst,
                                     float* __restrict__ bias_pad, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) {
+    const int co = s0.xp > 1 ? i % s0.cp : i;
     float b = 0.f;
-    if (i < cout_a) b = ba ? ba[i] : 0.f;
-    else if (i < cout_a + cout_b) b = bb ? bb[i - cout_a] : 0.f;
+    if (co < cout_a) b = ba ? ba[co] : 0.f;
+    else if (co < cout_a + cout_b) b = bb ? bb[co - cout_a] : 0.f;
     bias_pad[i] = b;
   }
   if (i >= total) return;
@@ -571,19 +657,26 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
   const int c8 = rem & 7; rem >>= 3;
   const int n = rem % n_pad; rem /= n_pad;
   // rem = linear (entry, chunk) index with per-source entry / chunk counts
-  const int per0 = (s0.kxpack ? k : kk) * s0.chunks;
+  const int per0 = (s0.xp > 1 ? k * (s0.xp + 2) : (s0.kxpack ? k : kk)) * s0.chunks;
   PackSrc s = s0;
   if (rem >= per0) { rem -= per0; s = s1; }
   const int chunk = rem % s.chunks, entry = rem / s.chunks;
   const int ch = chunk * 8 + c8;
-  int c = ch, tap = entry;
+  int c = ch, tap = entry, co = n;
   bool real = ch < s.real;
   if (s.kxpack) { const int kx = ch / s.real; c = ch - kx * s.real; tap = entry * k + kx; real = kx < k; }
+  if (s.xp > 1) {   // entry = ky * (xp + 2) + view; column n = phase * cp + filter; view v carries tap kx = v - phase
+    const int ky = entry / (s.xp + 2), view = entry - ky * (s.xp + 2), ph = n / s.cp;
+    co = n - ph * s.cp;
+    const int kx = view - ph;
+    tap = ky * k + kx;
+    real = real && kx >= 0 && kx < k;
+  }
   float v = 0.f;
   if (real) {
     const int cin = s.ch_off + c;
-    if (n < cout_a) v = wa[((size_t)n * cin_total + cin) * kk + tap];
-    else if (n < cout_a + cout_b) v = wb[((size_t)(n - cout_a) * cin_total + cin) * kk + tap];
+    if (co < cout_a) v = wa[((size_t)co * cin_total + cin) * kk + tap];
+    else if (co < cout_a + cout_b) v = wb[((size_t)(co - cout_a) * cin_total + cin) * kk + tap];
   }
   dst[i] = __float2bfloat16(v);
 }
@@ -591,10 +684,10 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
 int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a, const float* wb, const float* bb,
                          int cout_b, cudaStream_t st) {
   HV_CHECK_ARG(cout_a + cout_b == c.cout_real, "tc_conv_pack_weights: filter count mismatch");
-  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks, c.src[0].kxpack ? 1 : 0}, s1{0, 0, 1, 0};
+  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks, c.src[0].kxpack ? 1 : 0, c.p.in_xp, c.p.cp}, s1{0, 0, 1, 0, 1, 0};
   int cin_total = c.src[0].real_channels;
   if (c.nsrc == 2) {
-    s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks, c.src[1].kxpack ? 1 : 0};
+    s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks, c.src[1].kxpack ? 1 : 0, 1, 0};
     cin_total += c.src[1].real_channels;
   }
   const int total = (int)(c.p.w_bytes / 2);

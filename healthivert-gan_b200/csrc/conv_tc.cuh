@@ -23,6 +23,10 @@ struct TcBuf {
   __nv_bfloat16* ptr = nullptr;
   int n = 0, chunks = 0, h = 0, w = 0, border = 0;
   bool s2d = false;
+  // xp ("x phases", 1 or 4): the buffer feeds a THIN conv (<= 16 output channels); it is stored as xp sub-planes selected by
+  // x % xp, each a zero-bordered h x (w/xp) image.  The consumer then computes xp horizontally adjacent output pixels per
+  // accumulator row (N = xp * Cout columns), i.e. 4x fewer, 4x wider MMAs than one pixel per row.
+  int xp = 1;
   int img_chunks = 0;  // chunks per image in memory when this is a view of a chunk range of a wider buffer (0: == chunks)
   __host__ __device__ int image_chunks() const { return img_chunks ? img_chunks : chunks; }
   // element offset of chunk plane c of image i
@@ -36,12 +40,13 @@ struct TcBuf {
     return v;
   }
   __host__ __device__ int sub_h() const { return s2d ? h / 2 : h; }
-  __host__ __device__ int sub_w() const { return s2d ? w / 2 : w; }
+  __host__ __device__ int sub_w() const { return s2d ? w / 2 : w / xp; }
   __host__ __device__ int pitch() const { return sub_w() + 2 * border; }
   __host__ __device__ int rows() const { return sub_h() + 2 * border; }
   __host__ __device__ int sub_plane() const { return (pitch() * rows() + 7) & ~7; }
-  __host__ __device__ int plane() const { return s2d ? 4 * sub_plane() : sub_plane(); }
+  __host__ __device__ int plane() const { return s2d ? 4 * sub_plane() : xp * sub_plane(); }
   __host__ __device__ size_t pos(int y, int x) const {
+    if (xp > 1) return (size_t)(x % xp) * sub_plane() + (size_t)(y + border) * pitch() + x / xp + border;
     if (!s2d) return (size_t)(y + border) * pitch() + x + border;
     return (size_t)((y & 1) * 2 + (x & 1)) * sub_plane() + (size_t)((y >> 1) + border) * pitch() + (x >> 1) + border;
   }
@@ -74,7 +79,7 @@ enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2, T
 
 struct TcAux {  // optional bf16 side output of a head: one channel of a chunked buffer
   __nv_bfloat16* ptr;
-  int chunks, chunk, channel, pitch, border, plane;
+  int chunks, chunk, channel, pitch, border, plane, sub_plane;
 };
 
 struct TcParams {
@@ -85,11 +90,16 @@ struct TcParams {
   uint32_t w_bytes;
   const float* bias;  // [n_pad]
   int s2d_in;     // sources are space-to-depth buffers (stride-2 conv)
+  int in_xp;      // sources are x-phase buffers: every accumulator row holds in_xp adjacent output pixels (N = in_xp * cp)
+  int cp;         // accumulator columns per output pixel when in_xp > 1
+  int out_xp;     // the output buffer is an x-phase buffer (aux outputs of the heads too)
+  int map5d;      // tensor maps are 5-D (s2d / x-phase sources)
   int tile_adv;   // valid output positions per 128-row MMA tile (128 - widest tap shift)
   int tiles_per_image, total_tiles;
   int in_pitch, in_border, q_first;
   unsigned long long pitch_magic;  // ceil(2^40 / in_pitch): q / in_pitch == (q * magic) >> 40 for q < 2^20
-  int h_out, w_out;
+  int h_out, w_out;   // extent of the accumulator-row grid (w_out = image width / in_xp)
+  int w_img;          // image width in pixels
   int act;
   int out_mode;
   __nv_bfloat16* out;

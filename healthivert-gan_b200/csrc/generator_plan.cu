@@ -272,7 +272,7 @@ struct TcPlan {
 static TcAux make_aux(const TcBuf& b, int channel) {
   TcAux a;
   a.ptr = b.ptr; a.chunks = b.chunks; a.chunk = channel >> 3; a.channel = channel & 7;
-  a.pitch = b.pitch(); a.border = b.border; a.plane = b.plane();
+  a.pitch = b.pitch(); a.border = b.border; a.plane = b.plane(); a.sub_plane = b.sub_plane();
   return a;
 }
 
@@ -289,11 +289,14 @@ static int tc_plan_create(hv_generator* g) {
   g->tc = t;
   const int n = g->max_batch;
   size_t total = 0;
+  const bool no_xp = getenv("HV_NO_XP") != nullptr;   // A/B switch: plain layout for the thin 256x256 tail
   for (int i = 0; i < B_COUNT; ++i) {
     TcBuf& b = t->buf[i];
     b.n = n; b.chunks = kBufs[i].channels / 8; b.h = b.w = kBufs[i].extent; b.border = kBufs[i].border;
     // buffers consumed by a stride-2 conv are stored space-to-depth
     b.s2d = (i == B_C1 || i == B_C3 || i == B_F1 || i == B_F3 || i == B_P1 || i == B_P3);
+    // inputs of the thin 256x256 tail layers (<= 16 filters: conv15/16/17+18, allconv15/16/17+18) are stored in 4 x-phases
+    b.xp = (!no_xp && (i == B_C19 || i == B_C15 || i == B_C16 || i == B_A14U || i == B_A15 || i == B_A16CAT)) ? 4 : 1;
     total += (b.bytes() + 255) & ~(size_t)255;
   }
   total += TcBuf::kSlackBytes;
