@@ -164,6 +164,12 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 1 + 2 * ACC_STAGES);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA entry: wall clock (ns) and SM clock
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[12000 + 4 * blockIdx.x] = (long long)gt;
+    p.trace[12000 + 4 * blockIdx.x + 2] = clock64();
+  }
   if (warp == W_PRODUCER && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[1]) : "memory");
@@ -206,18 +212,27 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     const uint32_t slot_bytes = p.slot_bytes;
     int rel2 = p.segs[0].rel_start2, c1 = p.segs[0].c1;   // single-segment layers keep the load recipe in registers
     uint32_t tx = p.segs[0].tx_bytes;
+    int cpl = p.segs[0].cpl, nload = p.segs[0].nchunks / cpl;
+    uint32_t load_bytes = tx / (uint32_t)nload;
     bool map1 = false;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int img = tile / p.tiles_per_image;
       const int c_tile = 2 * ((tile - img * p.tiles_per_image) * p.tile_adv + p.q_first);  // tensor-map inner unit = 8 B
       for (int s = 0; s < nseg; ++s) {
-        if (nseg > 1) { rel2 = p.segs[s].rel_start2; c1 = p.segs[s].c1; tx = p.segs[s].tx_bytes; map1 = p.segs[s].map != 0; }
+        if (nseg > 1) {
+          rel2 = p.segs[s].rel_start2; c1 = p.segs[s].c1; tx = p.segs[s].tx_bytes; map1 = p.segs[s].map != 0;
+          cpl = p.segs[s].cpl; nload = p.segs[s].nchunks / cpl; load_bytes = tx / (uint32_t)nload;
+        }
+        if (leader) trace_ev(p.trace, ntr, 2);
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+        if (leader) trace_ev(p.trace, ntr, 3);
         if (leader) {
           const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_bytes;
-          mbar_expect_tx(fb, tx);
-          if (map5d) tma_load_5d(dst, &p.maps[0], fb, c_tile + rel2, c1, 0, 0, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
-          else tma_load_4d(dst, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, 0, img);
+          mbar_expect_tx(fb, (p.debug & 2) ? 0u : tx);
+          for (int i = 0; i < ((p.debug & 2) ? 0 : nload); ++i) {
+            if (map5d) tma_load_5d(dst + (uint32_t)i * load_bytes, &p.maps[0], fb, c_tile + rel2, c1, 0, i * cpl, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
+            else tma_load_4d(dst + (uint32_t)i * load_bytes, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, i * cpl, img);
+          }
           trace_ev(p.trace, ntr, 1);
         }
         if (++slot == nslots) { slot = 0; phase ^= 1u; }
@@ -226,6 +241,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   } else if (warp == W_MMA) {
     // ===================================================================== MMA issuer (warp-uniform, one lane issues)
     const bool leader = elect_one();
+    const bool mma_on = leader && !(p.debug & 1);
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_PAD >> 3) << 17) | ((128u >> 4) << 24);
     // smem descriptor = hi word (SBO = 128 B, version 1) : lo word (start >> 4 | LBO >> 4 << 16); offsets add into lo.
@@ -264,14 +280,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         const uint32_t cur_slot = (uint32_t)slot, cur_empty = bar_empty + 8u * slot;
         if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
         ready_full = mbar_peek(bar_full + 8u * slot, phase);
+        if (leader) trace_ev(tr, ntr, 14);
         const uint32_t a_row = a_lo_base + cur_slot * slot_units + (a_lbo << 16) + sg.a0;
         const uint32_t b_row = b_lo_base + sg.b0;
         if (s == nseg - 1) ready_acc = mbar_peek(bar_tempty + 8u * acc, acc_phase ^ 1u);
         if (s2d) {
           const uint32_t a_s2d = a_lo_base + cur_slot * slot_units + ((8u * TC_TILE_M) << 16);
-          if (ksteps == 1) issue_s2d<N_PAD, 1>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
-          else if (ksteps == 2) issue_s2d<N_PAD, 2>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
-          else issue_s2d<N_PAD, 4>(leader, d_tmem, a_s2d, b_row, b_step, idesc);
+          if (ksteps == 1) issue_s2d<N_PAD, 1>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
+          else if (ksteps == 2) issue_s2d<N_PAD, 2>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
+          else issue_s2d<N_PAD, 4>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
           accumulate = 1;
           if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
           continue;
@@ -280,10 +297,10 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
           const uint32_t a_xp = a_lo_base + cur_slot * slot_units + ((4u * (uint32_t)nrows * TC_TILE_M) << 16);
           const int shape_xp = (nrows << 4) | ksteps;
           switch (shape_xp) {
-            case (3 << 4) | 1: issue_xp4<N_PAD, 3, 1>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
-            case (3 << 4) | 2: issue_xp4<N_PAD, 3, 2>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
-            case (1 << 4) | 1: issue_xp4<N_PAD, 1, 1>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
-            default: issue_xp4<N_PAD, 1, 2>(leader, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            case (3 << 4) | 1: issue_xp4<N_PAD, 3, 1>(mma_on, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            case (3 << 4) | 2: issue_xp4<N_PAD, 3, 2>(mma_on, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            case (1 << 4) | 1: issue_xp4<N_PAD, 1, 1>(mma_on, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
+            default: issue_xp4<N_PAD, 1, 2>(mma_on, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
           }
           accumulate = 1;
           if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
@@ -292,17 +309,18 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         const int shape = (nrows << 8) | (ntaps << 4) | ksteps;
 #define HV_SEG(R, T, K)                                                                                                   \
   case ((R) << 8) | ((T) << 4) | (K):                                                                                     \
-    issue_segment<N_PAD, R, T, K>(leader, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);           \
+    issue_segment<N_PAD, R, T, K>(mma_on, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);           \
     break;
         switch (shape) {
           HV_SEG(3, 3, 1) HV_SEG(3, 3, 2) HV_SEG(3, 3, 4) HV_SEG(5, 5, 1) HV_SEG(5, 5, 2)
           HV_SEG(1, 3, 1) HV_SEG(1, 3, 2) HV_SEG(1, 3, 4) HV_SEG(1, 2, 1) HV_SEG(1, 2, 2) HV_SEG(1, 1, 1) HV_SEG(1, 1, 2)
           HV_SEG(5, 1, 1) HV_SEG(5, 1, 2) HV_SEG(1, 5, 1) HV_SEG(3, 1, 1) HV_SEG(1, 1, 4)
           default:
-            issue_segment_generic<N_PAD>(leader, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate, nrows, ntaps, ksteps);
+            issue_segment_generic<N_PAD>(mma_on, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate, nrows, ntaps, ksteps);
         }
 #undef HV_SEG
         accumulate = 1;
+        if (leader) trace_ev(tr, ntr, 15);
         if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }  // slot is free once these MMAs have read it
       }
       if (leader) umma_commit(cur_tfull);  // accumulator tile complete -> epilogue
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
       const int yy = qrow - p.in_border;
       const int xx = q - qrow * p.in_pitch - p.in_border;
       // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
-      const bool valid = m < p.tile_adv && yy >= 0 && yy < p.h_out && xx >= 0 && xx < p.w_out;
+      const bool valid = m < p.tile_adv && yy >= 0 && yy < p.h_out && xx >= 0 && xx < p.w_out && !(p.debug & 4);
       trace_ev(tr, ntr, 20);
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
@@ -409,6 +427,12 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   }
   tc_fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA exit
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    p.trace[12000 + 4 * blockIdx.x + 1] = (long long)gt;
+    p.trace[12000 + 4 * blockIdx.x + 3] = clock64();
+  }
   if (warp == W_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -520,6 +544,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   const int pitch = b0.pitch();
   HV_CHECK_ARG((long long)b0.plane() < (1ll << 20), "tc_conv: plane too large for the fast row division");
   p.s2d_in = stride == 2;
+  if (const char* e = getenv("HV_TC_DEBUG")) p.debug = atoi(e);
   p.in_xp = xp; p.cp = cp; p.map5d = (stride == 2 || xp > 1) ? 1 : 0;
   p.w_img = b0.w;
   p.in_pitch = pitch; p.in_border = b0.border;
@@ -585,6 +610,16 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   }
   p.nseg = seg;
   for (int i = 0; i < seg; ++i) p.segs[i].tx_bytes = (uint32_t)TC_TILE_M * p.segs[i].nchunks * 16u * p.segs[i].nrows * (xp > 1 ? xp : 1);
+  // chunks per TMA operation: 0 = the whole band in one operation.  Measured (HV_TMA_CPL = 1 / 2 / 4): splitting a band into
+  // concurrent operations changes nothing, the ingest rate is set by shared-memory bandwidth shared with the MMA operand reads
+  int cpl_req = 0;
+  if (const char* e = getenv("HV_TMA_CPL")) cpl_req = atoi(e);
+  for (int i = 0; i < seg; ++i) {
+    const int nch = p.segs[i].nchunks;
+    int cpl = (cpl_req <= 0 || cpl_req > nch) ? nch : cpl_req;
+    while (nch % cpl) --cpl;
+    p.segs[i].cpl = cpl;
+  }
   p.tile_adv = TC_TILE_M - max_shift;
   const int span = p.h_out * pitch;  // positions from output (0,0) to the end of the last row (incl. side borders)
   p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
@@ -595,7 +630,9 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.nslots = nslots;
   c.smem = fixed + (size_t)nslots * p.slot_bytes;
   for (int s = 0; s < nsrc; ++s) {
-    int rc = make_map(&p.maps[s], srcs[s].buf, srcs[s].buf.chunks, k, dil, box_rows);
+    int cpl = srcs[s].buf.chunks;
+    for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) cpl = p.segs[i].cpl;
+    int rc = make_map(&p.maps[s], srcs[s].buf, cpl, k, dil, box_rows);
     if (rc) return rc;
   }
   if (nsrc == 1) p.maps[1] = p.maps[0];

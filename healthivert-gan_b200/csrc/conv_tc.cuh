@@ -73,6 +73,8 @@ struct TcSeg {
   int ntaps;          // taps per row
   uint32_t a0, a_step, b0, b_step, b_row_step;
   uint32_t tx_bytes;  // bytes this load brings
+  int cpl;            // channel chunks per TMA operation: the band is brought by nchunks / cpl concurrent operations on one
+                      // barrier (a single TMA operation streams at only ~12 B/clk, see profiles/r1_probe_mma_tma.log)
 };
 
 enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2, TC_OUT_CHUNKED_S2D = 3 };
@@ -110,6 +112,7 @@ struct TcParams {
   uint32_t slot_bytes;
   int nslots;
   long long* trace;  // debug event trace (device buffer of 12000 int64) or null
+  int debug;         // ablation bits for bottleneck hunting (env HV_TC_DEBUG): 1 no MMAs, 2 no TMA loads, 4 no output stores
 };
 
 struct TcSource {
@@ -162,6 +165,6 @@ int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, floa
 // contextual attention on tensor cores (ctx_attn_tc.cu): f and y are 64-channel 64x64 chunked buffers
 size_t ctx_attn_tc_workspace_bytes(int n);
 int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
-                    int per_sample_mask, void* workspace, cudaStream_t st);
+                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_flow = nullptr, cudaEvent_t ev_argmax = nullptr);
 
 }  // namespace hv

@@ -204,8 +204,10 @@ static size_t ca_tc_layout(int n, char* base, CaTcWorkspace* ws) {
 size_t ctx_attn_tc_workspace_bytes(int n) { return ca_tc_layout(n, nullptr, nullptr); }
 
 // f: chunked bf16 [n][8 chunks][64x64, any border]; y: chunked bf16 output buffer of the same extent
+// st_flow / ev_argmax (optional): the offsets / flow outputs, which nothing downstream consumes, are produced on st_flow after
+// the arg-max is known instead of extending st's critical path
 int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
-                    int per_sample_mask, void* workspace, cudaStream_t st) {
+                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_flow, cudaEvent_t ev_argmax) {
   HV_CHECK_ARG(f.ptr && y.ptr && mask && workspace, "ctx_attn_fwd_tc: null argument");
   HV_CHECK_ARG(f.chunks == 8 && f.h == CA_H && f.w == CA_H && !f.s2d && y.chunks == 8 && y.h == CA_H && y.w == CA_H && !y.s2d && y.n == f.n,
                "ctx_attn_fwd_tc: built for 64-channel 64x64 feature maps");
@@ -222,11 +224,17 @@ int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* 
   if (rc) return rc;
   ca_tc_fuse_softmax_kernel<<<dim3(CA_L / 8, n), 256, 0, st>>>(ws.T, ws.mm, CA_L, ws.A, ws.argmax, scale, fuse);
   HV_LAUNCH_CHECK();
+  if ((offsets || flow) && st_flow && ev_argmax) {
+    HV_CUDA(cudaEventRecord(ev_argmax, st));
+    HV_CUDA(cudaStreamWaitEvent(st_flow, ev_argmax, 0));
+    rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, st_flow);
+    if (rc) return rc;
+  }
   rc = gemm_tc_nt(ws.Rt, ws.A, ws.cols, nullptr, CA_KR, CA_L, CA_L, n, (long long)CA_KR * CA_L, (long long)CA_L * CA_L, 1, st);
   if (rc) return rc;
   ca_tc_fold_kernel<<<(n * 32768 + 255) / 256, 256, 0, st>>>(ws.cols, y);
   HV_LAUNCH_CHECK();
-  if (offsets || flow) {
+  if ((offsets || flow) && !(st_flow && ev_argmax)) {
     rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, st);
     if (rc) return rc;
   }

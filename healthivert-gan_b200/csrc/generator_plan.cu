@@ -108,6 +108,10 @@ struct hv_generator {
   const float* last_heads[4] = {};  // x_stage1, coarse_seg, x_stage2, fine_seg of the last forward
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // bf16 plan: light kernels whose results are needed late (CAM packing, height heads, attention flow) run on `aux`,
+  // co-resident with the one-CTA-per-SM conv kernels of the main stream
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   struct hv::TcPlan* tc = nullptr;  // bf16 tensor-core plan (precision == HV_PREC_BF16)
 };
 
@@ -374,18 +378,37 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     tc_set_batch(c, n);
     return tc_conv_launch(c, s);
   };
+  const bool use_aux = getenv("HV_NO_AUX_STREAM") == nullptr;
+  cudaStream_t ax = use_aux ? g->aux : st;
+  auto fork_aux = [&](int ev) -> int {   // aux continues after everything enqueued on st so far
+    if (!use_aux) return HV_OK;
+    HV_CUDA(cudaEventRecord(g->ev_aux[ev], st));
+    HV_CUDA(cudaStreamWaitEvent(ax, g->ev_aux[ev], 0));
+    return HV_OK;
+  };
+  auto join_aux = [&](int ev) -> int {   // st continues after everything enqueued on aux so far
+    if (!use_aux) return HV_OK;
+    HV_CUDA(cudaEventRecord(g->ev_aux[ev], ax));
+    HV_CUDA(cudaStreamWaitEvent(st, g->ev_aux[ev], 0));
+    return HV_OK;
+  };
   // ---- pack the fp32 NCHW inputs into kx-packed chunked bf16 buffers (torch.cat of :77 / :179, F.interpolate of :98)
   {
+    RC(fork_aux(0));
     const TcPlaneSrc in_c[3] = {{x, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}, {mask, HV_SRC_DIRECT}};
     RC(tc_pack_kx(in_c, 3, 5, 1, view(B_IN_C), st));
     const TcPlaneSrc cam128[1] = {{cam, HV_SRC_SUB2}}, cam256[1] = {{cam, HV_SRC_DIRECT}};
-    RC(tc_pack_kx(cam128, 1, 3, 1, view(B_CAM128), st));
-    RC(tc_pack_kx(cam256, 1, 3, 1, view(B_CAM256), st));
+    RC(tc_pack_kx(cam128, 1, 3, 1, view(B_CAM128), ax));   // first needed by conv20 / conv19
+    RC(tc_pack_kx(cam256, 1, 3, 1, view(B_CAM256), ax));
+    if (use_aux) HV_CUDA(cudaEventRecord(g->ev_aux[1], ax));
   }
   // ---- coarse network
   for (int l : {C1, C2, C3, C4, C5, C6, C7, C8, C9, C10}) RC(run(l, st));
-  RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, t->gap_partial, t->gap_ticket, st));
-  for (int l : {C11, C12, C20, C13, C14, C19, C15, C16}) RC(run(l, st));
+  RC(fork_aux(2));
+  RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, t->gap_partial, t->gap_ticket, ax));
+  for (int l : {C11, C12}) RC(run(l, st));
+  if (use_aux) HV_CUDA(cudaStreamWaitEvent(st, g->ev_aux[1], 0));
+  for (int l : {C20, C13, C14, C19, C15, C16}) RC(run(l, st));
   t->conv[C17].p.head0 = x_stage1; t->conv[C17].p.head1 = coarse_seg;
   RC(run(C17, st));
   // ---- fine network: xnow = [xin, coarse_seg, mask, ratio]; conv1 | pmconv1 as one 32-filter conv, then the
@@ -399,17 +422,20 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
   HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
   cudaStream_t sa = g->side;
   for (int l : {PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
-  RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa));
+  RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa, use_aux ? ax : nullptr,
+                     g->ev_aux[3]));
   RC(run(PM9, sa));
   RC(run(PM10, sa));
   HV_CUDA(cudaEventRecord(g->ev_join, sa));
   for (int l : {F2, F3, F4, F5, F6, F7, F8, F9, F10}) RC(run(l, st));
   HV_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
   RC(run(A11, st));
-  RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, t->gap_partial + g->max_batch * 8, t->gap_ticket + g->max_batch, st));
+  RC(fork_aux(4));
+  RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, t->gap_partial + g->max_batch * 8, t->gap_ticket + g->max_batch, ax));
   for (int l : {A12, A19, A13, A14, A15, A16}) RC(run(l, st));
   t->conv[A17].p.head0 = x_stage2; t->conv[A17].p.head1 = fine_seg;
   RC(run(A17, st));
+  RC(join_aux(5));
   g->last_heads[0] = x_stage1; g->last_heads[1] = coarse_seg; g->last_heads[2] = x_stage2; g->last_heads[3] = fine_seg;
   g->last_n = n;
   return HV_OK;
@@ -446,6 +472,8 @@ int hv_generator_destroy(hv_generator* g) {
   if (g->side) cudaStreamDestroy(g->side);
   if (g->ev_fork) cudaEventDestroy(g->ev_fork);
   if (g->ev_join) cudaEventDestroy(g->ev_join);
+  if (g->aux) cudaStreamDestroy(g->aux);
+  for (cudaEvent_t e : g->ev_aux) if (e) cudaEventDestroy(e);
   delete g;
   return HV_OK;
 }
@@ -480,6 +508,8 @@ int hv_generator_create(hv_generator** out, int max_batch, int precision) {
   GEN_TRY(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
   GEN_TRY(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
+  GEN_TRY(cudaStreamCreateWithFlags(&g->aux, cudaStreamNonBlocking));
+  for (cudaEvent_t& e : g->ev_aux) GEN_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 #undef GEN_TRY
   if (precision == HV_PREC_BF16) {
     int rc = tc_plan_create(g);

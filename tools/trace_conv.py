@@ -27,10 +27,15 @@ def main():
     for _ in range(2):
         g.run_layer(layer, n)
     torch.cuda.synchronize()
-    buf = torch.zeros(12000 + 2 * 400, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(12000 + 4 * 400, dtype=torch.int64, device="cuda")
     L.hv_debug_conv_trace(buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g.run_layer(layer, n)            # predecessor (same layer) so that the traced launch is a dependent launch
+    e0.record()
     g.run_layer(layer, n)
+    e1.record()
     torch.cuda.synchronize()
+    print(f"kernel (event to event, after a predecessor) {e0.elapsed_time(e1) * 1e3:.1f} us")
     L.hv_debug_conv_trace(None)
     b = buf.cpu().tolist()
     ev = []
@@ -43,11 +48,14 @@ def main():
     ev.sort()
     t0 = ev[0][0]
     names = {1: "tma issued", 10: "weights ready wait start", 11: "acc stage free", 12: "band full", 13: "band MMAs issued+commit",
-             20: "epi tile start", 21: "acc full"}
+             20: "epi tile start", 21: "acc full",
+             2: "producer at slot wait", 3: "slot free", 14: "peeked next", 15: "MMAs issued"}
     print(f"layer {layer} batch {n}: {len(ev)} events, span {ev[-1][0] - t0} cycles")
     for clk, who, tag in ev[:140]:
         print(f"{clk - t0:8d} {who} {names.get(tag, tag)}")
-    ctas = [(b[12000 + 2 * i], b[12000 + 2 * i + 1]) for i in range(400) if b[12000 + 2 * i]]
+    ctas = [(b[12000 + 4 * i], b[12000 + 4 * i + 1]) for i in range(400) if b[12000 + 4 * i]]
+    if b[12000]:
+        print(f"CTA 0: entry -> first event {t0 - b[12002]} cycles, last event -> exit {b[12003] - ev[-1][0]} cycles, entry -> exit {b[12003] - b[12002]} cycles")
     if ctas:
         g0 = min(c[0] for c in ctas)
         starts = sorted(c[0] - g0 for c in ctas)
