@@ -170,6 +170,11 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     p.trace[12000 + 4 * blockIdx.x] = (long long)gt;
     p.trace[12000 + 4 * blockIdx.x + 2] = clock64();
   }
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMin(reinterpret_cast<unsigned long long*>(p.timeline), gt);
+  }
   if (warp == W_PRODUCER && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[0]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&p.maps[1]) : "memory");
@@ -432,6 +437,11 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.trace[12000 + 4 * blockIdx.x + 1] = (long long)gt;
     p.trace[12000 + 4 * blockIdx.x + 3] = clock64();
+  }
+  if (p.timeline && threadIdx.x == 0) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    atomicMax(reinterpret_cast<unsigned long long*>(p.timeline) + 1, gt);
   }
   if (warp == W_MMA) {
     tc_fence_after();
@@ -737,6 +747,9 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
 static long long* g_trace = nullptr;
 static bool g_pdl = getenv("HV_NO_PDL") == nullptr;
 void tc_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+static long long* g_timeline = nullptr;
+static int g_timeline_count = 0;
+void tc_set_timeline(long long* dev_buf) { g_timeline = dev_buf; g_timeline_count = 0; }
 
 template <int N_PAD, int ACT>
 static int tc_launch_na(const TcConv& c, cudaStream_t st) {
@@ -759,6 +772,7 @@ static int tc_launch_na(const TcConv& c, cudaStream_t st) {
   cfg.numAttrs = g_pdl ? 1 : 0;
   TcParams q = c.p;
   q.trace = g_trace;
+  q.timeline = g_timeline ? g_timeline + 4 * (g_timeline_count++) : nullptr;
   HV_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<N_PAD, ACT>, q));
   HV_LAUNCH_CHECK();
   return HV_OK;

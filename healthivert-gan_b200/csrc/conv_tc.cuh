@@ -112,6 +112,7 @@ struct TcParams {
   uint32_t slot_bytes;
   int nslots;
   long long* trace;  // debug event trace (device buffer of 12000 int64) or null
+  long long* timeline;  // debug: {min CTA entry, max CTA exit} globaltimer ns of this launch, or null
   int debug;         // ablation bits for bottleneck hunting (env HV_TC_DEBUG): 1 no MMAs, 2 no TMA loads, 4 no output stores
 };
 
@@ -163,6 +164,7 @@ int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, floa
                       unsigned int* ticket /*[n], zero-initialised, left zero*/, cudaStream_t st);
 
 // contextual attention on tensor cores (ctx_attn_tc.cu): f and y are 64-channel 64x64 chunked buffers
+void tc_set_timeline(long long* dev_buf);   // debug: launch i records {first CTA entry, last CTA exit} at dev_buf[4 i], [4 i + 1]
 size_t ctx_attn_tc_workspace_bytes(int n);
 int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
                     int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_flow = nullptr, cudaEvent_t ev_argmax = nullptr);

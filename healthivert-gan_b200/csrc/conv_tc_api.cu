@@ -111,6 +111,12 @@ extern "C" int hv_ctx_attn_fwd_bf16(const float* f, const float* mask, float* y,
 }
 
 // debug hook (not part of the drop-in surface): dev_buf = 12000 int64 on the device, or NULL to switch tracing off
+// debug hook: conv launch i (in host launch order) records {first CTA entry, last CTA exit} (globaltimer ns) at dev_buf[4 i], [4 i + 1];
+// the caller initialises the entry slots to a large value and the exit slots to 0
+extern "C" int hv_debug_conv_timeline(void* dev_buf) {
+  hv::tc_set_timeline(reinterpret_cast<long long*>(dev_buf));
+  return HV_OK;
+}
 extern "C" int hv_debug_conv_trace(void* dev_buf) {
   hv::tc_set_trace(reinterpret_cast<long long*>(dev_buf));
   return HV_OK;

@@ -19,6 +19,7 @@
 namespace hv {
 
 constexpr int G_BM = 128, G_BK = 64, G_STAGES = 6, G_TMEM_COLS = 512;
+constexpr int G_STAGE_PITCH = 36;   // floats per row of the epilogue transpose tile (32 + 4: conflict-free float4 rows)
 
 struct GemmParams {
   CUtensorMap map_a, map_b;
@@ -118,17 +119,21 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    float* stage_base = reinterpret_cast<float*>(smem + (size_t)G_STAGES * STAGE_BYTES + 256);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
       const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
-      const size_t out_row = ((size_t)b * p.M + (size_t)mt * G_BM + row) * p.N + (size_t)nt * BN;
+      const size_t out_row0 = ((size_t)b * p.M + (size_t)mt * G_BM) * p.N + (size_t)nt * BN;   // row 0 of the tile
       const float* cs = p.colscale ? p.colscale + (size_t)b * p.N + (size_t)nt * BN : nullptr;
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      // 32 x 32 blocks go through a per-warp staging tile so that global stores are row-contiguous: tcgen05.ld hands every lane
+      // its own ROW (32 lanes = 32 rows N*4 bytes apart); after the transpose 8 lanes cover 32 consecutive columns of one row
+      float* stage = stage_base + (warp - 2) * (32 * G_STAGE_PITCH);
+      const int tr = lane >> 3, tc = (lane & 7) * 4;   // read-back: rows tr + 4 i, columns tc .. tc + 3
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         float v[32];
@@ -138,27 +143,27 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           tc_fence_before();
           mbar_arrive(bar_tempty + 8u * acc);
         }
-        if (cs) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] *= __ldg(cs + c0 + j);
-        }
-        if (OUT_BF16) {
-          __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.c) + out_row + c0;
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(stage + lane * G_STAGE_PITCH + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        __syncwarp();
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (cs) sc = __ldg(reinterpret_cast<const float4*>(cs + c0 + tc));
+        const size_t blk = out_row0 + (size_t)(quad * 32) * p.N + c0 + tc;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h = __floats2bfloat162_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            reinterpret_cast<uint4*>(out)[j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        for (int i = 0; i < 8; ++i) {
+          const int r = tr + 4 * i;
+          float4 t = *reinterpret_cast<const float4*>(stage + r * G_STAGE_PITCH + tc);
+          t.x *= sc.x; t.y *= sc.y; t.z *= sc.z; t.w *= sc.w;
+          if (OUT_BF16) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(t.x, t.y), h1 = __floats2bfloat162_rn(t.z, t.w);
+            uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.c) + blk + (size_t)r * p.N) = pk;
+          } else {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.c) + blk + (size_t)r * p.N) = t;
           }
-        } else {
-          float* out = reinterpret_cast<float*>(p.c) + out_row + c0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(out)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         }
+        __syncwarp();
       }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
     }
@@ -203,7 +208,7 @@ static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int bat
 
 template <int BN, bool OUT_BF16>
 static int gemm_launch(const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)G_STAGES * (G_BM * 128 + BN * 128) + 256;
+  constexpr size_t smem = (size_t)G_STAGES * (G_BM * 128 + BN * 128) + 256 + 4 * 32 * G_STAGE_PITCH * sizeof(float);
   static bool configured = false;
   if (!configured) {
     HV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
