@@ -12,13 +12,18 @@
 //               stage's mbarrier before issuing so that the wait latency hides under the queued MMAs
 //   warps 2-5 : epilogue, one TMEM lane quadrant each; accumulators are ring-buffered in all 512 TMEM columns
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include "hv_common.cuh"
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
 namespace hv {
 
-constexpr int G_BM = 128, G_BK = 64, G_STAGES = 6, G_TMEM_COLS = 512;
+constexpr int G_BM = 128, G_BK = 64, G_TMEM_COLS = 512;
+// operand ring depth: 6 x 32 KB (BN = 128) or 4 x 48 KB (BN = 256).  BN = 256 is the default: an SS-mode MMA re-reads A (4 KB)
+// and B (BN x 32 B) from shared memory, TMA writes the same bytes once, and at 128 B/clk of shared-memory bandwidth a 128 x 128
+// tile is bound at 50 % of the tensor peak by that traffic, a 128 x 256 tile at 67 %
+__host__ __device__ constexpr int gemm_stages(int bn) { return bn == 256 ? 4 : 6; }
 constexpr int G_STAGE_PITCH = 36;   // floats per row of the epilogue transpose tile (32 + 4: conflict-free float4 rows)
 
 struct GemmParams {
@@ -32,6 +37,7 @@ struct GemmParams {
 template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
   constexpr int ACC_STAGES = G_TMEM_COLS / BN;
+  constexpr int G_STAGES = gemm_stages(BN);
   constexpr uint32_t A_BYTES = G_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -208,7 +214,7 @@ static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int bat
 
 template <int BN, bool OUT_BF16>
 static int gemm_launch(const GemmParams& p, int grid, cudaStream_t st) {
-  constexpr size_t smem = (size_t)G_STAGES * (G_BM * 128 + BN * 128) + 256 + 4 * 32 * G_STAGE_PITCH * sizeof(float);
+  constexpr size_t smem = (size_t)gemm_stages(BN) * (G_BM * 128 + BN * 128) + 256 + 4 * 32 * G_STAGE_PITCH * sizeof(float);
   static bool configured = false;
   if (!configured) {
     HV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -226,14 +232,18 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
   GemmParams p;
   int rc = gemm_map(&p.map_a, A, M, K, batch, strideA, G_BM);
   if (rc) return rc;
-  rc = gemm_map(&p.map_b, B, N, K, batch, strideB, 128);
+  // measured on B200 (batch 16, M = N = 1024): fp32 output K = 576: 28.5 us with BN = 128 vs 31.5 us with BN = 256 (512 tiles are
+  // only 3.5 waves); bf16 output K = 1024: 34.6 us vs 31.9 us
+  const int bn = (N % 256 == 0 && out_bf16 && getenv("HV_GEMM_BN128") == nullptr) ? 256 : 128;
+  rc = gemm_map(&p.map_b, B, N, K, batch, strideB, bn);
   if (rc) return rc;
   p.c = C; p.colscale = colscale; p.M = M; p.N = N; p.K = K; p.batch = batch;
-  p.tiles_m = M / G_BM; p.tiles_n = N / 128; p.total_tiles = p.tiles_m * p.tiles_n * batch; p.kblocks = K / G_BK;
+  p.tiles_m = M / G_BM; p.tiles_n = N / bn; p.total_tiles = p.tiles_m * p.tiles_n * batch; p.kblocks = K / G_BK;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  if (bn == 256) return out_bf16 ? gemm_launch<256, true>(p, grid, st) : gemm_launch<256, false>(p, grid, st);
   return out_bf16 ? gemm_launch<128, true>(p, grid, st) : gemm_launch<128, false>(p, grid, st);
 }
 
