@@ -36,8 +36,8 @@ __device__ __forceinline__ float act_fast(float x, int act_rt) {
 }
 
 // optional per-CTA event trace (debug / profiling aid, see tools/trace_conv.py): CTA 0 appends (tag, clock) pairs
-__device__ __forceinline__ void trace_ev(long long* tr, int& n, int tag) {
-  if (tr && blockIdx.x == 0 && n < 2000) { tr[2 * n] = tag; tr[2 * n + 1] = clock64(); ++n; }
+__device__ __forceinline__ void trace_ev(long long* tr, int& n, int tag) {   // tr is null except on CTA 0 of a traced launch
+  if (tr && n < 2000) { tr[2 * n] = tag; tr[2 * n + 1] = clock64(); ++n; }
 }
 
 
@@ -211,26 +211,27 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int slot = 0, ntr = 0;
     uint32_t phase = 0;
+    long long* tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    const unsigned long long tiles_magic = p.tiles_magic;
+    const int tiles_per_image = p.tiles_per_image, tile_adv = p.tile_adv, q_first = p.q_first, total_tiles = p.total_tiles;
     const uint32_t slots_base = smem_u32(s_slots);
     const int nseg = p.nseg, nslots = p.nslots;
     const bool map5d = p.map5d != 0;
     const uint32_t slot_bytes = p.slot_bytes;
     int rel2 = p.segs[0].rel_start2, c1 = p.segs[0].c1;   // single-segment layers keep the load recipe in registers
     uint32_t tx = p.segs[0].tx_bytes;
-    int cpl = p.segs[0].cpl, nload = p.segs[0].nchunks / cpl;
-    uint32_t load_bytes = tx / (uint32_t)nload;
+    int cpl = p.segs[0].cpl, nload = p.segs[0].nload;
+    uint32_t load_bytes = p.segs[0].load_bytes;
     bool map1 = false;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int img = tile / p.tiles_per_image;
-      const int c_tile = 2 * ((tile - img * p.tiles_per_image) * p.tile_adv + p.q_first);  // tensor-map inner unit = 8 B
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int img = (int)(((unsigned long long)tile * tiles_magic) >> 40);
+      const int c_tile = 2 * ((tile - img * tiles_per_image) * tile_adv + q_first);  // tensor-map inner unit = 8 B
       for (int s = 0; s < nseg; ++s) {
         if (nseg > 1) {
           rel2 = p.segs[s].rel_start2; c1 = p.segs[s].c1; tx = p.segs[s].tx_bytes; map1 = p.segs[s].map != 0;
-          cpl = p.segs[s].cpl; nload = p.segs[s].nchunks / cpl; load_bytes = tx / (uint32_t)nload;
+          cpl = p.segs[s].cpl; nload = p.segs[s].nload; load_bytes = p.segs[s].load_bytes;
         }
-        if (leader) trace_ev(p.trace, ntr, 2);
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
-        if (leader) trace_ev(p.trace, ntr, 3);
         if (leader) {
           const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_bytes;
           mbar_expect_tx(fb, (p.debug & 2) ? 0u : tx);
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
             if (map5d) tma_load_5d(dst + (uint32_t)i * load_bytes, &p.maps[0], fb, c_tile + rel2, c1, 0, i * cpl, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
             else tma_load_4d(dst + (uint32_t)i * load_bytes, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, i * cpl, img);
           }
-          trace_ev(p.trace, ntr, 1);
+          trace_ev(tr, ntr, 1);
         }
         if (++slot == nslots) { slot = 0; phase ^= 1u; }
       }
@@ -258,15 +259,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     const uint32_t a_lo_base = smem_u32(s_slots) >> 4;
     const uint32_t slot_units = p.slot_bytes >> 4;
     int slot = 0, acc = 0, ntr = 0;
-    long long* tr = p.trace ? p.trace + 4000 : nullptr;
+    long long* tr = (p.trace && blockIdx.x == 0) ? p.trace + 4000 : nullptr;
     uint32_t phase = 0, acc_phase = 0;
     // peek-ahead: the next barrier is probed BEFORE the current batch of MMAs is issued, so the probe latency
     // hides under the queued MMAs (the tensor pipe accepts only a few MMAs ahead of execution)
     bool ready_full = mbar_peek(bar_full, 0), ready_acc = mbar_peek(bar_tempty, 1);
-    const int nseg = p.nseg;
+    const int nseg = p.nseg, nslots = p.nslots, total_tiles = p.total_tiles;
     const bool s2d = p.s2d_in != 0, xp_in = p.in_xp > 1;
     TcSeg sg = p.segs[0];
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       mbar_wait_peeked(ready_acc, bar_tempty + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
       if (leader) trace_ev(tr, ntr, 11);
@@ -283,9 +284,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         tc_fence_after();
         if (leader) trace_ev(tr, ntr, 12);
         const uint32_t cur_slot = (uint32_t)slot, cur_empty = bar_empty + 8u * slot;
-        if (++slot == p.nslots) { slot = 0; phase ^= 1u; }
+        if (++slot == nslots) { slot = 0; phase ^= 1u; }
         ready_full = mbar_peek(bar_full + 8u * slot, phase);
-        if (leader) trace_ev(tr, ntr, 14);
         const uint32_t a_row = a_lo_base + cur_slot * slot_units + (a_lbo << 16) + sg.a0;
         const uint32_t b_row = b_lo_base + sg.b0;
         if (s == nseg - 1) ready_acc = mbar_peek(bar_tempty + 8u * acc, acc_phase ^ 1u);
@@ -325,7 +325,6 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         }
 #undef HV_SEG
         accumulate = 1;
-        if (leader) trace_ev(tr, ntr, 15);
         if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }  // slot is free once these MMAs have read it
       }
       if (leader) umma_commit(cur_tfull);  // accumulator tile complete -> epilogue
@@ -339,14 +338,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     const int group = warp / WPT;
     const int col0 = ((warp % WPT) >> 2) * NCOL;
     int ntr = 0;
-    long long* tr = (p.trace && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
+    long long* tr = (p.trace && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
+    const unsigned long long tiles_magic = p.tiles_magic;
     const int m = quad * 32 + lane;
     int j = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
       if (j % GROUPS != group) continue;
       const int acc = j % ACC_STAGES;
       const uint32_t acc_phase = (uint32_t)(j / ACC_STAGES) & 1u;
-      const int img = tile / p.tiles_per_image;
+      const int img = (int)(((unsigned long long)tile * tiles_magic) >> 40);
       const int q = (tile - img * p.tiles_per_image) * p.tile_adv + m + p.q_first;
       const int qrow = (int)(((unsigned long long)q * p.pitch_magic) >> 40);
       const int yy = qrow - p.in_border;
@@ -629,10 +629,13 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     int cpl = (cpl_req <= 0 || cpl_req > nch) ? nch : cpl_req;
     while (nch % cpl) --cpl;
     p.segs[i].cpl = cpl;
+    p.segs[i].nload = nch / cpl;
+    p.segs[i].load_bytes = p.segs[i].tx_bytes / (uint32_t)(nch / cpl);
   }
   p.tile_adv = TC_TILE_M - max_shift;
   const int span = p.h_out * pitch;  // positions from output (0,0) to the end of the last row (incl. side borders)
   p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
+  p.tiles_magic = ((1ull << 40) + (unsigned long long)p.tiles_per_image - 1) / (unsigned long long)p.tiles_per_image;
   p.total_tiles = p.tiles_per_image * n_images;
   int nslots = (int)((budget - fixed) / p.slot_bytes);
   nslots = min(nslots, max(2 * seg, 4));

@@ -73,8 +73,9 @@ struct TcSeg {
   int ntaps;          // taps per row
   uint32_t a0, a_step, b0, b_step, b_row_step;
   uint32_t tx_bytes;  // bytes this load brings
-  int cpl;            // channel chunks per TMA operation: the band is brought by nchunks / cpl concurrent operations on one
-                      // barrier (a single TMA operation streams at only ~12 B/clk, see profiles/r1_probe_mma_tma.log)
+  int cpl;            // channel chunks per TMA operation: the band is brought by nload = nchunks / cpl operations on one barrier
+  int nload;          // (precomputed on the host: the producer is one thread, an integer division costs it ~100 cycles)
+  uint32_t load_bytes;
 };
 
 enum TcOutMode { TC_OUT_CHUNKED = 0, TC_OUT_CHUNKED_UP2 = 1, TC_OUT_HEADS = 2, TC_OUT_CHUNKED_S2D = 3 };
@@ -100,6 +101,7 @@ struct TcParams {
   int tiles_per_image, total_tiles;
   int in_pitch, in_border, q_first;
   unsigned long long pitch_magic;  // ceil(2^40 / in_pitch): q / in_pitch == (q * magic) >> 40 for q < 2^20
+  unsigned long long tiles_magic;  // ceil(2^40 / tiles_per_image), same trick for tile -> image
   int h_out, w_out;   // extent of the accumulator-row grid (w_out = image width / in_xp)
   int w_img;          // image width in pixels
   int act;
