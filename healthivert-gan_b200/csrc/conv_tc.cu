@@ -823,6 +823,7 @@ int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst,
 struct PackKxArgs { const float* ptr[4]; int mode[4]; int dil; };
 template <int NSRC, int K>
 __global__ void __launch_bounds__(256) pack_kx_kernel(PackKxArgs a, TcBuf dst) {
+  pdl_prologue();
   constexpr int NCH = (K * NSRC + 15) / 16 * 2;  // chunks written (even)
   const int n = blockIdx.y, h = dst.h, w = dst.w;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -858,9 +859,9 @@ int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& ds
   dim3 grid((dst.h * dst.w + 255) / 256, dst.n);
   const int need = (k * nsrc + 15) / 16 * 2;
   HV_CHECK_ARG(need == dst.chunks, "tc_pack_kx: destination has %d chunks, the packed channels need %d", dst.chunks, need);
-  if (nsrc == 1 && k == 3) pack_kx_kernel<1, 3><<<grid, 256, 0, st>>>(a, dst);
-  else if (nsrc == 3 && k == 5) pack_kx_kernel<3, 5><<<grid, 256, 0, st>>>(a, dst);
-  else if (nsrc == 4 && k == 5) pack_kx_kernel<4, 5><<<grid, 256, 0, st>>>(a, dst);
+  if (nsrc == 1 && k == 3) HV_CUDA(launch_pdl(pack_kx_kernel<1, 3>, grid, dim3(256), 0, st, a, dst));
+  else if (nsrc == 3 && k == 5) HV_CUDA(launch_pdl(pack_kx_kernel<3, 5>, grid, dim3(256), 0, st, a, dst));
+  else if (nsrc == 4 && k == 5) HV_CUDA(launch_pdl(pack_kx_kernel<4, 5>, grid, dim3(256), 0, st, a, dst));
   else { set_error("tc_pack_kx: no instance for %d sources, k=%d", nsrc, k); return HV_ERR_UNSUPPORTED; }
   HV_LAUNCH_CHECK();
   return HV_OK;

@@ -25,6 +25,7 @@ constexpr int CA_C = 64, CA_H = 64, CA_SIDE = 32, CA_L = 1024, CA_KP = 576, CA_K
 
 // ------------------------------------------------------------------ patches P + column norms (one warp per (n, l))
 __global__ void __launch_bounds__(256) ca_tc_patches_kernel(TcBuf f, __nv_bfloat16* __restrict__ P, float* __restrict__ inv_norm) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int n = gw / CA_L, l = gw - n * CA_L;
   if (n >= f.n) return;
@@ -49,6 +50,7 @@ __global__ void __launch_bounds__(256) ca_tc_patches_kernel(TcBuf f, __nv_bfloat
 // ------------------------------------------------------------------ raw patches, transposed: Rt[c*16+ky*4+kx][b]
 // one thread = (n, chunk, tap, bh, group of 8 bw): 8 loads of 8 channels, 8x8 transpose in registers, 8 stores of 16 B
 __global__ void __launch_bounds__(256) ca_tc_raw_kernel(TcBuf f, __nv_bfloat16* __restrict__ Rt) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int g = i & 3, bh = (i >> 2) & 31, t = (i >> 7) & 15, ch = (i >> 11) & 7, n = i >> 14;
   if (n >= f.n) return;
@@ -81,6 +83,7 @@ __device__ __forceinline__ int ca_cm(int i) { return ((i & 31) << 5) | (i >> 5);
 __global__ void __launch_bounds__(256) ca_tc_fuse_softmax_kernel(const float* __restrict__ T, const float* __restrict__ mm,
                                                                  int mm_stride, __nv_bfloat16* __restrict__ A,
                                                                  int32_t* __restrict__ argmax_out, float scale, int fuse) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = blockIdx.y, j = blockIdx.x * 8 + warp;
   const float* Tn = T + (size_t)n * CA_L * CA_L;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(256) ca_tc_fuse_softmax_kernel(const float* __
 // ------------------------------------------------------------------ overlap-add of the pasted patches (:377-379) -> chunked bf16
 // one thread = (n, chunk, oy, ox): y[c][oy][ox] = 0.25 * sum over the (<= 4) patches covering the pixel
 __global__ void __launch_bounds__(256) ca_tc_fold_kernel(const __nv_bfloat16* __restrict__ cols, TcBuf y) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int ox = i & 63, oy = (i >> 6) & 63, ch = (i >> 12) & 7, n = i >> 15;
   if (n >= y.n) return;
@@ -214,15 +218,15 @@ int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* 
   const int n = f.n;
   CaTcWorkspace ws;
   ca_tc_layout(n, (char*)workspace, &ws);
-  ca_tc_patches_kernel<<<(n * CA_L + 7) / 8, 256, 0, st>>>(f, ws.P, ws.inv_norm);
+  HV_CUDA(launch_pdl(ca_tc_patches_kernel, dim3((n * CA_L + 7) / 8), dim3(256), 0, st, f, ws.P, ws.inv_norm));
   HV_LAUNCH_CHECK();
-  ca_tc_raw_kernel<<<(n * 16384 + 255) / 256, 256, 0, st>>>(f, ws.Rt);
+  HV_CUDA(launch_pdl(ca_tc_raw_kernel, dim3((n * 16384 + 255) / 256), dim3(256), 0, st, f, ws.Rt));
   HV_LAUNCH_CHECK();
   int rc = ca_mask_launch(mask, ws.mm, n, CA_SIDE, 4 * CA_H, 4 * CA_H, per_sample_mask, st);
   if (rc) return rc;
   rc = gemm_tc_nt(ws.P, ws.P, ws.T, ws.inv_norm, CA_L, CA_L, CA_KP, n, (long long)CA_L * CA_KP, (long long)CA_L * CA_KP, 0, st);
   if (rc) return rc;
-  ca_tc_fuse_softmax_kernel<<<dim3(CA_L / 8, n), 256, 0, st>>>(ws.T, ws.mm, CA_L, ws.A, ws.argmax, scale, fuse);
+  HV_CUDA(launch_pdl(ca_tc_fuse_softmax_kernel, dim3(CA_L / 8, n), dim3(256), 0, st, (const float*)ws.T, (const float*)ws.mm, (int)CA_L, ws.A, ws.argmax, scale, fuse));
   HV_LAUNCH_CHECK();
   if ((offsets || flow) && st_flow && ev_argmax) {
     HV_CUDA(cudaEventRecord(ev_argmax, st));
@@ -232,7 +236,7 @@ int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* 
   }
   rc = gemm_tc_nt(ws.Rt, ws.A, ws.cols, nullptr, CA_KR, CA_L, CA_L, n, (long long)CA_KR * CA_L, (long long)CA_L * CA_L, 1, st);
   if (rc) return rc;
-  ca_tc_fold_kernel<<<(n * 32768 + 255) / 256, 256, 0, st>>>(ws.cols, y);
+  HV_CUDA(launch_pdl(ca_tc_fold_kernel, dim3((n * 32768 + 255) / 256), dim3(256), 0, st, (const __nv_bfloat16*)ws.cols, y));
   HV_LAUNCH_CHECK();
   if ((offsets || flow) && !(st_flow && ev_argmax)) {
     rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, st);

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();   // barriers / TMEM / tensor-map prefetch above overlap the predecessor's tail
   const int tiles_per_batch = p.tiles_m * p.tiles_n;
 
   if (warp == 0) {
@@ -220,7 +221,7 @@ static int gemm_launch(const GemmParams& p, int grid, cudaStream_t st) {
     HV_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, OUT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  gemm_tc_kernel<BN, OUT_BF16><<<grid, 192, smem, st>>>(p);
+  HV_CUDA(launch_pdl(gemm_tc_kernel<BN, OUT_BF16>, dim3(grid), dim3(192), smem, st, p));
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
