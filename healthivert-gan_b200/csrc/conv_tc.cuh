@@ -169,6 +169,6 @@ int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, floa
 void tc_set_timeline(long long* dev_buf);   // debug: launch i records {first CTA entry, last CTA exit} at dev_buf[4 i], [4 i + 1]
 size_t ctx_attn_tc_workspace_bytes(int n);
 int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
-                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_flow = nullptr, cudaEvent_t ev_argmax = nullptr);
+                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_aux = nullptr, cudaEvent_t* evs = nullptr);
 
 }  // namespace hv

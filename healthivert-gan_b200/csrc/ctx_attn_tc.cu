@@ -208,37 +208,46 @@ static size_t ca_tc_layout(int n, char* base, CaTcWorkspace* ws) {
 size_t ctx_attn_tc_workspace_bytes(int n) { return ca_tc_layout(n, nullptr, nullptr); }
 
 // f: chunked bf16 [n][8 chunks][64x64, any border]; y: chunked bf16 output buffer of the same extent
-// st_flow / ev_argmax (optional): the offsets / flow outputs, which nothing downstream consumes, are produced on st_flow after
-// the arg-max is known instead of extending st's critical path
+// st_aux / evs (optional, 3 events): a second stream for the work that is off the critical path patches -> similarity -> softmax ->
+// paste -> fold: the raw 4x4 patch matrix and the mask run beside the similarity GEMM, the offsets / flow outputs (which nothing
+// downstream consumes) after the arg-max is known
 int ctx_attn_fwd_tc(const TcBuf& f, const float* mask, const TcBuf& y, int32_t* offsets, float* flow, float scale, int fuse,
-                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_flow, cudaEvent_t ev_argmax) {
+                    int per_sample_mask, void* workspace, cudaStream_t st, cudaStream_t st_aux, cudaEvent_t* evs) {
   HV_CHECK_ARG(f.ptr && y.ptr && mask && workspace, "ctx_attn_fwd_tc: null argument");
   HV_CHECK_ARG(f.chunks == 8 && f.h == CA_H && f.w == CA_H && !f.s2d && y.chunks == 8 && y.h == CA_H && y.w == CA_H && !y.s2d && y.n == f.n,
                "ctx_attn_fwd_tc: built for 64-channel 64x64 feature maps");
   const int n = f.n;
+  const bool two = st_aux != nullptr && evs != nullptr;
+  cudaStream_t sx = two ? st_aux : st;
   CaTcWorkspace ws;
   ca_tc_layout(n, (char*)workspace, &ws);
+  if (two) {
+    HV_CUDA(cudaEventRecord(evs[0], st));
+    HV_CUDA(cudaStreamWaitEvent(sx, evs[0], 0));
+  }
   HV_CUDA(launch_pdl(ca_tc_patches_kernel, dim3((n * CA_L + 7) / 8), dim3(256), 0, st, f, ws.P, ws.inv_norm));
   HV_LAUNCH_CHECK();
-  HV_CUDA(launch_pdl(ca_tc_raw_kernel, dim3((n * 16384 + 255) / 256), dim3(256), 0, st, f, ws.Rt));
-  HV_LAUNCH_CHECK();
-  int rc = ca_mask_launch(mask, ws.mm, n, CA_SIDE, 4 * CA_H, 4 * CA_H, per_sample_mask, st);
+  int rc = ca_mask_launch(mask, ws.mm, n, CA_SIDE, 4 * CA_H, 4 * CA_H, per_sample_mask, sx);
   if (rc) return rc;
+  HV_CUDA(launch_pdl(ca_tc_raw_kernel, dim3((n * 16384 + 255) / 256), dim3(256), 0, sx, f, ws.Rt));
+  HV_LAUNCH_CHECK();
+  if (two) HV_CUDA(cudaEventRecord(evs[1], sx));
   rc = gemm_tc_nt(ws.P, ws.P, ws.T, ws.inv_norm, CA_L, CA_L, CA_KP, n, (long long)CA_L * CA_KP, (long long)CA_L * CA_KP, 0, st);
   if (rc) return rc;
+  if (two) HV_CUDA(cudaStreamWaitEvent(st, evs[1], 0));
   HV_CUDA(launch_pdl(ca_tc_fuse_softmax_kernel, dim3(CA_L / 8, n), dim3(256), 0, st, (const float*)ws.T, (const float*)ws.mm, (int)CA_L, ws.A, ws.argmax, scale, fuse));
   HV_LAUNCH_CHECK();
-  if ((offsets || flow) && st_flow && ev_argmax) {
-    HV_CUDA(cudaEventRecord(ev_argmax, st));
-    HV_CUDA(cudaStreamWaitEvent(st_flow, ev_argmax, 0));
-    rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, st_flow);
+  if ((offsets || flow) && two) {
+    HV_CUDA(cudaEventRecord(evs[2], st));
+    HV_CUDA(cudaStreamWaitEvent(sx, evs[2], 0));
+    rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, sx);
     if (rc) return rc;
   }
   rc = gemm_tc_nt(ws.Rt, ws.A, ws.cols, nullptr, CA_KR, CA_L, CA_L, n, (long long)CA_KR * CA_L, (long long)CA_L * CA_L, 1, st);
   if (rc) return rc;
   HV_CUDA(launch_pdl(ca_tc_fold_kernel, dim3((n * 32768 + 255) / 256), dim3(256), 0, st, (const __nv_bfloat16*)ws.cols, y));
   HV_LAUNCH_CHECK();
-  if ((offsets || flow) && !(st_flow && ev_argmax)) {
+  if ((offsets || flow) && !two) {
     rc = ca_offsets_flow_launch(ws.argmax, offsets, flow, n, CA_SIDE, 8, ws.scratch, st);
     if (rc) return rc;
   }

@@ -111,7 +111,7 @@ struct hv_generator {
   // bf16 plan: light kernels whose results are needed late (CAM packing, height heads, attention flow) run on `aux`,
   // co-resident with the one-CTA-per-SM conv kernels of the main stream
   cudaStream_t aux = nullptr;
-  cudaEvent_t ev_aux[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_aux[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   struct hv::TcPlan* tc = nullptr;  // bf16 tensor-core plan (precision == HV_PREC_BF16)
 };
 
@@ -423,7 +423,7 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
   cudaStream_t sa = g->side;
   for (int l : {PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
   RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa, use_aux ? ax : nullptr,
-                     g->ev_aux[3]));
+                     use_aux ? &g->ev_aux[6] : nullptr));
   RC(run(PM9, sa));
   RC(run(PM10, sa));
   HV_CUDA(cudaEventRecord(g->ev_join, sa));
