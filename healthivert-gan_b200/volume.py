@@ -7,12 +7,15 @@ run as one batch through the generator, slice preparation / stitching / uint8 ha
 The host only decides WHICH slices enter which stage (a [S, 3] int32 count table, one small D2H per volume), exactly the
 control decisions the reference takes at eval:186-197, :204, :213.  ``axis=2`` walks sagittal slices ``vol[:, :, z]`` like the
 reference driver; ``axis=1`` is the coronal twin (``vol[:, z, :]``, evaluation/RHLV_quantification_coronal.py:51-54) needed by
-the 2.5D RHLV features.  NIfTI I/O is out of scope: volumes come and go as arrays.
+the 2.5D RHLV features.  ``synthesize`` takes and returns arrays; ``synthesize_files`` is the file-level twin of the reference
+loop body (NIfTI in, NIfTI out, healthivert_gan_b200.nifti).
 """
+import os
+
 import numpy as np
 import torch
 
-from . import _lib, mask_ops
+from . import _lib, mask_ops, nifti
 from ._lib import check, ptr
 
 
@@ -112,3 +115,26 @@ class VolumeSynthesizer:
             return ct_f.cpu().numpy(), lab_f.cpu().numpy()
         finally:
             self.g.per_sample_mask, self.g.return_flow = prev_flags
+
+    def synthesize_files(self, ct_path, label_path, cam_path, out_ct_path, out_label_path, vert_id=None, axis=2):
+        """One iteration of the reference's file loop (eval_3d_sagittal_twostage.py:153-241): read the straightened CT / label /
+        Grad-CAM volumes, synthesise, write `CT_fake` / `label_fake` with the CT volume's affine.  ``vert_id`` defaults to the
+        number after the last underscore of the file name (`<patient>_<vert>.nii.gz`, eval:166-167).  Outputs are float64 like
+        the reference's `np.zeros_like(ct_nii.get_fdata())` volumes."""
+        if vert_id is None:
+            stem = os.path.basename(ct_path)
+            stem = stem[:-7] if stem.endswith(".nii.gz") else os.path.splitext(stem)[0]
+            vert_id = int(stem.rsplit("_", 1)[1])
+        ct_img = nifti.load(ct_path)
+        ct = ct_img.get_fdata()
+        label = nifti.load(label_path).get_fdata()
+        cam = nifti.load(cam_path).get_fdata()
+        if not (ct.shape == label.shape == cam.shape and ct.ndim == 3):
+            raise _lib.HvError(f"CT {ct.shape}, label {label.shape} and CAM {cam.shape} volumes must be 3-D and of one shape")
+        ct_fake, label_fake = self.synthesize(ct, label, cam, vert_id, axis=axis)
+        for path, vol in ((out_ct_path, ct_fake), (out_label_path, label_fake)):
+            d = os.path.dirname(path)
+            if d:
+                os.makedirs(d, exist_ok=True)
+            nifti.save(path, vol.astype(np.float64), ct_img.affine)
+        return vert_id

@@ -142,3 +142,26 @@ def test_volume_driver_three_stage_loop_against_oracle(gen, synthetic_sd):
     # three chained forwards: fp32 re-association noise can flip isolated threshold / truncation decisions
     assert (got_seg != ref_seg).mean() <= 2e-4
     assert np.abs(got_ct - ref_ct).max() <= 2.0 and np.abs(got_ct - ref_ct).mean() <= 0.01
+
+
+def test_file_level_driver_matches_array_driver(gen, tmp_path):
+    """synthesize_files (NIfTI in / out, process_nii_files loop body eval:153-241) == synthesize on the same volumes; the outputs
+    carry the CT volume's affine and stay float64 like the reference's np.zeros_like(get_fdata()) volumes."""
+    from healthivert_gan_b200 import nifti
+    label, ct, cam = synth.synthetic_volume(seed=5, depth=8)
+    aff = np.array([[0.0, 0.0, -1.0, 102.25], [0.0, -1.0, 0.0, 90.5], [-1.0, 0.0, 0.0, -1053.0], [0.0, 0.0, 0.0, 1.0]])   # float32-exact
+    paths = {k: str(tmp_path / k / "case7_20.nii.gz") for k in ("CT", "label", "CAM", "CT_fake", "label_fake")}
+    for k, vol in (("CT", ct), ("label", label), ("CAM", cam)):
+        os.makedirs(os.path.dirname(paths[k]), exist_ok=True)
+        nifti.save(paths[k], vol.astype(np.float64), aff)
+    vs = VolumeSynthesizer(gen, batch=4)
+    vid = vs.synthesize_files(paths["CT"], paths["label"], paths["CAM"], paths["CT_fake"], paths["label_fake"])
+    assert vid == 20
+    want_ct, want_seg = vs.synthesize(ct, label, cam, 20)
+    got_ct, got_seg = nifti.load(paths["CT_fake"]), nifti.load(paths["label_fake"])
+    assert got_ct.dataobj.dtype == np.float64 and got_ct.shape == ct.shape
+    np.testing.assert_array_equal(got_ct.affine, aff)
+    np.testing.assert_array_equal(got_seg.affine, aff)
+    assert np.array_equal(got_ct.get_fdata(), want_ct.astype(np.float64))
+    assert np.array_equal(got_seg.get_fdata(), want_seg.astype(np.float64))
+    assert got_seg.get_fdata().any()
