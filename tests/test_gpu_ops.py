@@ -223,3 +223,28 @@ def test_column_heights_and_rhlv_against_oracle(axis, golden_dir):
     assert counts.shape[0] == 0
     with pytest.raises(_lib.HvError):
         mask_ops.column_heights(tf, tl, axis, 0, 10_000)
+
+
+@pytest.mark.parametrize("axis", [2, 1])
+def test_rhlv_table_from_nifti_files(axis, golden_dir, tmp_path):
+    """grading.rhlv_table (process_datasets_to_excel, RHLV_quantification.py:150-195) on NIfTI files == the reference's known answers
+    for the shipped 0007_20 label volume (fake := label shifted up by 3 rows, threshold 0.7, divisor 5)."""
+    import json
+    import os
+    from healthivert_gan_b200 import grading, nifti
+    v = np.load(os.path.join(golden_dir, "rhlv_label_0007_20.npz"))["label"].astype(np.float64)
+    lab = (v == 20).astype(np.float64)
+    fk = np.maximum(lab, np.roll(lab, -3, axis=0))
+    fk[-3:] = lab[-3:]
+    fake = np.where(fk > 0, 20.0, np.where(v == 20, 0.0, v))
+    os.makedirs(tmp_path / "label"), os.makedirs(tmp_path / "label_fake")
+    nifti.save(str(tmp_path / "label" / "0007_20.nii.gz"), v, np.eye(4))
+    nifti.save(str(tmp_path / "label_fake" / "0007_20.nii.gz"), fake, np.eye(4))
+    info = {"train": {"0007_19": 0}, "val": {"0007_20": 2}}          # 0007_19 has no files: skipped like the reference does
+    rows = grading.rhlv_table(info, str(tmp_path / "label"), str(tmp_path / "label_fake"), length_divisor=5, height_threshold=0.7, axis=axis)
+    known = json.load(open(os.path.join(golden_dir, "rhlv_known.json")))[f"0007_20_axis{axis}"]
+    assert len(rows) == 1 and rows[0]["Vertebra"] == "0007_20" and rows[0]["Label"] == 2 and rows[0]["Dataset"] == "val"
+    got = [rows[0][k] for k in ("All RHLV", "Pre RHLV", "Mid RHLV", "Post RHLV", "Relative Height Label")]
+    assert np.allclose(got, known["rhlv"], rtol=0, atol=1e-12)
+    grading.write_table(rows, str(tmp_path / "t.csv"))
+    assert grading.read_table(str(tmp_path / "t.csv"))["Mid RHLV"][0] == rows[0]["Mid RHLV"]
