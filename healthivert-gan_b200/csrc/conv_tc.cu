@@ -161,6 +161,11 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   // output mode / layouts: compile-time constants in the specialised instances (bits 16.. of FIXED: 1 chunked, 2 chunked + x2
   // upsample, 3 heads, 4 space-to-depth, 5 chunked into an x-phase buffer, 6 upsample into an x-phase buffer), else kernel parameters
   constexpr int FO = (FIXED >> 16) & 15;
+  // PAIR (bit 20): a round of the producer / issuer / barrier protocol covers TWO consecutive tiles (two bands per slot, two
+  // accumulators per stage): the thin layers are bound by the latency of the single-thread handshake chain per round, not by MMAs
+  constexpr bool PAIR = ((FIXED >> 20) & 1) != 0;
+  constexpr int TPR = PAIR ? 2 : 1;                      // tiles per round
+  constexpr int RSTAGES = ACC_STAGES / TPR;              // accumulator barrier stages
   const int k_in_xp = FIXED != 0 ? ((FIXED >> 12 & 15) == 3 ? 4 : 1) : p.in_xp;
   const int k_out_mode = FO == 0 ? p.out_mode : (FO == 1 || FO == 5) ? (int)TC_OUT_CHUNKED : (FO == 2 || FO == 6) ? (int)TC_OUT_CHUNKED_UP2
                                               : FO == 3 ? (int)TC_OUT_HEADS : (int)TC_OUT_CHUNKED_S2D;
@@ -168,7 +173,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   const uint32_t w_region = (p.w_bytes + 127u) & ~127u;
   uint8_t* s_slots = smem + w_region;
   // 1 KB pad after the band ring: the last chunk of a shifted tap view reads past its band
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + (size_t)p.nslots * p.slot_bytes + 1024);
+  const uint32_t slot_stride = p.slot_bytes * TPR;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_slots + (size_t)p.nslots * slot_stride + 1024);
   const uint32_t bar_full = smem_u32(bars);
   const uint32_t bar_empty = bar_full + 8u * p.nslots;
   const uint32_t bar_w = bar_empty + 8u * p.nslots;
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     if (lane == 0) {
       for (int i = 0; i < p.nslots; ++i) { mbar_init(bar_full + 8u * i, 1); mbar_init(bar_empty + 8u * i, 1); }
       mbar_init(bar_w, 1);
-      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * WPT); }
+      for (int i = 0; i < ACC_STAGES; ++i) { mbar_init(bar_tfull + 8u * i, 1); mbar_init(bar_tempty + 8u * i, 32 * WPT * TPR); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -236,9 +242,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     int cpl = p.segs[0].cpl, nload = p.segs[0].nload;
     uint32_t load_bytes = p.segs[0].load_bytes;
     bool map1 = false;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int rounds = (total_tiles + TPR - 1) / TPR;
+    for (int round = blockIdx.x; round < rounds; round += gridDim.x) {
+      const int tile = round * TPR;
       const int img = (int)(((unsigned long long)tile * tiles_magic) >> 40);
       const int c_tile = 2 * ((tile - img * tiles_per_image) * tile_adv + q_first);  // tensor-map inner unit = 8 B
+      // second tile of a pair (the last round of an odd tile count repeats its first tile: same values stored twice)
+      const int tile_b = min(tile + 1, total_tiles - 1);
+      const int img_b = (int)(((unsigned long long)tile_b * tiles_magic) >> 40);
+      const int c_tile_b = 2 * ((tile_b - img_b * tiles_per_image) * tile_adv + q_first);
       for (int s = 0; s < nseg; ++s) {
         if (nseg > 1) {
           rel2 = p.segs[s].rel_start2; c1 = p.segs[s].c1; tx = p.segs[s].tx_bytes; map1 = p.segs[s].map != 0;
@@ -246,11 +258,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         }
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
         if (leader) {
-          const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_bytes;
-          mbar_expect_tx(fb, (p.debug & 2) ? 0u : tx);
+          const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_stride;
+          mbar_expect_tx(fb, (p.debug & 2) ? 0u : tx * TPR);
           for (int i = 0; i < ((p.debug & 2) ? 0 : nload); ++i) {
             if (map5d) tma_load_5d(dst + (uint32_t)i * load_bytes, &p.maps[0], fb, c_tile + rel2, c1, 0, i * cpl, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
             else tma_load_4d(dst + (uint32_t)i * load_bytes, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, i * cpl, img);
+            if (PAIR) {
+              if (map5d) tma_load_5d(dst + slot_bytes + (uint32_t)i * load_bytes, &p.maps[0], fb, c_tile_b + rel2, c1, 0, i * cpl, img_b);
+              else tma_load_4d(dst + slot_bytes + (uint32_t)i * load_bytes, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile_b + rel2, c1, i * cpl, img_b);
+            }
           }
           trace_ev(tr, ntr, 1);
         }
@@ -281,13 +297,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     constexpr int FK = (FIXED >> 12) & 15, FR = (FIXED >> 8) & 15, FT = (FIXED >> 4) & 15, FS = FIXED & 15;
     const bool s2d = FIXED == 0 && p.s2d_in != 0, xp_in = FIXED == 0 && p.in_xp > 1;
     TcSeg sg = p.segs[0];
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int rounds = (total_tiles + TPR - 1) / TPR;
+    const uint32_t stride_units = slot_units * TPR;
+    for (int round = blockIdx.x; round < rounds; round += gridDim.x) {
       mbar_wait_peeked(ready_acc, bar_tempty + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
       if (leader) trace_ev(tr, ntr, 11);
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * N_PAD);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TPR * N_PAD);
       const uint32_t cur_tfull = bar_tfull + 8u * acc;
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1u; }
+      if (++acc == RSTAGES) { acc = 0; acc_phase ^= 1u; }
       uint32_t accumulate = 0;
       for (int s = 0; s < nseg; ++s) {
         if (nseg > 1) sg = p.segs[s];  // single-segment layers keep the descriptor recipe in registers
@@ -300,27 +318,32 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         const uint32_t cur_slot = (uint32_t)slot, cur_empty = bar_empty + 8u * slot;
         if (++slot == nslots) { slot = 0; phase ^= 1u; }
         ready_full = mbar_peek(bar_full + 8u * slot, phase);
-        const uint32_t a_row = a_lo_base + cur_slot * slot_units + (a_lbo << 16) + sg.a0;
+        const uint32_t a_slot = a_lo_base + cur_slot * stride_units;
+        const uint32_t a_row = a_slot + (a_lbo << 16) + sg.a0;
         const uint32_t b_row = b_lo_base + sg.b0;
         if (s == nseg - 1) ready_acc = mbar_peek(bar_tempty + 8u * acc, acc_phase ^ 1u);
         if (FIXED != 0) {
-          if (FK == 1) {
-            issue_segment<N_PAD, FR ? FR : 1, FT ? FT : 1, FS ? FS : 1>(mma_on, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);
-          } else if (FK == 2) {
-            issue_s2d<N_PAD, FS ? FS : 1>(mma_on, d_tmem, a_lo_base + cur_slot * slot_units + ((8u * TC_TILE_M) << 16), b_row, b_step, idesc);
-          } else if (FK == 3) {
-            issue_xp4<N_PAD, FR ? FR : 1, FS ? FS : 1>(mma_on, d_tmem, a_lo_base + cur_slot * slot_units + ((4u * (uint32_t)(FR ? FR : 1) * TC_TILE_M) << 16),
-                                                     b_row, b_step, idesc, accumulate);
-          } else {
-            if (s == 0) issue_segment<N_PAD, 3, 3, FS ? FS : 1>(mma_on, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);
-            else issue_segment<N_PAD, 3, 1, 1>(mma_on, d_tmem, a_row, b_row, a_step, b_step, b_row_step, idesc, accumulate);
+#pragma unroll
+          for (int u = 0; u < TPR; ++u) {   // the tiles of the round: band u of the slot -> accumulator u of the stage
+            const uint32_t dt = d_tmem + (uint32_t)(u * N_PAD), au = (uint32_t)u * slot_units;
+            if (FK == 1) {
+              issue_segment<N_PAD, FR ? FR : 1, FT ? FT : 1, FS ? FS : 1>(mma_on, dt, a_row + au, b_row, a_step, b_step, b_row_step, idesc, accumulate);
+            } else if (FK == 2) {
+              issue_s2d<N_PAD, FS ? FS : 1>(mma_on, dt, a_slot + au + ((8u * TC_TILE_M) << 16), b_row, b_step, idesc);
+            } else if (FK == 3) {
+              issue_xp4<N_PAD, FR ? FR : 1, FS ? FS : 1>(mma_on, dt, a_slot + au + ((4u * (uint32_t)(FR ? FR : 1) * TC_TILE_M) << 16), b_row, b_step, idesc,
+                                                       accumulate);
+            } else {
+              if (s == 0) issue_segment<N_PAD, 3, 3, FS ? FS : 1>(mma_on, dt, a_row + au, b_row, a_step, b_step, b_row_step, idesc, accumulate);
+              else issue_segment<N_PAD, 3, 1, 1>(mma_on, dt, a_row + au, b_row, a_step, b_step, b_row_step, idesc, accumulate);
+            }
           }
           accumulate = 1;
           if (leader) { umma_commit(cur_empty); trace_ev(tr, ntr, 13); }
           continue;
         }
         if (s2d) {
-          const uint32_t a_s2d = a_lo_base + cur_slot * slot_units + ((8u * TC_TILE_M) << 16);
+          const uint32_t a_s2d = a_slot + ((8u * TC_TILE_M) << 16);
           if (ksteps == 1) issue_s2d<N_PAD, 1>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
           else if (ksteps == 2) issue_s2d<N_PAD, 2>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
           else issue_s2d<N_PAD, 4>(mma_on, d_tmem, a_s2d, b_row, b_step, idesc);
@@ -329,7 +352,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
           continue;
         }
         if (xp_in) {
-          const uint32_t a_xp = a_lo_base + cur_slot * slot_units + ((4u * (uint32_t)nrows * TC_TILE_M) << 16);
+          const uint32_t a_xp = a_slot + ((4u * (uint32_t)nrows * TC_TILE_M) << 16);
           const int shape_xp = (nrows << 4) | ksteps;
           switch (shape_xp) {
             case (3 << 4) | 1: issue_xp4<N_PAD, 3, 1>(mma_on, d_tmem, a_xp, b_row, b_step, idesc, accumulate); break;
@@ -371,11 +394,15 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     long long* tr = (p.trace && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
     const unsigned long long tiles_magic = p.tiles_magic;
     const int m = quad * 32 + lane;
-    int j = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++j) {
-      if (j % GROUPS != group) continue;
-      const int acc = j % ACC_STAGES;
-      const uint32_t acc_phase = (uint32_t)(j / ACC_STAGES) & 1u;
+    const int total_tiles = p.total_tiles, rounds = (total_tiles + TPR - 1) / TPR;
+    // the CTA's tiles in processing order: q = TPR * (round index of this CTA) + (tile of the round); group g owns q % GROUPS == g
+    for (int q_lin = group; ; q_lin += GROUPS) {
+      const int j = q_lin / TPR, u = q_lin - j * TPR;
+      const int round = blockIdx.x + j * (int)gridDim.x;
+      if (round >= rounds) break;
+      const int tile = min(round * TPR + u, total_tiles - 1);
+      const int acc = j % RSTAGES;
+      const uint32_t acc_phase = (uint32_t)(j / RSTAGES) & 1u;
       const int img = (int)(((unsigned long long)tile * tiles_magic) >> 40);
       const int q = (tile - img * p.tiles_per_image) * p.tile_adv + m + p.q_first;
       const int qrow = (int)(((unsigned long long)q * p.pitch_magic) >> 40);
@@ -387,7 +414,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
       trace_ev(tr, ntr, 21);
-      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * N_PAD);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((acc * TPR + u) * N_PAD);
 
       // position of output pixel (y, x) inside one chunk plane of the output buffer (plain / space-to-depth / x-phase)
       auto out_pos = [&](int y, int x) -> size_t {
@@ -546,6 +573,8 @@ static int max_chunks_of(const TcSource* srcs, int nsrc) {
   return m;
 }
 
+static int tc_issue_code(const TcConv& c);
+
 int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images) {
   HV_CHECK_ARG(nsrc >= 1 && nsrc <= 2, "tc_conv: 1 or 2 sources supported");
   HV_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || (stride == 2 && k == 3 && dil == 1)), "tc_conv: unsupported k/stride");
@@ -596,6 +625,20 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   size_t budget = 227 * 1024 - 2048;
   const size_t fixed = ((p.w_bytes + 127u) & ~127u) + 1024 /* over-read pad */ + TC_BAR_BYTES;
   c.ctas_per_sm = 1;
+  // Tile pairs (see PAIR in the kernel) for a thin, long layer that cannot run as two co-resident CTAs (its three band slots do not
+  // fit in half the shared memory): at least ~6 rounds per SM and two pair slots beside the weights.  Measured per layer on B200:
+  // pairs help exactly there (merged fine conv1|pmconv1: 45.0 -> 40.5 us); where two CTAs per SM are possible they are the better
+  // latency hiding (pairs: conv3 +4 us, heads +8 us), and the x-phase layers lose too (conv16 +3 us).  HV_TC_PAIR=0 switches the
+  // mode off (A/B).
+  bool want_pair = false;
+  {
+    const char* e = getenv("HV_TC_PAIR");
+    const long long est_tiles = ((long long)b0.sub_h() * pitch / (TC_TILE_M - 2) + 1) * n_images;
+    const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k * xp);
+    const bool two_ctas = tc_ctas_per_sm(c.n_pad) == 2 && fixed + 3 * band <= half;
+    want_pair = !(e && atoi(e) == 0) && c.n_pad <= 32 && xp == 1 && !two_ctas && est_tiles >= 12ll * 148 && fixed + 2 * 2 * band <= budget;
+  }
+  if (!want_pair)
   {  // two co-resident CTAs when the layer is thin and three tile slots still fit in half the shared memory (measured: with
      // only two slots per CTA the merged fine conv1|pmconv1 layer got 30 % slower)
     const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k * xp);
@@ -667,11 +710,13 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.tiles_per_image = (span + p.tile_adv - 1) / p.tile_adv;
   p.tiles_magic = ((1ull << 40) + (unsigned long long)p.tiles_per_image - 1) / (unsigned long long)p.tiles_per_image;
   p.total_tiles = p.tiles_per_image * n_images;
-  int nslots = (int)((budget - fixed) / p.slot_bytes);
+  p.pair = (want_pair && tc_issue_code(c) != 0) ? 1 : 0;
+  const size_t slot_stride = (size_t)p.slot_bytes * (p.pair ? 2 : 1);
+  int nslots = (int)((budget - fixed) / slot_stride);
   nslots = min(nslots, max(2 * seg, 4));
   nslots = min(nslots, 12);
   p.nslots = nslots;
-  c.smem = fixed + (size_t)nslots * p.slot_bytes;
+  c.smem = fixed + (size_t)nslots * slot_stride;
   for (int s = 0; s < nsrc; ++s) {
     int cpl = srcs[s].buf.chunks;
     for (int i = 0; i < seg; ++i) if (p.segs[i].map == s) cpl = p.segs[i].cpl;
@@ -686,7 +731,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c.grid = min(p.total_tiles, sms * c.ctas_per_sm);
+  tc_conv_set_batch(c, n_images);
   if (getenv("HV_TC_DUMP")) {
     fprintf(stderr, "tc_conv: n_pad %d k %d stride %d dil %d cout %d ctas/sm %d slots %d nseg %d s2d %d xp %d tiles %d :", c.n_pad, k, stride, dil,
             cout_real, c.ctas_per_sm, p.nslots, p.nseg, p.s2d_in, p.in_xp, p.total_tiles);
@@ -694,6 +739,15 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     fprintf(stderr, "\n");
   }
   return HV_OK;
+}
+
+void tc_conv_set_batch(TcConv& c, int n_images) {
+  c.p.total_tiles = c.p.tiles_per_image * n_images;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int rounds = c.p.pair ? (c.p.total_tiles + 1) / 2 : c.p.total_tiles;
+  c.grid = min(rounds, sms * c.ctas_per_sm);
 }
 
 void tc_conv_set_output_chunked(TcConv& c, const TcBuf& out, int chunk_off, int nchunks, bool up2, int act) {
@@ -828,7 +882,7 @@ static int tc_fixed_code(const TcConv& c) {
   else if (p.out_mode == TC_OUT_CHUNKED_S2D) out = 4;
   else if (p.out_mode == TC_OUT_CHUNKED) out = p.out_xp > 1 ? 5 : 1;
   else out = p.out_xp > 1 ? 6 : 2;
-  return out << 16 | issue;
+  return (p.pair ? 1 << 20 : 0) | out << 16 | issue;
 }
 static int tc_issue_code(const TcConv& c) {
   const TcParams& p = c.p;
@@ -871,18 +925,21 @@ static int tc_issue_code(const TcConv& c) {
   X(32, HV_ACT_ELU, 2 << 16 | tc_shape_code(1, 3, 3, 2)) \
   X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(2, 0, 0, 2)) \
   X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(2, 0, 0, 1)) \
-  X(16, HV_ACT_ELU, 4 << 16 | tc_shape_code(1, 5, 1, 1))
+  X(16, HV_ACT_ELU, 4 << 16 | tc_shape_code(1, 5, 1, 1)) \
+  X(32, HV_ACT_ELU, 1 << 20 | 4 << 16 | tc_shape_code(1, 5, 1, 2))
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {
   const int act = (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_ELU) ? HV_ACT_ELU : -1;
   const int fixed = tc_fixed_code(c);
-  if (getenv("HV_TC_DUMP")) fprintf(stderr, "tc_launch: X(%d, %s, %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : "-1",
-                                    fixed >> 16, (fixed >> 12) & 15, (fixed >> 8) & 15, (fixed >> 4) & 15, fixed & 15);
+  if (getenv("HV_TC_DUMP")) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : "-1",
+                                    fixed >> 20 & 1, fixed >> 16 & 15, (fixed >> 12) & 15, (fixed >> 8) & 15, (fixed >> 4) & 15, fixed & 15);
+  if (c.p.pair && !(fixed >> 20 & 1)) { set_error("tc_conv: a paired layer needs a specialised kernel instance"); return HV_ERR_UNSUPPORTED; }
 #define HV_TC_TRY(NP, A, F) \
   if (N_PAD == (NP) && act == (A) && fixed == (F)) return tc_launch_na<NP, A, (N_PAD == (NP) ? (F) : 0)>(c, st);
   HV_TC_FIXED_LIST(HV_TC_TRY)
 #undef HV_TC_TRY
+  if (c.p.pair) { set_error("tc_conv: no specialised kernel instance for paired layer code 0x%x (n_pad %d)", fixed, N_PAD); return HV_ERR_UNSUPPORTED; }
   if (act == HV_ACT_ELU) return tc_launch_na<N_PAD, HV_ACT_ELU>(c, st);
   return tc_launch_na<N_PAD, -1>(c, st);
 }

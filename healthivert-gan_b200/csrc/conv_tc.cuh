@@ -97,6 +97,7 @@ struct TcParams {
   int cp;         // accumulator columns per output pixel when in_xp > 1
   int out_xp;     // the output buffer is an x-phase buffer (aux outputs of the heads too)
   int map5d;      // tensor maps are 5-D (s2d / x-phase sources)
+  int pair;       // two consecutive tiles per producer / issuer / barrier round (thin layers: halves the single-thread handshakes)
   int tile_adv;   // valid output positions per 128-row MMA tile (128 - widest tap shift)
   int tiles_per_image, total_tiles;
   int in_pitch, in_border, q_first;
@@ -144,6 +145,8 @@ struct TcConv {
 // geometry + tensor maps + tables; allocates the packed-weight / bias buffers
 int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real,
                   int n_images);
+// batch of the next launches (<= the n_images of the setup): tile count and grid
+void tc_conv_set_batch(TcConv& c, int n_images);
 // w_eff_a: [cout_a][cin_total][k][k] fp32 effective weights (cin_total = sum real_channels);
 // w_eff_b (heads only): second filter bank stacked after the first along cout
 int tc_conv_pack_weights(TcConv& c, const float* w_eff_a, const float* bias_a, int cout_a, const float* w_eff_b,

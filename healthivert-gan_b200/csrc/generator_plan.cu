@@ -344,13 +344,7 @@ static int tc_plan_create(hv_generator* g) {
 }
 
 // batch-size dependent fields (the plan is sized for max_batch; a smaller batch runs fewer tiles)
-static void tc_set_batch(TcConv& c, int n) {
-  c.p.total_tiles = c.p.tiles_per_image * n;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  c.grid = c.p.total_tiles < sms * c.ctas_per_sm ? c.p.total_tiles : sms * c.ctas_per_sm;
-}
+static void tc_set_batch(TcConv& c, int n) { tc_conv_set_batch(c, n); }
 
 static int tc_plan_pack_weights(hv_generator* g, cudaStream_t st) {
   TcPlan* t = g->tc;
