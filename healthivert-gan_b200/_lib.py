@@ -79,6 +79,7 @@ SIGNATURES = {
     "hv_slice_id_counts": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "hv_slice_prepare": (c_int, [c_void_p] * 5 + [c_int, c_int, c_int, c_int] + [c_void_p] * 10 + [c_void_p]),
     "hv_slice_finish": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int] + [c_void_p] * 4 + [c_void_p]),
+    "hv_resample_curve": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, ctypes.c_double, c_void_p, c_void_p]),
     "hv_generator_num_layers": (c_int, []),
     "hv_generator_layer_info": (c_int, [c_int, c_char_p] + [POINTER(c_int)] * 7),
     "hv_generator_create": (c_int, [POINTER(c_void_p), c_int, c_int]),

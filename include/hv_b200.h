@@ -275,6 +275,16 @@ int hv_slice_finish(const float* fake_ct, const float* fine_seg, const int32_t* 
                     const int32_t* slice_idx, const int32_t* vert_ids, const uint8_t* label_in, int nb, int h, int w,
                     float* ct_out, float* label_out, uint8_t* ct_u8_next, uint8_t* label_next, hv_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Spine straightening resampler: straighten/straighten/curve.py:54-101 (Interpolator.get_grid +
+ * interpolate_along = scipy.ndimage.map_coordinates(array, grid, order, cval), mode 'constant') as one gather kernel.
+ * vol: float64 [d0][d1][d2] (C order); knots: float64 [npts][3]; basis: float64 [npts][3][3] (basis[n][i][j] = component i of
+ * local basis vector j, vector 0 = tangent); out: float64 [npts][s1][s0], out[n][a][b] = sample at
+ * knots[n] + basis[n][:,1] * (b - s0/2) + basis[n][:,2] * (a - s1/2); order 0 = nearest (label maps), 1 = trilinear (CT);
+ * samples with a coordinate outside [0, extent-1] get cval.                                                            */
+int hv_resample_curve(const double* vol, int d0, int d1, int d2, const double* knots, const double* basis, int npts, int s0,
+                      int s1, int order, double cval, double* out, hv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -165,3 +165,47 @@ def test_file_level_driver_matches_array_driver(gen, tmp_path):
     assert np.array_equal(got_ct.get_fdata(), want_ct.astype(np.float64))
     assert np.array_equal(got_seg.get_fdata(), want_seg.astype(np.float64))
     assert got_seg.get_fdata().any()
+
+
+def test_straightening_against_reference_golden(golden_dir):
+    """hv_resample_curve + straighten.straighten_case on the raw case the reference ships (multi-label mask + centroids, synthetic
+    smooth CT) == the UNMODIFIED reference (vendored `straighten` package + straighten_mask_3d.py helpers, scipy map_coordinates):
+    label maps bit-exact (SHA-256 of the straightened volume, before and after the posterior-element removal, and of the vertebra
+    crop), trilinear CT within 1e-9."""
+    import hashlib
+    import json
+    from healthivert_gan_b200 import nifti, straighten as st
+    g = np.load(os.path.join(golden_dir, "straighten_0007.npz"))
+    label = nifti.load(os.path.join(golden_dir, "raw_0007_msk.nii.gz")).get_fdata()
+    entries = json.load(open(os.path.join(golden_dir, "raw_0007.json")))
+    x, y, z = np.meshgrid(*(np.arange(s, dtype=np.float64) for s in label.shape), indexing="ij")
+    ct = 500.0 * np.sin(x / 17.0) + 400.0 * np.cos(y / 23.0) + 2.5 * z - 150.0
+    coords = [[e["X"], e["Y"], e["Z"]] for e in entries if isinstance(e, dict) and "X" in e]
+    inter = st.Interpolator(st.extend_curve(np.array(coords), 20, (0, 0, 0), label.shape), step=1, get_local_basis=st.get_local_basis)
+    raw = inter.interpolate_along(label, (128, 128), order=0)
+    assert raw.shape == tuple(g["ct_shape"]) and raw.dtype == np.float64
+    assert hashlib.sha256(raw.astype(np.uint8).tobytes()).hexdigest() == str(g["label_sha_before_split"])
+    vids = [int(v) for v in g["vert_ids"]]
+    sct, slab, crops = st.straighten_case(ct, label, entries, vids, outputsize=(128, 128, 128))
+    assert hashlib.sha256(slab.astype(np.uint8).tobytes()).hexdigest() == str(g["label_sha"])
+    assert [int((slab == i).sum()) for i in range(17, 25)] == [int(v) for v in g["label_counts"]]
+    assert np.array_equal(slab.reshape(-1)[g["probe"]], g["label_probe"])
+    np.testing.assert_allclose(sct.reshape(-1)[g["probe"]], g["ct_probe"], rtol=0, atol=1e-9)
+    assert abs(sct.mean() - float(g["ct_mean"])) <= 1e-10
+    assert sorted(crops) == vids
+    for vid, want in zip(vids, g["centroids"]):
+        np.testing.assert_allclose(crops[vid][2], want, rtol=0, atol=1e-8)
+    crop_ct, crop_lab, _ = crops[20]
+    assert crop_ct.shape == (128, 128, 128)
+    assert hashlib.sha256(crop_lab.astype(np.uint8).tobytes()).hexdigest() == str(g["crop_label_sha"])
+    np.testing.assert_allclose(crop_ct.reshape(-1)[g["probe"] % crop_ct.size], g["crop_ct_probe"], rtol=0, atol=1e-9)
+    # the kernel against its own host grid + a scalar restatement of map_coordinates' rules on a handful of samples
+    grid = inter.get_grid((128, 128))
+    win = st.window(ct, -300, 800)
+    for n, a, b in ((0, 0, 0), (100, 64, 64), (212, 127, 3), (57, 10, 120)):
+        c = grid[:, n, a, b]
+        inside = all(0 <= c[d] <= label.shape[d] - 1 for d in range(3))
+        want = label[tuple(int(np.floor(v + 0.5)) for v in c)] if inside else 0.0
+        assert raw[n, a, b] == want
+    with pytest.raises(_lib.HvError):
+        inter.interpolate_along(win, (128, 128), order=3)
