@@ -741,11 +741,19 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   return HV_OK;
 }
 
+static int sm_count() {   // of the current device; one process drives one GPU (one rank per GPU), so the first answer is cached
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
 void tc_conv_set_batch(TcConv& c, int n_images) {
   c.p.total_tiles = c.p.tiles_per_image * n_images;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int rounds = c.p.pair ? (c.p.total_tiles + 1) / 2 : c.p.total_tiles;
   c.grid = min(rounds, sms * c.ctas_per_sm);
 }
@@ -886,7 +894,8 @@ static int tc_fixed_code(const TcConv& c) {
 }
 static int tc_issue_code(const TcConv& c) {
   const TcParams& p = c.p;
-  if (getenv("HV_TC_NO_FIXED")) return 0;
+  static const bool no_fixed = getenv("HV_TC_NO_FIXED") != nullptr;
+  if (no_fixed) return 0;
   const TcSeg& s0 = p.segs[0];
   const int ks = s0.nchunks >> 1;
   if (p.s2d_in) return p.nseg == 1 ? tc_shape_code(2, 0, 0, ks) : 0;
@@ -932,7 +941,8 @@ template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {
   const int act = (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_ELU) ? HV_ACT_ELU : -1;
   const int fixed = tc_fixed_code(c);
-  if (getenv("HV_TC_DUMP")) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : "-1",
+  static const bool dump = getenv("HV_TC_DUMP") != nullptr;
+  if (dump) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : "-1",
                                     fixed >> 20 & 1, fixed >> 16 & 15, (fixed >> 12) & 15, (fixed >> 8) & 15, (fixed >> 4) & 15, fixed & 15);
   if (c.p.pair && !(fixed >> 20 & 1)) { set_error("tc_conv: a paired layer needs a specialised kernel instance"); return HV_ERR_UNSUPPORTED; }
 #define HV_TC_TRY(NP, A, F) \

@@ -372,7 +372,7 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     tc_set_batch(c, n);
     return tc_conv_launch(c, s);
   };
-  const bool use_aux = getenv("HV_NO_AUX_STREAM") == nullptr;
+  static const bool use_aux = getenv("HV_NO_AUX_STREAM") == nullptr;
   cudaStream_t ax = use_aux ? g->aux : st;
   auto fork_aux = [&](int ev) -> int {   // aux continues after everything enqueued on st so far
     if (!use_aux) return HV_OK;

@@ -402,6 +402,8 @@ class Generator(nn.Module):
         self._plan = None
         self._plan_key = None
         self._param_sig = None
+        self._sig_slots = None
+        self.static_weights = False   # True: skip the per-forward weight-change check (weights frozen after the first forward)
         self.last_offsets = None
         self._last_out = None
 
@@ -414,6 +416,11 @@ class Generator(nn.Module):
             check(L.hv_generator_layer_info(i, name, None, None, None, None, None, None, None))
             net, layer = name.value.decode().split(".")
             out.append(getattr(getattr(self, net), layer).conv)
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)   # .cuda() / .to() / .float(): storages may have been swapped under the same tensors
+        self._param_sig = None
         return out
 
     def _destroy_plan(self):
@@ -442,13 +449,23 @@ class Generator(nn.Module):
             check(L.hv_generator_create(_lib.ctypes.byref(handle), cap, _lib.HV_PREC[self.precision]))
             self._plan = handle
             self._plan_key = key + (cap,)
-        convs = self._layers()
-        fcs = (self.coarse_generator.fc_height, self.fine_generator.fc_height)
-        sig = tuple((c.weight_orig.data_ptr(), c.weight_orig._version, c.bias.data_ptr(), c.bias._version,
-                     c.weight_u.data_ptr(), c.weight_u._version, c.weight_v.data_ptr(), c.weight_v._version)
-                    for c in convs) + tuple((f.weight.data_ptr(), f.weight._version, f.bias.data_ptr(),
-                                             f.bias._version) for f in fcs)
         training = self.training
+        if self.static_weights and self._param_sig is not None and not training:
+            return self._plan          # the caller vouches that the weights do not change between forwards (eval loops)
+        # Weight signature: identity + version counter of the 192 tensors, read through the modules' own dicts (Module.__getattr__
+        # and data_ptr() made this check cost as much host time as the 59 kernel launches of the forward).  In-place updates
+        # (optimizer steps, load_state_dict) bump the version; .cuda() / .to() go through _apply, which drops the signature.
+        if self._sig_slots is None:
+            convs = self._layers()
+            fcs = (self.coarse_generator.fc_height, self.fine_generator.fc_height)
+            slots = []
+            for c in convs:
+                slots += [(c._parameters, "weight_orig"), (c._parameters, "bias"), (c._buffers, "weight_u"), (c._buffers, "weight_v")]
+            for f in fcs:
+                slots += [(f._parameters, "weight"), (f._parameters, "bias")]
+            self._sig_slots = (convs, fcs, slots)
+        convs, fcs, slots = self._sig_slots
+        sig = [(id(t), t._version) for t in [d[k] for d, k in slots]]
         if sig != self._param_sig or training:
             for i, c in enumerate(convs):
                 for t in (c.weight_orig, c.bias, c.weight_u, c.weight_v):
