@@ -575,7 +575,7 @@ static int max_chunks_of(const TcSource* srcs, int nsrc) {
 
 static int tc_issue_code(const TcConv& c);
 
-int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images) {
+int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images, bool allow_pair) {
   HV_CHECK_ARG(nsrc >= 1 && nsrc <= 2, "tc_conv: 1 or 2 sources supported");
   HV_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || (stride == 2 && k == 3 && dil == 1)), "tc_conv: unsupported k/stride");
   memset(&c.p, 0, sizeof(c.p));
@@ -636,7 +636,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     const long long est_tiles = ((long long)b0.sub_h() * pitch / (TC_TILE_M - 2) + 1) * n_images;
     const size_t half = (227 * 1024) / 2 - 2048, band = (size_t)TC_TILE_M * max_chunks_of(srcs, nsrc) * 16u * (stride == 2 ? 8 : k * xp);
     const bool two_ctas = tc_ctas_per_sm(c.n_pad) == 2 && fixed + 3 * band <= half;
-    want_pair = !(e && atoi(e) == 0) && c.n_pad <= 32 && xp == 1 && !two_ctas && est_tiles >= 12ll * 148 && fixed + 2 * 2 * band <= budget;
+    want_pair = allow_pair && !(e && atoi(e) == 0) && c.n_pad <= 32 && xp == 1 && !two_ctas && est_tiles >= 12ll * 148 && fixed + 2 * 2 * band <= budget;
   }
   if (!want_pair)
   {  // two co-resident CTAs when the layer is thin and three tile slots still fit in half the shared memory (measured: with

@@ -143,8 +143,10 @@ struct TcConv {
 };
 
 // geometry + tensor maps + tables; allocates the packed-weight / bias buffers
+// allow_pair: the caller has a tile-pair kernel instance for this layer (the generator plan does for its layers; a stand-alone
+// conv of arbitrary geometry does not and runs the generic instance)
 int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real,
-                  int n_images);
+                  int n_images, bool allow_pair = false);
 // batch of the next launches (<= the n_images of the setup): tile count and grid
 void tc_conv_set_batch(TcConv& c, int n_images);
 // w_eff_a: [cout_a][cin_total][k][k] fp32 effective weights (cin_total = sum real_channels);

@@ -329,7 +329,7 @@ static int tc_plan_create(hv_generator* g) {
     const bool heads = s.out < 0;
     TcConv& c = t->conv[s.layer];
     const int cout = heads ? 2 : (s.layer == F1 ? kLayers[F1].cout + kLayers[PM1].cout : L.cout);
-    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, cout, n);
+    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, cout, n, /*allow_pair=*/true);
     if (rc) return rc;
     t->has[s.layer] = true;
     if (heads) {
