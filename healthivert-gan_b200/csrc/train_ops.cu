@@ -133,17 +133,52 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
   }
 }
 
-// per-channel sum over (n, hw): db[c] = sum dy[n][c][:]  (bias gradient, BatchNorm sums)
-__global__ void __launch_bounds__(256) channel_sum_kernel(const float* __restrict__ x, float* __restrict__ out, int n, int c, int hw) {
+// per-channel sum over (n, hw): db[c] = sum dy[n][c][:]  (bias gradient, BatchNorm sums).  Two deterministic passes: block
+// (split, channel) sums one slice of the channel's n * hw elements, then one thread per channel adds the slices in a fixed order
+// (a single block per channel left a 1-filter head layer reading 4 MB through one CTA: 578 us per call, 10 % of a training step).
+constexpr int kSumSlice = 8192;   // elements per block
+__global__ void __launch_bounds__(256) channel_sum_partial_kernel(const float* __restrict__ x, float* __restrict__ partial, int n, int c, int hw) {
   __shared__ float red[32];
-  const int ch = blockIdx.x;
+  const int ch = blockIdx.y, split = blockIdx.x;
+  const long long total = (long long)n * hw, lo = (long long)split * kSumSlice, hi = min(total, lo + kSumSlice);
   float s = 0.f;
-  for (int i = 0; i < n; ++i) {
-    const float* pl = x + ((size_t)i * c + ch) * hw;
-    for (int j = threadIdx.x; j < hw; j += blockDim.x) s += pl[j];
+  long long e = lo + threadIdx.x;
+  long long i = e / hw;
+  int j = (int)(e - i * hw);
+  for (; e < hi; e += blockDim.x) {
+    s += x[((size_t)i * c + ch) * hw + j];
+    j += blockDim.x;
+    while (j >= hw) { j -= hw; ++i; }
   }
   s = block_sum(s, red);
-  if (threadIdx.x == 0) out[ch] = s;
+  if (threadIdx.x == 0) partial[(size_t)split * c + ch] = s;
+}
+__global__ void channel_sum_final_kernel(const float* __restrict__ partial, float* __restrict__ out, int splits, int c) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += partial[(size_t)k * c + ch];
+  out[ch] = s;
+}
+static int channel_sum_launch(const float* x, float* out, int n, int c, int hw, cudaStream_t st) {
+  const long long total = (long long)n * hw;
+  const int splits = (int)((total + kSumSlice - 1) / kSumSlice);
+  // scratch for the slice sums: one grow-only buffer per host thread (the training step drives one stream; stream order keeps
+  // successive calls from overlapping).  cudaMallocAsync per call cost more than the kernels (step 340 -> 448 ms).
+  static thread_local float* partial = nullptr;
+  static thread_local size_t capacity = 0;
+  const size_t need = (size_t)splits * c;
+  if (need > capacity) {
+    if (partial) { HV_CUDA(cudaStreamSynchronize(st)); HV_CUDA(cudaFree(partial)); partial = nullptr; capacity = 0; }
+    const size_t grow = need > (1u << 18) ? need : (1u << 18);
+    HV_CUDA(cudaMalloc((void**)&partial, sizeof(float) * grow));
+    capacity = grow;
+  }
+  channel_sum_partial_kernel<<<dim3(splits, c), 256, 0, st>>>(x, partial, n, c, hw);
+  HV_LAUNCH_CHECK();
+  channel_sum_final_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, out, splits, c);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
 }
 
 int conv2d_wgrad_fp32(const hv_conv_desc* d, const float* dy, float* dw, float* db, cudaStream_t st) {
@@ -175,8 +210,8 @@ int conv2d_wgrad_fp32(const hv_conv_desc* d, const float* dy, float* dw, float* 
   conv_wgrad_kernel<<<grid, 256, 0, st>>>(a);
   HV_LAUNCH_CHECK();
   if (db) {
-    channel_sum_kernel<<<d->cout, 256, 0, st>>>(dy, db, d->n, d->cout, a.Hout * a.Wout);
-    HV_LAUNCH_CHECK();
+    int rc = channel_sum_launch(dy, db, d->n, d->cout, a.Hout * a.Wout, st);
+    if (rc) return rc;
   }
   return HV_OK;
 }
