@@ -28,11 +28,13 @@ struct ConvArgs {
 };
 
 constexpr int CONV_CI = 8;
-constexpr int CONV_TW = 64;
 
-template <int K, int S, int CPT, int WCO, int WPX>
+// CONV_TW = 64: a warp owns 2 rows x 64 columns; CONV_TW = 32: 4 rows x 32 columns (same 4 pixels per lane, same accumulation order,
+// so results are bit-identical): the PatchGAN layers are 30 .. 34 pixels wide and left half of every 64-wide tile empty
+template <int K, int S, int CPT, int WCO, int WPX, int CONV_TW = 64>
 __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
-  constexpr int TH = 2 * WPX;
+  constexpr int RPW = CONV_TW == 64 ? 2 : 4;   // output rows per warp
+  constexpr int TH = RPW * WPX;
   constexpr int TH_IN = (TH - 1) * S + 1;
   constexpr int COB = CPT * WCO;
   constexpr int KK = K * K;
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
       const float* w_c = s_w + c * KK * COB + warp_co * CPT;
 #pragma unroll
       for (int ky = 0; ky < K; ++ky) {
-        const float* row0 = in_c + (ky * p.rowstep + (warp_px * 2) * S) * p.pitch + lane * S;
+        const float* row0 = in_c + (ky * p.rowstep + (warp_px * RPW) * S) * p.pitch + lane * S;
         const float* row1 = row0 + S * p.pitch;
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
@@ -117,7 +119,9 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
 #pragma unroll
           for (int q = 0; q < CPT; ++q) wv[q] = w_c[(ky * K + kx) * COB + q];
           const int xo = kx * p.dil;
-          float v0 = row0[xo], v1 = row0[xo + 32 * S], v2 = row1[xo], v3 = row1[xo + 32 * S];
+          float v0, v1, v2, v3;
+          if (CONV_TW == 64) { v0 = row0[xo]; v1 = row0[xo + 32 * S]; v2 = row1[xo]; v3 = row1[xo + 32 * S]; }
+          else { v0 = row0[xo]; v1 = row1[xo]; v2 = row1[xo + S * p.pitch]; v3 = row1[xo + 2 * S * p.pitch]; }
 #pragma unroll
           for (int q = 0; q < CPT; ++q) {
             acc[0][q] = fmaf(v0, wv[q], acc[0][q]);
@@ -138,7 +142,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
     const float b = p.bias ? __ldg(p.bias + co) : 0.f;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int oy = oy0 + warp_px * 2 + (j >> 1), ox = ox0 + lane + 32 * (j & 1);
+      const int oy = oy0 + warp_px * RPW + (CONV_TW == 64 ? (j >> 1) : j), ox = ox0 + lane + (CONV_TW == 64 ? 32 * (j & 1) : 0);
       if (oy >= p.Hout || ox >= p.Wout) continue;
       float v = acc[j][q] + b;
       if (p.act == HV_ACT_HEADS) {
@@ -151,9 +155,9 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
   }
 }
 
-template <int K, int S, int CPT, int WCO, int WPX>
+template <int K, int S, int CPT, int WCO, int WPX, int CONV_TW = 64>
 static int launch_cfg(ConvArgs& a, cudaStream_t st) {
-  constexpr int TH = 2 * WPX, TH_IN = (TH - 1) * S + 1, COB = CPT * WCO;
+  constexpr int TH = (CONV_TW == 64 ? 2 : 4) * WPX, TH_IN = (TH - 1) * S + 1, COB = CPT * WCO;
   const int contiguous_rows = TH_IN + (K - 1) * a.dil, compact_rows = K * TH_IN;
   a.compact = contiguous_rows > compact_rows;
   a.nrows = a.compact ? compact_rows : contiguous_rows;
@@ -165,7 +169,7 @@ static int launch_cfg(ConvArgs& a, cudaStream_t st) {
     set_error("conv2d_fwd: tile needs %zu bytes of shared memory (k=%d dil=%d)", smem, K, a.dil);
     return HV_ERR_UNSUPPORTED;
   }
-  auto kern = conv_fp32_kernel<K, S, CPT, WCO, WPX>;
+  auto kern = conv_fp32_kernel<K, S, CPT, WCO, WPX, CONV_TW>;
   if (smem > 48 * 1024) HV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(((a.Wout + CONV_TW - 1) / CONV_TW) * ((a.Hout + TH - 1) / TH), (a.Cout + COB - 1) / COB, a.N);
   kern<<<grid, 256, smem, st>>>(a);
@@ -179,6 +183,7 @@ static int launch_ks(ConvArgs& a, cudaStream_t st) {
   if (a.Cout <= 8) return launch_cfg<K, S, 8, 1, 8>(a, st);
   if (a.Cout <= 16) return launch_cfg<K, S, 8, 2, 4>(a, st);
   if (a.Cout <= 32) return launch_cfg<K, S, 8, 4, 2>(a, st);
+  if (K == 4 && a.Wout <= 40) return launch_cfg<K, S, 8, 8, 1, 32>(a, st);   // PatchGAN layers: 30 .. 34 pixels wide
   return launch_cfg<K, S, 8, 8, 1>(a, st);
 }
 
