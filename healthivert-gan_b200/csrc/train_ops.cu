@@ -68,8 +68,9 @@ __device__ __forceinline__ float wg_load(const WgradArgs& p, int n, int ch, int 
 }
 
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
-  __shared__ float s_a[32][65];  // [pos][co]
-  __shared__ float s_b[32][65];  // [pos][col]
+  // tiles of 32 positions: [pos][co] and [pos][col]; rows of 68 floats keep every 4-float group 16-byte aligned (LDS.128)
+  __shared__ __align__(16) float s_a[32][68];
+  __shared__ __align__(16) float s_b[32][68];
   const int kk = p.k * p.k, ncols = p.Cin * kk;
   const int col0 = blockIdx.x * 64, co0 = blockIdx.y * 64;
   const int hw = p.Hout * p.Wout;
@@ -83,43 +84,57 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
+  // Every thread stages position pp = tid % 32 of the tile for rows / columns (tid / 32) + 8 e, e = 0 .. 7: the (ci, ky, kx) of its
+  // eight im2col columns never change, and its position advances by 32 per tile, so (n, oy, ox) are carried incrementally -
+  // no integer division in the loop (the gather used to cost more than the FMAs).
+  const int pp = tid & 31, lane_row = tid >> 5;
+  int cci[8], cky[8], ckx[8];
+  bool cok[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int c = col0 + lane_row + 8 * e;
+    cok[e] = c < ncols;
+    const int ci = cok[e] ? c / kk : 0, t = cok[e] ? c - ci * kk : 0;
+    cci[e] = ci; cky[e] = (t / p.k) * p.dil - p.pad; ckx[e] = (t % p.k) * p.dil - p.pad;
+  }
+  long long pos = p_begin + pp;
+  int n = (int)(pos / hw), r = (int)(pos - (long long)n * hw);
+  int oy = r / p.Wout, ox = r - oy * p.Wout;
+
   for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+    const bool live = pos < p_end;
     // dy tile: 64 co x 32 positions (positions contiguous inside a (n, co) plane)
-    for (int i = tid; i < 64 * 32; i += 256) {
-      const int pp = i & 31, co = i >> 5;
-      const long long pos = p0 + pp;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int co = lane_row + 8 * e;
       float v = 0.f;
-      if (pos < p_end && co0 + co < p.Cout) {
-        const int n = (int)(pos / hw), r = (int)(pos - (long long)n * hw);
-        v = __ldg(p.dy + ((size_t)n * p.Cout + co0 + co) * hw + r);
-      }
+      if (live && co0 + co < p.Cout) v = __ldg(p.dy + ((size_t)n * p.Cout + co0 + co) * hw + r);
       s_a[pp][co] = v;
     }
     // im2col tile: 64 (ci, tap) x 32 positions
-    for (int i = tid; i < 64 * 32; i += 256) {
-      const int pp = i & 31, c = i >> 5;
-      const long long pos = p0 + pp;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
       float v = 0.f;
-      if (pos < p_end && col0 + c < ncols) {
-        const int n = (int)(pos / hw), r = (int)(pos - (long long)n * hw);
-        const int oy = r / p.Wout, ox = r - oy * p.Wout;
-        const int ci = (col0 + c) / kk, t = (col0 + c) - ci * kk, ky = t / p.k, kx = t - ky * p.k;
-        v = wg_load(p, n, ci, oy * p.stride + ky * p.dil - p.pad, ox * p.stride + kx * p.dil - p.pad);
-      }
-      s_b[pp][c] = v;
+      if (live && cok[e]) v = wg_load(p, n, cci[e], oy * p.stride + cky[e], ox * p.stride + ckx[e]);
+      s_b[pp][lane_row + 8 * e] = v;
     }
     __syncthreads();
 #pragma unroll 8
-    for (int pp = 0; pp < 32; ++pp) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = s_a[pp][ty * 4 + i]; b[i] = s_b[pp][tx * 4 + i]; }
+    for (int q = 0; q < 32; ++q) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&s_a[q][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&s_b[q][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
+    // next tile: the same lane, 32 positions further
+    pos += 32; r += 32; ox += 32;
+    while (r >= hw) { r -= hw; ++n; }
+    if (ox >= p.Wout) { const int rows = ox / p.Wout; ox -= rows * p.Wout; oy += rows; }   // rare: once per output row
+    while (oy >= p.Hout) oy -= p.Hout;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
