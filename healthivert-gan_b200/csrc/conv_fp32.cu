@@ -38,7 +38,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
   constexpr int TH_IN = (TH - 1) * S + 1;
   constexpr int COB = CPT * WCO;
   constexpr int KK = K * K;
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   float* s_in = smem;                                  // [CI][nrows][pitch]
   float* s_w = smem + CONV_CI * p.nrows * p.pitch;     // [CI][KK][COB]
 
@@ -116,8 +116,16 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
 #pragma unroll
         for (int kx = 0; kx < K; ++kx) {
           float wv[CPT];
+          if (CPT % 4 == 0) {   // the CPT weights of a tap are contiguous and 16-byte aligned: LDS.128 broadcasts
 #pragma unroll
-          for (int q = 0; q < CPT; ++q) wv[q] = w_c[(ky * K + kx) * COB + q];
+            for (int q = 0; q < CPT; q += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(w_c + (ky * K + kx) * COB + q);
+              wv[q] = w4.x; wv[q + 1] = w4.y; wv[q + 2] = w4.z; wv[q + 3] = w4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < CPT; ++q) wv[q] = w_c[(ky * K + kx) * COB + q];
+          }
           const int xo = kx * p.dil;
           float v0, v1, v2, v3;
           if (CONV_TW == 64) { v0 = row0[xo]; v1 = row0[xo + 32 * S]; v2 = row1[xo]; v3 = row1[xo + 32 * S]; }
