@@ -25,6 +25,9 @@ struct ConvArgs {
   float* y2;
   int N, Cin, Cout, Hin, Win, Hout, Wout, pad, dil, act;
   int nrows, rowstep, compact, twin, pitch;
+  // sub-pixel outputs (data gradient of stride-2 convs): column padding of its own, output written at (oy * os + ooy, ox * os + oox)
+  // of a yH x yW plane.  Plain convs: pad_x = pad, os = 1, offsets 0, yH x yW = Hout x Wout.
+  int pad_x, os, ooy, oox, yH, yW;
 };
 
 constexpr int CONV_CI = 8;
@@ -49,7 +52,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
   const int oy0 = (blockIdx.x / tiles_x) * TH;
   const int co0 = blockIdx.y * COB;
   const int n = blockIdx.z;
-  const int gy0 = oy0 * S - p.pad, gx0 = ox0 * S - p.pad;
+  const int gy0 = oy0 * S - p.pad, gx0 = ox0 * S - p.pad_x;
 
   float acc[4][CPT];
 #pragma unroll
@@ -157,7 +160,7 @@ __global__ void __launch_bounds__(256) conv_fp32_kernel(const ConvArgs p) {
         if (co == 0) p.y[((size_t)n * p.Hout + oy) * p.Wout + ox] = act_apply(v, HV_ACT_CLAMP1);
         else p.y2[((size_t)n * p.Hout + oy) * p.Wout + ox] = act_apply(v, HV_ACT_SIGMOID);
       } else {
-        p.y[(((size_t)n * p.Cout + co) * p.Hout + oy) * p.Wout + ox] = act_apply(v, p.act);
+        p.y[(((size_t)n * p.Cout + co) * p.yH + oy * p.os + p.ooy) * p.yW + ox * p.os + p.oox] = act_apply(v, p.act);
       }
     }
   }
@@ -191,7 +194,7 @@ static int launch_ks(ConvArgs& a, cudaStream_t st) {
   if (a.Cout <= 8) return launch_cfg<K, S, 8, 1, 8>(a, st);
   if (a.Cout <= 16) return launch_cfg<K, S, 8, 2, 4>(a, st);
   if (a.Cout <= 32) return launch_cfg<K, S, 8, 4, 2>(a, st);
-  if (K == 4 && a.Wout <= 40) return launch_cfg<K, S, 8, 8, 1, 32>(a, st);   // PatchGAN layers: 30 .. 34 pixels wide
+  if ((K == 4 || K == 2) && a.Wout <= 40) return launch_cfg<K, S, 8, 8, 1, 32>(a, st);   // PatchGAN layers: 30 .. 34 pixels wide
   return launch_cfg<K, S, 8, 8, 1>(a, st);
 }
 
@@ -200,9 +203,15 @@ int conv2d_fwd_fp32(const hv_conv_desc* d, const float* w, const float* bias, fl
   return conv2d_fwd_fp32_ex(d, w, bias, y, y2, 0, 0, st);
 }
 
-// hout/wout > 0 override the output extent (reads beyond the virtual input are zero): used by the data gradient
 int conv2d_fwd_fp32_ex(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
                        cudaStream_t st) {
+  return conv2d_fwd_fp32_sub(d, w, bias, y, y2, hout, wout, nullptr, st);
+}
+
+// hout/wout > 0 override the output extent (reads beyond the virtual input are zero): used by the data gradient; sub != null:
+// sub-pixel output (separate row / column padding, strided output positions)
+int conv2d_fwd_fp32_sub(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
+                        const ConvSubpixel* sub, cudaStream_t st) {
   HV_CHECK_ARG(d && w && y, "conv2d_fwd: null argument");
   HV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= 4, "conv2d_fwd: nsrc=%d out of range", d->nsrc);
   int csum = 0;
@@ -229,8 +238,14 @@ int conv2d_fwd_fp32_ex(const hv_conv_desc* d, const float* w, const float* bias,
   if (wout > 0) a.Wout = wout;
   HV_CHECK_ARG(a.Hout > 0 && a.Wout > 0, "conv2d_fwd: empty output");
   a.pad = d->pad; a.dil = d->dil; a.act = d->act;
+  a.pad_x = d->pad; a.os = 1; a.ooy = a.oox = 0; a.yH = a.Hout; a.yW = a.Wout;
+  if (sub) {
+    HV_CHECK_ARG(d->act != HV_ACT_HEADS && sub->os >= 1, "conv2d_fwd: bad sub-pixel output description");
+    a.pad = sub->pad_y; a.pad_x = sub->pad_x; a.os = sub->os; a.ooy = sub->ooy; a.oox = sub->oox; a.yH = sub->yH; a.yW = sub->yW;
+  }
   const int key = d->k * 10 + d->stride;
   switch (key) {
+    case 21: return launch_ks<2, 1>(a, st);
     case 31: return launch_ks<3, 1>(a, st);
     case 32: return launch_ks<3, 2>(a, st);
     case 51: return launch_ks<5, 1>(a, st);

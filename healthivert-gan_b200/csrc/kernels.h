@@ -23,6 +23,10 @@ int conv2d_fwd_fp32(const hv_conv_desc* d, const float* w, const float* bias, fl
                     cudaStream_t st);
 int conv2d_fwd_fp32_ex(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
                        cudaStream_t st);
+// sub-pixel output of conv2d_fwd_fp32_sub: row / column padding of their own, outputs at (oy * os + ooy, ox * os + oox) of a yH x yW plane
+struct ConvSubpixel { int pad_y, pad_x, os, ooy, oox, yH, yW; };
+int conv2d_fwd_fp32_sub(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int hout, int wout,
+                        const ConvSubpixel* sub, cudaStream_t st);
 // internal source mode: [N,ch,H/2,W/2] read through zero insertion (value at even (y,x) only) - stride-2 data gradient
 #define HV_SRC_ZEROINS2 4
 

@@ -17,6 +17,17 @@ __global__ void flip_weights_kernel(const float* __restrict__ w, float* __restri
   wt[((size_t)ci * cout + co) * kk + (kk - 1 - t)] = w[i];
 }
 
+// Sub-pixel weights for the data gradient of a 4x4 stride-2 pad-1 conv: output parity class (py, px) only meets the flipped taps
+// a = py + 2 t, b = px + 2 s (the other taps fall on the inserted zeros), i.e. a 2x2 conv over dy itself:
+//   ws[(py, px)][ci][co][t][s] = w[co][ci][3 - py - 2 t][3 - px - 2 s]
+__global__ void subpixel_weights_kernel(const float* __restrict__ w, float* __restrict__ ws, int cout, int cin) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * 16) return;
+  const int s = i & 1, t = (i >> 1) & 1, rest = i >> 2;
+  const int co = rest % cout, ci = (rest / cout) % cin, cls = rest / (cout * cin), py = cls >> 1, px = cls & 1;
+  ws[i] = w[((size_t)co * cin + ci) * 16 + (3 - py - 2 * t) * 4 + (3 - px - 2 * s)];
+}
+
 // dx over the VIRTUAL input extent [n, cin, hin, win] of the forward conv described by d (sources concatenated; the caller
 // routes channel ranges back to their tensors, see upsample2_bwd for HV_SRC_UP2 sources).  workspace: cin*cout*k*k floats.
 int conv2d_dgrad_fp32(const hv_conv_desc* d, const float* w, const float* dy, float* dx, float* workspace, cudaStream_t st) {
@@ -27,6 +38,25 @@ int conv2d_dgrad_fp32(const hv_conv_desc* d, const float* w, const float* dy, fl
   const int hout = (d->hin + 2 * d->pad - eff) / d->stride + 1, wout = (d->win + 2 * d->pad - eff) / d->stride + 1;
   HV_CHECK_ARG(d->stride == 1 || (2 * hout == d->hin && 2 * wout == d->win), "conv2d_dgrad: stride-2 conv must halve the extent");
   const int total = d->cout * d->cin * d->k * d->k;
+  if (d->stride == 2 && d->k == 4 && d->pad == 1) {
+    // four 2x2 convs over dy, one per output parity class, instead of a 4x4 conv over the zero-inserted dy: a quarter of the
+    // multiply-adds, the same non-zero terms in the same order (bit-identical results)
+    subpixel_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, workspace, d->cout, d->cin);
+    HV_LAUNCH_CHECK();
+    hv_conv_desc b;
+    b = *d;
+    b.cin = d->cout; b.cout = d->cin; b.k = 2; b.stride = 1; b.dil = 1; b.act = HV_ACT_NONE;
+    b.nsrc = 1; b.src[0].ptr = dy; b.src[0].channels = d->cout; b.src[0].mode = HV_SRC_DIRECT;
+    b.hin = hout; b.win = wout;
+    for (int cls = 0; cls < 4; ++cls) {
+      const int py = cls >> 1, px = cls & 1;
+      b.pad = 1 - py;
+      const ConvSubpixel sub{1 - py, 1 - px, 2, py, px, d->hin, d->win};
+      int rc = conv2d_fwd_fp32_sub(&b, workspace + (size_t)cls * d->cout * d->cin * 4, nullptr, dx, nullptr, d->hin / 2, d->win / 2, &sub, st);
+      if (rc) return rc;
+    }
+    return HV_OK;
+  }
   flip_weights_kernel<<<(total + 255) / 256, 256, 0, st>>>(w, workspace, d->cout, d->cin, d->k);
   HV_LAUNCH_CHECK();
   hv_conv_desc b;
