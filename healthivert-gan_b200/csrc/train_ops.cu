@@ -131,24 +131,30 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
   int n = (int)(pos / hw), r = (int)(pos - (long long)n * hw);
   int oy = r / p.Wout, ox = r - oy * p.Wout;
 
-  for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+  // software pipeline: the global loads of tile t + 1 are issued before the FMAs of tile t (registers ra / rb carry them over)
+  float ra[8], rb[8];
+  auto fetch = [&]() {
     const bool live = pos < p_end;
-    // dy tile: 64 co x 32 positions (positions contiguous inside a (n, co) plane)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
+    for (int e = 0; e < 8; ++e) {   // dy tile: 64 co x 32 positions (positions contiguous inside a (n, co) plane)
       const int co = lane_row + 8 * e;
-      float v = 0.f;
-      if (live && co0 + co < p.Cout) v = __ldg(p.dy + ((size_t)n * p.Cout + co0 + co) * hw + r);
-      s_a[pp][co] = v;
+      ra[e] = (live && co0 + co < p.Cout) ? __ldg(p.dy + ((size_t)n * p.Cout + co0 + co) * hw + r) : 0.f;
     }
-    // im2col tile: 64 (ci, tap) x 32 positions
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float v = 0.f;
-      if (live && cok[e]) v = wg_load(p, n, cci[e], oy * p.stride + cky[e], ox * p.stride + ckx[e]);
-      s_b[pp][lane_row + 8 * e] = v;
-    }
+    for (int e = 0; e < 8; ++e)     // im2col tile: 64 (ci, tap) x 32 positions
+      rb[e] = (live && cok[e]) ? wg_load(p, n, cci[e], oy * p.stride + cky[e], ox * p.stride + ckx[e]) : 0.f;
+  };
+  fetch();
+  for (long long p0 = p_begin; p0 < p_end; p0 += 32) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { s_a[pp][lane_row + 8 * e] = ra[e]; s_b[pp][lane_row + 8 * e] = rb[e]; }
     __syncthreads();
+    // next tile: the same lane, 32 positions further
+    pos += 32; r += 32; ox += 32;
+    while (r >= hw) { r -= hw; ++n; }
+    if (ox >= p.Wout) { const int rows = ox / p.Wout; ox -= rows * p.Wout; oy += rows; }   // rare: once per output row
+    while (oy >= p.Hout) oy -= p.Hout;
+    if (p0 + 32 < p_end) fetch();
 #pragma unroll 8
     for (int q = 0; q < 32; ++q) {
       const float4 a4 = *reinterpret_cast<const float4*>(&s_a[q][ty * 4]);
@@ -160,11 +166,6 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs p) {
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
-    // next tile: the same lane, 32 positions further
-    pos += 32; r += 32; ox += 32;
-    while (r >= hw) { r -= hw; ++n; }
-    if (ox >= p.Wout) { const int rows = ox / p.Wout; ox -= rows * p.Wout; oy += rows; }   // rare: once per output row
-    while (oy >= p.Hout) oy -= p.Hout;
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
