@@ -189,3 +189,32 @@ def test_bf16_layer_taps_track_fp32_oracle(gen_bf16, synthetic_sd):
         scale = float(ref.abs().max())
         err = float((got - ref).abs().max())
         assert err <= 0.03 * scale + 1e-3, (name, err, scale)
+
+
+def test_plan_follows_weight_changes(synthetic_sd):
+    """The native plan caches sigma / packed weights behind a cheap weight signature (tensor identity + version counters, dropped by
+    Module._apply): in-place updates, load_state_dict and device round trips must all reach the kernels; `static_weights = True`
+    is the documented opt-out for frozen eval loops."""
+    x, mask, cam, ratio = synth.synthetic_slices(2, seed=5)
+    for precision in ("fp32", "bf16"):
+        g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+        g.load_state_dict(synthetic_sd)
+        g = g.cuda().eval()
+        g.precision = precision
+        base = _run(g, x, mask, cam, ratio)[3]
+        again = _run(g, x, mask, cam, ratio)[3]
+        assert torch.equal(base, again)
+        with torch.no_grad():
+            g.coarse_generator.conv1.conv.bias.add_(0.25)                 # in-place update (what an optimizer step does)
+        changed = _run(g, x, mask, cam, ratio)[3]
+        assert not torch.equal(base, changed)
+        g.load_state_dict(synthetic_sd)                                     # copy_ into the same tensors
+        assert torch.equal(_run(g, x, mask, cam, ratio)[3], base)
+        g = g.cpu().cuda()                                                  # storages swapped under the same Parameter objects
+        assert torch.equal(_run(g, x, mask, cam, ratio)[3], base)
+        g.static_weights = True                                             # opt-out: later changes are (by contract) not seen
+        with torch.no_grad():
+            g.coarse_generator.conv1.conv.bias.add_(0.25)
+        assert torch.equal(_run(g, x, mask, cam, ratio)[3], base)
+        g.static_weights = False
+        assert torch.equal(_run(g, x, mask, cam, ratio)[3], changed)
