@@ -926,7 +926,7 @@ static int tc_issue_code(const TcConv& c) {
   X(64, HV_ACT_ELU, 1 << 16 | tc_shape_code(4, 0, 0, 4)) \
   X(64, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
   X(64, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 1, 3, 4)) \
-  X(64, -1, 1 << 16 | tc_shape_code(1, 3, 3, 4)) \
+  X(64, HV_ACT_RELU, 1 << 16 | tc_shape_code(1, 3, 3, 4)) \
   X(32, HV_ACT_ELU, 6 << 16 | tc_shape_code(1, 3, 3, 2)) \
   X(32, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2)) \
   X(32, HV_ACT_ELU, 4 << 16 | tc_shape_code(1, 5, 1, 2)) \
@@ -939,10 +939,13 @@ static int tc_issue_code(const TcConv& c) {
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {
-  const int act = (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_ELU) ? HV_ACT_ELU : -1;
+  // activation as a compile-time constant where an instance exists (ELU everywhere, ReLU for pmconv6), else -1 = run-time switch
+  int act = -1;
+  if (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_ELU) act = HV_ACT_ELU;
   const int fixed = tc_fixed_code(c);
+  if (c.p.out_mode != TC_OUT_HEADS && c.p.act == HV_ACT_RELU && N_PAD == 64 && fixed == (1 << 16 | tc_shape_code(1, 3, 3, 4))) act = HV_ACT_RELU;
   static const bool dump = getenv("HV_TC_DUMP") != nullptr;
-  if (dump) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : "-1",
+  if (dump) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : (act == HV_ACT_RELU ? "HV_ACT_RELU" : "-1"),
                                     fixed >> 20 & 1, fixed >> 16 & 15, (fixed >> 12) & 15, (fixed >> 8) & 15, (fixed >> 4) & 15, fixed & 15);
   if (c.p.pair && !(fixed >> 20 & 1)) { set_error("tc_conv: a paired layer needs a specialised kernel instance"); return HV_ERR_UNSUPPORTED; }
 #define HV_TC_TRY(NP, A, F) \
