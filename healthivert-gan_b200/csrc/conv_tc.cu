@@ -149,7 +149,10 @@ __host__ __device__ constexpr int tc_ctas_per_sm(int n_pad) { return n_pad <= 32
 //   FIXED = kind << 12 | rows << 8 | taps << 4 | k-steps;  kind 1: plain segments of one shape, 2: space-to-depth (k-steps),
 //   3: x-phase (rows, k-steps), 4: two sources, segment 0 = (3 rows, 3 taps, k-steps), segment 1 = kx-packed plane (3, 1, 1)
 __host__ __device__ constexpr int tc_shape_code(int kind, int rows, int taps, int ksteps) { return kind << 12 | rows << 8 | taps << 4 | ksteps; }
-template <int N_PAD, int ACT, int FIXED = 0>
+// DIAG: the diagnostics (per-role clock trace, launch timeline stamps, HV_TC_DEBUG ablation bits) are compiled in only for the
+// instances that the host picks while a diagnostic is active: in the production instances they cost 2.4 % of the forward (the
+// single-thread loops pay for every extra instruction).
+template <int N_PAD, int ACT, int FIXED = 0, bool DIAG = true>
 __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv_tc_kernel(const __grid_constant__ TcParams p) {
   constexpr int ACC_STAGES = tc_acc_stages(N_PAD);       // accumulator tiles in flight
   constexpr int EPI_WARPS = tc_epi_warps(N_PAD);
@@ -183,13 +186,13 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nslots + 1 + 2 * ACC_STAGES);
   float* s_bias = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 512);
 
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA entry: wall clock (ns) and SM clock
+  if (DIAG && p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA entry: wall clock (ns) and SM clock
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.trace[12000 + 4 * blockIdx.x] = (long long)gt;
     p.trace[12000 + 4 * blockIdx.x + 2] = clock64();
   }
-  if (p.timeline && threadIdx.x == 0) {
+  if (DIAG && p.timeline && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     atomicMin(reinterpret_cast<unsigned long long*>(p.timeline), gt);
@@ -230,7 +233,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     asm volatile("griddepcontrol.wait;" ::: "memory");
     int slot = 0, ntr = 0;
     uint32_t phase = 0;
-    long long* tr = (p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    long long* tr = (DIAG && p.trace && blockIdx.x == 0) ? p.trace : nullptr;
+    const int debug = DIAG ? p.debug : 0;
     const unsigned long long tiles_magic = p.tiles_magic;
     const int tiles_per_image = p.tiles_per_image, tile_adv = p.tile_adv, q_first = p.q_first, total_tiles = p.total_tiles;
     const uint32_t slots_base = smem_u32(s_slots);
@@ -259,8 +263,8 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
         if (leader) {
           const uint32_t fb = bar_full + 8u * slot, dst = slots_base + (uint32_t)slot * slot_stride;
-          mbar_expect_tx(fb, (p.debug & 2) ? 0u : tx * TPR);
-          for (int i = 0; i < ((p.debug & 2) ? 0 : nload); ++i) {
+          mbar_expect_tx(fb, (debug & 2) ? 0u : tx * TPR);
+          for (int i = 0; i < ((debug & 2) ? 0 : nload); ++i) {
             if (map5d) tma_load_5d(dst + (uint32_t)i * load_bytes, &p.maps[0], fb, c_tile + rel2, c1, 0, i * cpl, img);   // {positions, rows, 4 sub-planes / phases, chunks, image}
             else tma_load_4d(dst + (uint32_t)i * load_bytes, map1 ? &p.maps[1] : &p.maps[0], fb, c_tile + rel2, c1, i * cpl, img);
             if (PAIR) {
@@ -276,7 +280,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   } else if (warp == W_MMA) {
     // ===================================================================== MMA issuer (warp-uniform, one lane issues)
     const bool leader = elect_one();
-    const bool mma_on = leader && !(p.debug & 1);
+    const bool mma_on = leader && !(DIAG && (p.debug & 1));
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = N_PAD, M = 128
     constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_PAD >> 3) << 17) | ((128u >> 4) << 24);
     // smem descriptor = hi word (SBO = 128 B, version 1) : lo word (start >> 4 | LBO >> 4 << 16); offsets add into lo.
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     const uint32_t a_lo_base = smem_u32(s_slots) >> 4;
     const uint32_t slot_units = p.slot_bytes >> 4;
     int slot = 0, acc = 0, ntr = 0;
-    long long* tr = (p.trace && blockIdx.x == 0) ? p.trace + 4000 : nullptr;
+    long long* tr = (DIAG && p.trace && blockIdx.x == 0) ? p.trace + 4000 : nullptr;
     uint32_t phase = 0, acc_phase = 0;
     // peek-ahead: the next barrier is probed BEFORE the current batch of MMAs is issued, so the probe latency
     // hides under the queued MMAs (the tensor pipe accepts only a few MMAs ahead of execution)
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
     const int group = warp / WPT;
     const int col0 = ((warp % WPT) >> 2) * NCOL;
     int ntr = 0;
-    long long* tr = (p.trace && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
+    long long* tr = (DIAG && p.trace && blockIdx.x == 0 && warp == 0 && lane == 0) ? p.trace + 8000 : nullptr;
     const unsigned long long tiles_magic = p.tiles_magic;
     const int m = quad * 32 + lane;
     const int total_tiles = p.total_tiles, rounds = (total_tiles + TPR - 1) / TPR;
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
       const int yy = qrow - p.in_border;
       const int xx = q - qrow * p.in_pitch - p.in_border;
       // rows >= tile_adv read past the band (their taps shift beyond position 127): garbage, skipped
-      const bool valid = m < p.tile_adv && yy >= 0 && yy < p.h_out && xx >= 0 && xx < p.w_out && !(p.debug & 4);
+      const bool valid = m < p.tile_adv && yy >= 0 && yy < p.h_out && xx >= 0 && xx < p.w_out && !(DIAG && (p.debug & 4));
       trace_ev(tr, ntr, 20);
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
@@ -489,13 +493,13 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   }
   tc_fence_before();
   __syncthreads();
-  if (p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA exit
+  if (DIAG && p.trace && threadIdx.x == 0 && blockIdx.x < 400) {   // CTA exit
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     p.trace[12000 + 4 * blockIdx.x + 1] = (long long)gt;
     p.trace[12000 + 4 * blockIdx.x + 3] = clock64();
   }
-  if (p.timeline && threadIdx.x == 0) {
+  if (DIAG && p.timeline && threadIdx.x == 0) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     atomicMax(reinterpret_cast<unsigned long long*>(p.timeline) + 1, gt);
@@ -852,11 +856,11 @@ static long long* g_timeline = nullptr;
 static int g_timeline_count = 0;
 void tc_set_timeline(long long* dev_buf) { g_timeline = dev_buf; g_timeline_count = 0; }
 
-template <int N_PAD, int ACT, int FIXED = 0>
+template <int N_PAD, int ACT, int FIXED = 0, bool DIAG = true>
 static int tc_launch_na(const TcConv& c, cudaStream_t st) {
   static bool configured = false;  // per instantiation; the attribute is sticky for the process
   if (!configured) {
-    HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD, ACT, FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    HV_CUDA(cudaFuncSetAttribute(conv_tc_kernel<N_PAD, ACT, FIXED, DIAG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   // programmatic dependent launch: the kernel may start while its predecessor in the stream drains; it prefetches its
@@ -874,7 +878,7 @@ static int tc_launch_na(const TcConv& c, cudaStream_t st) {
   TcParams q = c.p;
   q.trace = g_trace;
   q.timeline = g_timeline ? g_timeline + 4 * (g_timeline_count++) : nullptr;
-  HV_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<N_PAD, ACT, FIXED>, q));
+  HV_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<N_PAD, ACT, FIXED, DIAG>, q));
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
@@ -948,8 +952,12 @@ static int tc_launch_n(const TcConv& c, cudaStream_t st) {
   if (dump) fprintf(stderr, "tc_launch: X(%d, %s, %d << 20 | %d << 16 | tc_shape_code(%d, %d, %d, %d))\n", N_PAD, act == HV_ACT_ELU ? "HV_ACT_ELU" : (act == HV_ACT_RELU ? "HV_ACT_RELU" : "-1"),
                                     fixed >> 20 & 1, fixed >> 16 & 15, (fixed >> 12) & 15, (fixed >> 8) & 15, (fixed >> 4) & 15, fixed & 15);
   if (c.p.pair && !(fixed >> 20 & 1)) { set_error("tc_conv: a paired layer needs a specialised kernel instance"); return HV_ERR_UNSUPPORTED; }
-#define HV_TC_TRY(NP, A, F) \
-  if (N_PAD == (NP) && act == (A) && fixed == (F)) return tc_launch_na<NP, A, (N_PAD == (NP) ? (F) : 0)>(c, st);
+  // a diagnostic is active (trace / timeline hook set, or ablation bits from HV_TC_DEBUG): the instances that carry the hooks
+  const bool diag = g_trace != nullptr || g_timeline != nullptr || c.p.debug != 0;
+#define HV_TC_TRY(NP, A, F)                                                                                      \
+  if (N_PAD == (NP) && act == (A) && fixed == (F))                                                              \
+    return diag ? tc_launch_na<NP, A, (N_PAD == (NP) ? (F) : 0), true>(c, st)                                   \
+                : tc_launch_na<NP, A, (N_PAD == (NP) ? (F) : 0), (N_PAD == (NP) ? false : true)>(c, st);
   HV_TC_FIXED_LIST(HV_TC_TRY)
 #undef HV_TC_TRY
   if (c.p.pair) { set_error("tc_conv: no specialised kernel instance for paired layer code 0x%x (n_pad %d)", fixed, N_PAD); return HV_ERR_UNSUPPORTED; }

@@ -22,6 +22,11 @@ with torch.no_grad():
     buf[0::4] = 1 << 62
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     L.hv_debug_conv_timeline(buf.data_ptr())
+    g(x, mask, cam, ratio)           # first use of the instances that carry the diagnostics (lazy module load), not measured
+    torch.cuda.synchronize()
+    buf.zero_()
+    buf[0::4] = 1 << 62
+    L.hv_debug_conv_timeline(buf.data_ptr())
     e0.record()
     g(x, mask, cam, ratio)
     e1.record()
