@@ -1018,18 +1018,40 @@ __global__ void __launch_bounds__(256) pack_kx_kernel(PackKxArgs a, TcBuf dst) {
   __align__(16) __nv_bfloat16 o[NCH * 8];
 #pragma unroll
   for (int j = 0; j < NCH * 8; ++j) o[j] = __float2bfloat16(0.f);
+  // the kernel is issue-bound (ncu: 78 - 86 % of the issue slots): the source mode is decided once per source, not per tap, and
+  // positions whose K taps all lie inside the row skip the per-tap bounds checks
+  const int reach = (K / 2) * a.dil;
+  const bool interior = x >= reach && x + reach < w;
 #pragma unroll
   for (int c = 0; c < NSRC; ++c) {
     const float* src = a.ptr[c];
     const int mode = a.mode[c];
-    const float* row = mode == HV_SRC_SUB2 ? src + ((size_t)n * (2 * h) + 2 * y) * (2 * w) : src + ((size_t)n * h + y) * w;
-    const float scalar = mode == HV_SRC_SCALAR ? src[n] : 0.f;
+    if (mode == HV_SRC_SCALAR) {
+      const __nv_bfloat16 sv = __float2bfloat16(src[n]);
 #pragma unroll
-    for (int kx = 0; kx < K; ++kx) {
-      const int xs = x + (kx - K / 2) * a.dil;
-      float v = 0.f;
-      if (xs >= 0 && xs < w) v = mode == HV_SRC_SCALAR ? scalar : (mode == HV_SRC_SUB2 ? row[2 * xs] : row[xs]);
-      o[kx * NSRC + c] = __float2bfloat16(v);
+      for (int kx = 0; kx < K; ++kx) {
+        const int xs = x + (kx - K / 2) * a.dil;
+        o[kx * NSRC + c] = (interior || (xs >= 0 && xs < w)) ? sv : __float2bfloat16(0.f);
+      }
+    } else if (mode == HV_SRC_SUB2) {
+      const float* row = src + ((size_t)n * (2 * h) + 2 * y) * (2 * w);
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int xs = x + (kx - K / 2) * a.dil;
+        o[kx * NSRC + c] = __float2bfloat16((interior || (xs >= 0 && xs < w)) ? row[2 * xs] : 0.f);
+      }
+    } else {
+      const float* row = src + ((size_t)n * h + y) * w + x;
+      if (interior) {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) o[kx * NSRC + c] = __float2bfloat16(row[(kx - K / 2) * a.dil]);
+      } else {
+#pragma unroll
+        for (int kx = 0; kx < K; ++kx) {
+          const int d = (kx - K / 2) * a.dil, xs = x + d;
+          o[kx * NSRC + c] = __float2bfloat16((xs >= 0 && xs < w) ? row[d] : 0.f);
+        }
+      }
     }
   }
 #pragma unroll
