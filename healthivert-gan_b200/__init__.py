@@ -9,6 +9,7 @@ from .inpaint_networks import (Conv2dBlock, ContextualAttention, CoarseGenerator
 from .edge_operator import Sobel, edge_mse_loss  # noqa: F401
 from . import mask_ops  # noqa: F401
 from . import sharding  # noqa: F401
+from .pipeline import SlicePipeline  # noqa: F401
 
 __all__ = ["Generator", "CoarseGenerator", "FineGenerator", "ContextualAttention", "Conv2dBlock", "gen_conv",
-           "Sobel", "edge_mse_loss", "mask_ops", "sharding"]
+           "Sobel", "edge_mse_loss", "mask_ops", "sharding", "SlicePipeline"]

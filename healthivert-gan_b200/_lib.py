@@ -89,6 +89,14 @@ SIGNATURES = {
     "hv_generator_prepare": (c_int, [c_void_p, c_int, c_void_p]),
     "hv_generator_forward": (c_int, [c_void_p] + [c_void_p] * 4 + [c_int] + [c_void_p] * 8 + [c_int, c_void_p]),
     "hv_generator_run_layer": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "hv_generator_run_chain": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p]),
+    "hv_pipeline_create": (c_int, [POINTER(c_void_p), c_void_p, c_int, c_int, c_int, c_int]),
+    "hv_pipeline_destroy": (c_int, [c_void_p]),
+    "hv_pipeline_slot": (c_int, [c_void_p, c_int] + [POINTER(c_void_p)] * 8),
+    "hv_pipeline_bytes": (c_size_t, [c_void_p, c_int]),
+    "hv_pipeline_stream": (c_void_p, [c_void_p, c_int]),
+    "hv_pipeline_submit": (c_int, [c_void_p, c_int, c_int]),
+    "hv_pipeline_wait": (c_int, [c_void_p, c_int]),
     "hv_generator_read_tap": (c_longlong, [c_void_p, c_int, c_void_p, c_void_p]),
 }
 

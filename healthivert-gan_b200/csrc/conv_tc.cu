@@ -894,6 +894,7 @@ static int tc_launch_na(const TcConv& c, cudaStream_t st) {
 // compile-time issue shape of a layer, or 0 when its segments do not fit one of the specialised families
 static int tc_issue_code(const TcConv& c);
 static int tc_fixed_code(const TcConv& c) {
+  if (c.force_generic) return 0;
   const int issue = tc_issue_code(c);
   if (!issue) return 0;
   const TcParams& p = c.p;
@@ -1075,19 +1076,21 @@ int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& ds
   return HV_OK;
 }
 
-__global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst) {
-  const int n = blockIdx.z, c = blockIdx.y, h = src.h, w = src.w;
+// sub = 2 reads every second pixel of every second row: the native-resolution result of a layer whose output is stored
+// nearest-x2-upsampled (the producer's epilogue writes the 2 x 2 replicas)
+__global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst, int sub) {
+  const int n = blockIdx.z, c = blockIdx.y, h = src.h / sub, w = src.w / sub;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int y = i / w, x = i - y * w, ch = ch0 + c;
   dst[((size_t)n * channels + c) * h * w + i] =
-      __bfloat162float(src.ptr[src.chunk_base(n, ch >> 3) + src.pos(y, x) * 8 + (ch & 7)]);
+      __bfloat162float(src.ptr[src.chunk_base(n, ch >> 3) + src.pos(y * sub, x * sub) * 8 + (ch & 7)]);
 }
 
-int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st) {
-  HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8, "tc_unpack_nchw: bad argument");
-  dim3 grid((src.h * src.w + 255) / 256, channels, src.n);
-  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src, ch0, channels, dst);
+int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st, int sub) {
+  HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8 && (sub == 1 || sub == 2), "tc_unpack_nchw: bad argument");
+  dim3 grid((src.h / sub * (src.w / sub) + 255) / 256, channels, src.n);
+  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src, ch0, channels, dst, sub);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }

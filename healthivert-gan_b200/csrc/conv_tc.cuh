@@ -140,6 +140,7 @@ struct TcConv {
   int nsrc = 0;
   TcSource src[2];
   int cout_real = 0;
+  bool force_generic = false;   // run the FIXED = 0 kernel instance even when a specialised one matches (parity tests)
 };
 
 // geometry + tensor maps + tables; allocates the packed-weight / bias buffers
@@ -166,7 +167,7 @@ int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, c
 // dst channel kx*nsrc + c at (y, x) = source c at (y, x + (kx - k/2)*dil), zero outside the image
 struct TcPlaneSrc { const float* ptr; int mode; };
 int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& dst, cudaStream_t st);
-int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st);
+int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st, int sub = 1);
 int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, float* partial /*[n*chunks]*/,
                       unsigned int* ticket /*[n], zero-initialised, left zero*/, cudaStream_t st);
 

@@ -15,8 +15,9 @@ static int alloc_buf(TcBuf& b, int n, int channels, int h, int w, int border, bo
   return HV_OK;
 }
 
-int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int up2_out,
+int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int flags,
                 cudaStream_t st) {
+  const int up2_out = flags & 1;
   HV_CHECK_ARG(d && w && y, "conv2d_bf16: null argument");
   HV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= 4, "conv2d_bf16: nsrc out of range");
   HV_CHECK_ARG(d->k == 3 || d->k == 5, "conv2d_bf16: kernel %d not built (3 or 5)", d->k);
@@ -50,6 +51,7 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
   TcConv c;
   rc = tc_conv_setup(c, srcs, nts, d->k, d->stride, d->dil, d->cout, d->n);
   if (rc) return rc;
+  c.force_generic = (flags & 2) != 0;
   const int ho = d->hin / d->stride, wo = d->win / d->stride;
   TcBuf out;
   if (d->act == HV_ACT_HEADS) {
@@ -79,9 +81,9 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
 
 }  // namespace hv
 
-extern "C" int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int up2_out,
+extern "C" int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int flags,
                               hv_stream_t stream) {
-  return hv::conv2d_bf16(d, w, bias, y, y2, up2_out, hv::as_stream(stream));
+  return hv::conv2d_bf16(d, w, bias, y, y2, flags, hv::as_stream(stream));
 }
 
 // bf16 tensor-core variant of hv_ctx_attn_fwd on fp32 NCHW tensors: pack -> ctx_attn_fwd_tc -> unpack

@@ -576,6 +576,19 @@ int hv_generator_run_layer(hv_generator* g, int idx, int n, hv_stream_t stream) 
   return tc_conv_launch(g->tc->conv[idx], as_stream(stream));
 }
 
+int hv_generator_run_chain(hv_generator* g, int first, int count, int n, hv_stream_t stream) {
+  HV_CHECK_ARG(g && g->tc, "generator_run_chain: needs a bf16 plan");
+  if (!g->prepared) { set_error("generator_run_chain: call hv_generator_prepare first"); return HV_ERR_STATE; }
+  HV_CHECK_ARG(n >= 1 && n <= g->max_batch && count >= 1 && first >= 0 && first + count <= kNumLayers, "generator_run_chain: bad range");
+  for (int idx = first; idx < first + count; ++idx) {
+    HV_CHECK_ARG(g->tc->has[idx] && g->tc->out_buf[idx] >= 0, "generator_run_chain: layer %d is not a stand-alone tensor-core conv", idx);
+    tc_set_batch(g->tc->conv[idx], n);
+    int rc = tc_conv_launch(g->tc->conv[idx], as_stream(stream));
+    if (rc) return rc;
+  }
+  return HV_OK;
+}
+
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream) {
   HV_CHECK_ARG(g && out, "generator_read_tap: null argument");
   HV_CHECK_ARG(g->last_n > 0, "generator_read_tap: no forward has run");
@@ -601,9 +614,9 @@ long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_
       HV_CHECK_ARG(b >= 0, "generator_read_tap: layer %d has no tap in bf16 mode", idx);
       TcBuf v = g->tc->buf[b];
       v.n = g->last_n;
-      if (g->tc->out_up2[idx]) { set_error("generator_read_tap: layer %d is stored upsampled in bf16 mode", idx); return HV_ERR_UNSUPPORTED; }
       const int ch = idx == A16 ? 8 : kLayers[idx].cout;
-      int rc = tc_unpack_nchw(v, 0, ch, out, as_stream(stream));
+      // layers whose output is stored nearest-x2-upsampled (conv12, conv14, allconv19, allconv14): read the native grid back
+      int rc = tc_unpack_nchw(v, 0, ch, out, as_stream(stream), g->tc->out_up2[idx] ? 2 : 1);
       if (rc) return rc;
       return (long long)count;
     }

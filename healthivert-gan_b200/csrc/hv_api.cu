@@ -1,6 +1,9 @@
 // extern "C" surface of libhv_b200.so (declared in include/hv_b200.h) for the stand-alone ops,
 // plus the thread-local error string and the launch counter.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "hv_common.cuh"
 #include "kernels.h"
 
@@ -17,6 +20,29 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+// Small internal scratch buffers keyed by (device, stream): kernels enqueued on one stream are ordered, so one grow-only
+// buffer per stream is race-free; different streams / devices / host threads get different buffers (the C ABI stays re-entrant).
+void* stream_scratch(cudaStream_t st, size_t bytes) {
+  static std::mutex mu;
+  struct Buf { void* ptr = nullptr; size_t cap = 0; };
+  static std::map<std::pair<int, cudaStream_t>, Buf> bufs;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  Buf& b = bufs[std::make_pair(dev, st)];
+  if (bytes > b.cap) {
+    if (b.ptr) {   // work already enqueued on this stream may still read the old buffer
+      if (cudaStreamSynchronize(st) != cudaSuccess) return nullptr;
+      cudaFree(b.ptr);
+      b.ptr = nullptr; b.cap = 0;
+    }
+    const size_t grow = bytes > (1u << 20) ? bytes : (1u << 20);
+    if (cudaMalloc(&b.ptr, grow) != cudaSuccess) { b.ptr = nullptr; return nullptr; }
+    b.cap = grow;
+  }
+  return b.ptr;
+}
 
 }  // namespace hv
 

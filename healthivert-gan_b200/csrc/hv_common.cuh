@@ -11,6 +11,8 @@ namespace hv {
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
+// grow-only device scratch private to (current device, stream); nullptr on allocation failure
+void* stream_scratch(cudaStream_t st, size_t bytes);
 
 #define HV_CHECK_ARG(cond, ...)                      \
   do {                                               \

@@ -168,8 +168,8 @@ __global__ void edge_loss_finish_kernel(const double* sq_sum, float* loss, doubl
 int edge_xor_loss(const float* fake, const float* real, unsigned long long* xor_count, float* loss, int n, int h, int w,
                   cudaStream_t st) {
   HV_CHECK_ARG(fake && real && xor_count && loss && n > 0 && n <= 65535 && h > 0 && w > 0, "edge_xor_loss: bad argument");
-  static double* d_sq = nullptr;  // tiny persistent scratch
-  if (!d_sq) HV_CUDA(cudaMalloc(&d_sq, sizeof(double)));
+  double* d_sq = static_cast<double*>(stream_scratch(st, sizeof(double)));  // per (device, stream): no shared accumulator
+  HV_CHECK_ARG(d_sq, "edge_xor_loss: scratch allocation failed");
   HV_CUDA(cudaMemsetAsync(d_sq, 0, sizeof(double), st));
   HV_CUDA(cudaMemsetAsync(xor_count, 0, sizeof(unsigned long long), st));
   edge_loss_kernel<<<dim3((h * w + 255) / 256, n), 256, 0, st>>>(fake, real, xor_count, d_sq, h, w);

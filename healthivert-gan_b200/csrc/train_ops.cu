@@ -209,17 +209,12 @@ __global__ void channel_sum_final_kernel(const float* __restrict__ partial, floa
 static int channel_sum_launch(const float* x, float* out, int n, int c, int hw, cudaStream_t st) {
   const long long total = (long long)n * hw;
   const int splits = (int)((total + kSumSlice - 1) / kSumSlice);
-  // scratch for the slice sums: one grow-only buffer per host thread (the training step drives one stream; stream order keeps
-  // successive calls from overlapping).  cudaMallocAsync per call cost more than the kernels (step 340 -> 448 ms).
-  static thread_local float* partial = nullptr;
-  static thread_local size_t capacity = 0;
+  // scratch for the slice sums: one grow-only buffer per (device, stream) (stream order keeps successive calls from overlapping).
+  // cudaMallocAsync per call cost more than the kernels (step 340 -> 448 ms).
   const size_t need = (size_t)splits * c;
-  if (need > capacity) {
-    if (partial) { HV_CUDA(cudaStreamSynchronize(st)); HV_CUDA(cudaFree(partial)); partial = nullptr; capacity = 0; }
-    const size_t grow = need > (1u << 18) ? need : (1u << 18);
-    HV_CUDA(cudaMalloc((void**)&partial, sizeof(float) * grow));
-    capacity = grow;
-  }
+  float* partial = static_cast<float*>(stream_scratch(st, sizeof(float) * need + 256)) ;
+  HV_CHECK_ARG(partial, "channel_sum: scratch allocation failed");
+  partial += 64;   // the first 256 bytes of the stream's scratch belong to the scalar reductions (edge loss)
   channel_sum_partial_kernel<<<dim3(splits, c), 256, 0, st>>>(x, partial, n, c, hw);
   HV_LAUNCH_CHECK();
   channel_sum_final_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, out, splits, c);

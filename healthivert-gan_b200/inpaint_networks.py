@@ -58,6 +58,9 @@ class SNConv2d(nn.Module):
         sigma = torch.empty(1, device=w.device, dtype=torch.float32)
         check(_lib.lib().hv_sn_prepare(ptr(w), ptr(self.weight_u), ptr(self.weight_v), self.out_channels,
                                        w[0].numel(), int(training), ptr(w_eff), ptr(sigma), _lib.stream()))
+        if training:   # the power iteration wrote u / v through raw pointers: bump their version counters like an in-place torch op
+            torch.autograd.graph.increment_version(self.weight_u)
+            torch.autograd.graph.increment_version(self.weight_v)
         return w_eff, sigma
 
 
@@ -406,6 +409,8 @@ class Generator(nn.Module):
         self.static_weights = False   # True: skip the per-forward weight-change check (weights frozen after the first forward)
         self.last_offsets = None
         self._last_out = None
+        self._pipelines = []          # weak references to SlicePipelines built on the native plan (closed before the plan goes)
+        self._u8_pipe = None
 
     # ---- native plan management -------------------------------------------------------
     def _layers(self):
@@ -423,7 +428,19 @@ class Generator(nn.Module):
         self._param_sig = None
         return out
 
+    def train(self, mode=True):
+        # a mode switch always re-prepares the plan: the train-mode forward power-iterates u / v inside the library (raw pointers,
+        # no version bump), so the signature taken before it says nothing about the weights the next eval forward must use
+        self._param_sig = None
+        return super().train(mode)
+
     def _destroy_plan(self):
+        for ref in getattr(self, "_pipelines", []):
+            pipe = ref()
+            if pipe is not None:
+                pipe.close()
+        self._pipelines = []
+        self._u8_pipe = None
         if self._plan is not None:
             _lib.lib().hv_generator_destroy(self._plan)
             self._plan = None
@@ -454,7 +471,9 @@ class Generator(nn.Module):
             return self._plan          # the caller vouches that the weights do not change between forwards (eval loops)
         # Weight signature: identity + version counter of the 192 tensors, read through the modules' own dicts (Module.__getattr__
         # and data_ptr() made this check cost as much host time as the 59 kernel launches of the forward).  In-place updates
-        # (optimizer steps, load_state_dict) bump the version; .cuda() / .to() go through _apply, which drops the signature.
+        # (torch optimizers, load_state_dict, and this package's own FusedAdam.step / train-mode power iteration, which call
+        # increment_version after writing through raw pointers) bump the version; .cuda() / .to() go through _apply and
+        # train() / eval() through train(), both of which drop the signature.
         if self._sig_slots is None:
             convs = self._layers()
             fcs = (self.coarse_generator.fc_height, self.fine_generator.fc_height)
@@ -477,6 +496,10 @@ class Generator(nn.Module):
             for i, f in enumerate(fcs):
                 check(L.hv_generator_set_fc(self._plan, i, ptr(f.weight.data), ptr(f.bias.data)))
             check(L.hv_generator_prepare(self._plan, int(training), _lib.stream()))
+            if training:   # the library power-iterated u / v in place through raw pointers
+                for c in convs:
+                    torch.autograd.graph.increment_version(c.weight_u)
+                    torch.autograd.graph.increment_version(c.weight_v)
             self._param_sig = None if training else sig
         return self._plan
 
@@ -510,6 +533,30 @@ class Generator(nn.Module):
         self._last_out = out  # the head taps of read_tap() alias these buffers
         return out
 
+    @torch.no_grad()
+    def forward_u8(self, ct_u8, cam_u8, rows, slice_ratio):
+        """The generator behind the uint8 HOST interface of the eval driver (eval_3d_sagittal_twostage.py:84-121): numpy / CPU
+        arrays in, numpy arrays out, one H2D copy + one CUDA-graph launch + one D2H copy (healthivert_gan_b200.pipeline).
+        ct_u8, cam_u8: [n, 256, 256] uint8 (the composed CT plane and CAM * 255; the network sees (u8/255 - 0.5)/0.5 and
+        1 - u8/255); rows: [n, 2] mask row range [r0, r1); slice_ratio: [n].
+        Returns (ct_u8_out = trunc((x_stage2 + 1) * 127.5), fine_mask, coarse_mask in {0,1}, pred1_h, pred2_h)."""
+        import numpy as np
+        from .pipeline import SlicePipeline
+        ct_u8 = np.asarray(ct_u8, dtype=np.uint8)
+        n = ct_u8.shape[0]
+        pipe = self._u8_pipe
+        if pipe is None or pipe._h is None or pipe.batch < n:
+            pipe = self._u8_pipe = SlicePipeline(self, batch=max(n, 16), depth=1)
+        pipe.refresh()
+        s = pipe.slot(0)
+        s.ct[:n] = ct_u8.reshape(n, 256, 256)
+        s.cam[:n] = np.asarray(cam_u8, dtype=np.uint8).reshape(n, 256, 256)
+        s.rows[:n] = np.asarray(rows, dtype=np.int32).reshape(n, 2)
+        s.ratio[:n] = np.asarray(slice_ratio, dtype=np.float32).reshape(n)
+        pipe.submit(0, n)
+        pipe.wait(0)
+        return (s.ct_out[:n].copy(), s.fine_mask[:n].copy(), s.coarse_mask[:n].copy(), s.heights[0, :n].copy(), s.heights[1, :n].copy())
+
     def forward_tape(self, tape, x, mask, CAM, slice_ratio):
         """Training-path forward (layer by layer, fp32) recorded on ``tape``: returns the reference's 7-tuple with tape
         Vars in place of the differentiable outputs (coarse_seg, fine_seg, x_stage1, x_stage2, flow tensor, pred1_h, pred2_h)."""
@@ -528,6 +575,10 @@ class Generator(nn.Module):
     def run_layer(self, idx, n):
         """Measurement hook: launch the tensor-core conv kernel of layer ``idx`` alone (bf16 plan)."""
         check(_lib.lib().hv_generator_run_layer(self._plan, idx, n, _lib.stream()))
+
+    def run_chain(self, first, count, n):
+        """Measurement hook: layers first .. first+count-1 back to back, each on its predecessor's output (bf16 plan)."""
+        check(_lib.lib().hv_generator_run_chain(self._plan, first, count, n, _lib.stream()))
 
     @torch.no_grad()
     def read_tap(self, idx):

@@ -83,8 +83,18 @@ def header_affine(h):
         return aff
     if h["qform_code"] > 0:
         return _quatern_to_affine(h)
+    # neither code set: nibabel's get_base_affine() = shape_zoom_affine(shape, zooms, x_flip=True): voxel sizes on the diagonal
+    # with the x axis flipped (radiological default of Nifti1Header) and the origin at the centre voxel of the first 3 dimensions
+    ndim = int(h["dim"][0])
+    shape = np.ones(3)
+    zooms = np.ones(3)
+    for i in range(min(ndim, 3)):
+        shape[i] = float(h["dim"][1 + i])
+        zooms[i] = float(h["pixdim"][1 + i])
+    zooms[0] *= -1.0
     aff = np.eye(4)
-    aff[0, 0], aff[1, 1], aff[2, 2] = (abs(float(v)) or 1.0 for v in h["pixdim"][1:4])
+    aff[:3, :3] = np.diag(zooms)
+    aff[:3, 3] = -((shape - 1.0) / 2.0) * zooms
     return aff
 
 
@@ -120,9 +130,7 @@ def _read_all(path):
 def load(path):
     raw = _read_all(path)
     h = parse_header(raw)
-    shape = tuple(int(v) for v in h["dim"][1:1 + h["dim"][0]])
-    while len(shape) > 3 and shape[-1] == 1:
-        shape = shape[:-1]
+    shape = tuple(int(v) for v in h["dim"][1:1 + h["dim"][0]])   # all dim[0] dimensions as stored, like nibabel's dataobj
     dt = np.dtype(_DTYPES[h["datatype"]]).newbyteorder(h["endian"])
     off = int(h["vox_offset"]) or 352
     count = int(np.prod(shape))

@@ -25,6 +25,10 @@ class BaseModel:
         self.gpu_ids = opt.gpu_ids
         self.isTrain = opt.isTrain
         self.device = torch.device("cuda:{}".format(self.gpu_ids[0])) if self.gpu_ids else torch.device("cuda")
+        # every kernel launches on the CURRENT device's current stream and hv_generator_create allocates on the current device:
+        # make gpu_ids[0] current, as the reference does in its option parsing (options/base_options.py:137-139)
+        if self.gpu_ids and torch.cuda.is_available():
+            torch.cuda.set_device(self.device)
         self.save_dir = os.path.join(opt.checkpoints_dir, opt.name)
         self.loss_names, self.model_names, self.visual_names, self.optimizers, self.image_paths = [], [], [], [], []
         self.metric = 0
@@ -124,6 +128,13 @@ class Pix2PixModel(BaseModel):
         self.x1 = input["x1"].to(dev)
         self.x2 = input["x2"].to(dev)
         self.maxheight = input["h2"].to(dev)
+        # the stitch / height-loss kernels take ONE maxheight for the batch (the dataset's h2 is the constant 40,
+        # data/aligned_dataset.py:202); it is read here, from the collated host tensor, not per forward on the device
+        h2 = input["h2"].reshape(-1)
+        self._maxh = int(h2[0]) if h2.numel() else 40
+        if h2.numel() and not bool((h2 == h2[0]).all()):
+            raise _lib.HvError("hv_b200 Pix2PixModel: per-sample maxheight (h2) values differ within the batch; "
+                               "the device-side stitch takes one value per batch")
         self.image_paths = input["A_paths" if AtoB else "B_paths"]
 
     # ------------------------------------------------------------------------------------------ forward
@@ -144,8 +155,7 @@ class Pix2PixModel(BaseModel):
                 cs, fs, x1t, x2t, flow, p1t, p2t = self.netG(self.real_A, self.mask, cam_temp, self.slice_ratio)
         self.coarse_seg_sigmoid, self.fake_B_mask_sigmoid, self.x_stage1, self.fake_B_raw, self.offset_flow = cs, fs, x1t, x2t, flow
         self._pred1_raw, self._pred2_raw = p1t, p2t                  # sigmoid outputs in (0, 1), [N, 1]
-        maxh = int(self.maxheight.reshape(-1)[0].item()) if self.maxheight.numel() else 40
-        self._maxh = maxh
+        maxh = self._maxh
         self.fake_B_mask_raw = mask_ops.threshold(fs)                # :201
         self.coarse_seg_binary = mask_ops.threshold(cs)              # :202
         # height-adaptive stitching on the device, no .item() syncs (:206-252)

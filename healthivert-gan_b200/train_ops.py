@@ -309,3 +309,6 @@ class FusedAdam:
             grad = p.grad.contiguous()
             check(_L().hv_adam_step(ptr(p.data), ptr(grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(g["lr"]),
                                     float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), int(st["step"]), _lib.stream()))
+            # the kernel wrote through a raw pointer: tell torch (and the Generator's cached-plan signature, which compares
+            # tensor._version) that the parameter changed in place, exactly as an eager optimizer step would
+            torch.autograd.graph.increment_version(p)

@@ -81,10 +81,11 @@ int hv_conv2d_fwd(const hv_conv_desc* d, const float* w, const float* bias, floa
 /* bf16 tensor-core variant of hv_conv2d_fwd (tcgen05.mma, fp32 accumulate in TMEM): same
  * descriptor and fp32 NCHW tensors; inputs and weights are rounded to bf16, the output is rounded to
  * bf16 (heads: fp32).  k in {3,5}, 'same' padding, stride 1 or (k=3) 2, cout <= 64.
- * up2_out != 0 additionally applies the nearest x2 upsample of the NEXT layer to the stored
- * result (y is [n,cout,2*hout,2*wout]).                                                        */
+ * flags bit 0: additionally apply the nearest x2 upsample of the NEXT layer to the stored result
+ * (y is [n,cout,2*hout,2*wout]); bit 1: run the generic kernel instance even where a geometry-
+ * specialised one exists (both must agree: tests/test_gpu_conv_bf16.py).                       */
 int hv_conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2,
-                   int up2_out, hv_stream_t stream);
+                   int flags, hv_stream_t stream);
 
 /* replaces global_pool + fc_height + sigmoid (models/inpaint_networks.py:90-93,:211-214) */
 int hv_gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* out,
@@ -169,9 +170,38 @@ int hv_generator_forward(hv_generator* g, const float* x, const float* mask, con
 /* measurement hook (bf16 plan): launch the tensor-core conv kernel of layer idx alone on the
  * activations of the last forward (bench.py times the dominant kernel with it)            */
 int hv_generator_run_layer(hv_generator* g, int idx, int n, hv_stream_t stream);
+/* the same for `count` consecutive layers first .. first+count-1 of the state_dict order, each reading its predecessor's output
+ * exactly as in the forward (one host call: bench.py's roofline leg times the chain of 64->64 trunk layers with it)        */
+int hv_generator_run_chain(hv_generator* g, int first, int count, int n, hv_stream_t stream);
 /* debug/parity tap: copy the fp32 NCHW activation of layer idx (or idx==47: attention
  * output) of the LAST forward into out; returns element count or negative status        */
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream);
+
+/* ---- uint8 HOST interface of the generator: what run_model hands over and keeps ----------
+ * replaces, for host buffers, the per-slice tensor plumbing around `model(ct, mask, 1-CAM, ratio)` in
+ * eval_3d_sagittal_twostage.py: inputs :84-98 (uint8 CT / CAM planes -> ToTensor -> Normalize(0.5, 0.5); the
+ * mask is a row range painted 255, :73-75), outputs :103-121 (seg > 0.5, (x_stage2 + 1) * 127.5 truncated by the
+ * next astype(uint8), pred_h).  A pipeline owns `depth` slots of pinned HOST memory and their device mirrors;
+ * submit() = 1 H2D copy + ONE CUDA-graph launch of the whole two-stage forward + 1 D2H copy on three streams,
+ * so that consecutive slots overlap.  The generator must be prepared and outlive the pipeline; its weights
+ * may be re-prepared between submits (the graph reads the plan's buffers, not the parameters).
+ * per_sample_mask: see hv_generator_forward; use_graph = 0 launches the kernels directly (A/B, debugging). */
+typedef struct hv_pipeline hv_pipeline;
+int hv_pipeline_create(hv_pipeline** out, hv_generator* g, int batch, int depth, int per_sample_mask, int use_graph);
+int hv_pipeline_destroy(hv_pipeline* p);
+/* HOST pointers into slot `slot` (any may be NULL): inputs ct_in / cam_in [batch][256][256] u8, rows_in [batch][2]
+ * int32 = mask rows [r0, r1) (eval: (min_x, max_x + 1)), ratio_in [batch] fp32; outputs ct_out = trunc((x_stage2+1)*127.5),
+ * fine_mask_out / coarse_mask_out in {0,1} [batch][256][256] u8, heights_out [2][batch] fp32 = pred1_h then pred2_h.  */
+int hv_pipeline_slot(hv_pipeline* p, int slot, uint8_t** ct_in, uint8_t** cam_in, int32_t** rows_in, float** ratio_in,
+                     uint8_t** ct_out, uint8_t** fine_mask_out, uint8_t** coarse_mask_out, float** heights_out);
+/* bytes copied per submit: which = 0 host->device, 1 device->host */
+size_t hv_pipeline_bytes(hv_pipeline* p, int which);
+/* the pipeline's streams (cudaStream_t): 0 input copies, 1 compute, 2 output copies (for event timing by the caller) */
+void* hv_pipeline_stream(hv_pipeline* p, int which);
+/* enqueue the first n entries of the slot (fill the inputs first); returns at once.  HV_ERR_STATE while in flight. */
+int hv_pipeline_submit(hv_pipeline* p, int slot, int n);
+/* block the calling host thread until the slot's outputs have landed in its pinned output block */
+int hv_pipeline_wait(hv_pipeline* p, int slot);
 
 
 /* ======================================================================================

@@ -1,6 +1,7 @@
-"""Generate tests/golden/train_step_n2.npz by running the UNMODIFIED reference Pix2PixModel on CPU (build container only).
+"""Generate tests/golden/train_step_n2.npz (and, with `--n 16 --steps 1`, train_step_n16.npz: BASELINE.json config 4's batch
+size) by running the UNMODIFIED reference Pix2PixModel on CPU (build container only).
 
-TEST INFRASTRUCTURE.  Run from the repo root:  python -m oracle.make_golden_train
+TEST INFRASTRUCTURE.  Run from the repo root:  python -m oracle.make_golden_train [--n N] [--steps K]
 Two optimize_parameters() steps (models/pix2pix_model.py:356-382) on synthetic_train_batch(n=2, seed=7) with the shared
 synthetic generator / discriminator state_dicts.  Stored per step: the 12 loss_names; after step 1 additionally, for every
 parameter of G, D_1, D_2, D_3: the gradient L2 norm, 8 gradient probes and 8 probes of the updated parameter; the
@@ -47,12 +48,17 @@ def build_reference(n):
 
 
 def main():
-    n = 2
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=2)
+    ap.add_argument("--steps", type=int, default=2)
+    args = ap.parse_args()
+    n = args.n
     torch.set_num_threads(os.cpu_count() or 1)
     m = build_reference(n)
     batch = synth.synthetic_train_batch(n=n, seed=7)
     out = {}
-    for step in (1, 2):
+    for step in range(1, args.steps + 1):
         m.set_input(batch)
         m.optimize_parameters()
         out[f"losses_step{step}"] = np.array([float(getattr(m, "loss_" + k)) for k in m.loss_names])
@@ -75,8 +81,8 @@ def main():
             out["fake_B_probe"] = probe(m.fake_B)
             out["pred_h"] = np.concatenate([m.pred1_h.detach().numpy().reshape(-1), m.pred2_h.detach().numpy().reshape(-1)])
         print("step", step, dict(zip(m.loss_names, np.round(out[f"losses_step{step}"], 5))))
-    np.savez_compressed(os.path.join(GOLD, "train_step_n2.npz"), **out)
-    print("wrote train_step_n2.npz")
+    np.savez_compressed(os.path.join(GOLD, f"train_step_n{n}.npz"), **out)
+    print(f"wrote train_step_n{n}.npz")
 
 
 if __name__ == "__main__":

@@ -277,6 +277,123 @@ def test_two_training_steps_against_reference_golden(golden_dir):
     assert np.abs(got2 - ref2).max() <= 0.05 * np.maximum(1.0, np.abs(ref2)).max(), dict(zip(names, zip(got2, ref2)))
 
 
+def test_one_training_step_batch16_against_reference_golden(golden_dir):
+    """BASELINE.json config 4 at its stated batch size: one optimize_parameters() step on synthetic_train_batch(n=16) against the
+    golden vectors of the UNMODIFIED reference Pix2PixModel (oracle/make_golden_train.py --n 16 --steps 1)."""
+    gold = np.load(os.path.join(golden_dir, "train_step_n16.npz"))
+    m = _build_model(16)
+    m.set_input(synth.synthetic_train_batch(n=16, seed=7))
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    names = [str(s) for s in gold["loss_names"]]
+    got = np.array([m.get_current_losses()[k] for k in names])
+    ref = gold["losses_step1"]
+    assert np.abs(got - ref).max() <= 2e-3 * np.maximum(1.0, np.abs(ref)).max(), dict(zip(names, zip(got, ref)))
+    assert np.abs(probe(m.fake_B) - gold["fake_B_probe"]).max() <= 1e-4
+    for tag, net in (("D_1", m.netD_1), ("D_2", m.netD_2), ("D_3", m.netD_3), ("G", m.netG)):
+        params = dict(net.named_parameters())
+        for i, name in enumerate(str(s) for s in gold[f"{tag}_names"]):
+            p = params[name]
+            gn, rn = float(p.grad.double().norm()), float(gold[f"{tag}_grad_norm"][i])
+            assert abs(gn - rn) <= 5e-3 * rn + 1e-7, (tag, name, gn, rn)
+            assert np.abs(probe(p.grad) - gold[f"{tag}_grad_probe"][i]).max() <= 5e-3 * rn + 1e-7, (tag, name)
+            assert np.abs(probe(p) - gold[f"{tag}_param_probe"][i]).max() <= 4.5e-4, (tag, name)
+
+
+def test_eval_forward_follows_the_fused_optimizer(synthetic_sd):
+    """The cached native plan must see what FusedAdam.step and the train-mode power iteration wrote through raw pointers
+    (reference flow: train.py:225 evaluate_model between training epochs): eval forward, optimize_parameters(), eval forward -
+    the output changes and equals what a freshly built plan computes from the updated state_dict."""
+    m = _build_model(2)
+    x, mask, cam, ratio = (t.cuda() for t in synth.synthetic_slices(2, seed=5))
+    for precision in ("fp32", "bf16"):
+        m.netG.precision = precision
+        m.netG.eval()
+        with torch.no_grad():
+            before = m.netG(x, mask, cam, ratio)[3].clone()
+        m.netG.train()
+        m.set_input(synth.synthetic_train_batch(n=2, seed=7))
+        m.optimize_parameters()
+        m.netG.eval()
+        with torch.no_grad():
+            after = m.netG(x, mask, cam, ratio)[3].clone()
+        assert not torch.equal(before, after), precision
+        fresh = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+        fresh.load_state_dict({k: v.detach().clone() for k, v in m.netG.state_dict().items()})
+        fresh = fresh.cuda().eval()
+        fresh.precision = precision
+        with torch.no_grad():
+            want = fresh(x, mask, cam, ratio)[3]
+        assert torch.equal(after, want), precision
+        m.netG.train()
+
+
+def _replica(seed_batch):
+    opt = synth.train_options(gpu_ids=[torch.cuda.current_device()])
+    m = Pix2PixModel(opt)
+    m.setup(opt)
+    m.netG.load_state_dict(synth.synthetic_generator_state_dict())
+    for k, net in enumerate((m.netD_1, m.netD_2, m.netD_3), start=1):
+        net.load_state_dict(synth.synthetic_discriminator_state_dict(seed=k))
+    m.train()
+    m.set_input(seed_batch)
+    return m
+
+
+def data_parallel_truth(world=2, per_rank=2, seed=7):
+    """The data-parallel step restated in ONE process (SURVEY 8(d) config 4 "against our own 1-GPU run"): `world` replicas with
+    identical weights, replica r on samples [r * per_rank, (r + 1) * per_rank) - so BatchNorm statistics, the masked-L1 pixel
+    count and the loss means are per per_rank-sample group, as on separate ranks - and the gradient exchange done by hand: after
+    every net's backward the replicas' gradients are replaced by their mean.  Returns replica 0 and the averaged gradients."""
+    full = synth.synthetic_train_batch(n=world * per_rank, seed=seed)
+    cut = lambda r: {k: v[r * per_rank:(r + 1) * per_rank] for k, v in full.items()}
+    reps = [_replica(cut(r)) for r in range(world)]
+    grads = {}
+
+    def exchange(tag, nets):
+        mean = []
+        for ps in zip(*(n.parameters() for n in nets)):
+            g = torch.stack([p.grad for p in ps]).sum(0) / world
+            for p in ps:
+                p.grad = g.clone()
+            mean.append(g.clone())
+        grads[tag] = mean
+
+    for m in reps:
+        m.forward()
+    for k in (1, 2, 3):
+        for m in reps:
+            net = getattr(m, f"netD_{k}")
+            m.set_requires_grad(net, True)
+            getattr(m, f"optimizer_D_{k}").zero_grad()
+            getattr(m, f"backward_D_{k}")()
+        exchange(f"D_{k}", [getattr(m, f"netD_{k}") for m in reps])
+        for m in reps:
+            getattr(m, f"optimizer_D_{k}").step()
+    for m in reps:
+        m.set_requires_grad([m.netD_1, m.netD_2, m.netD_3], False)
+        m.optimizer_G.zero_grad()
+        m.backward_G()
+    exchange("G", [m.netG for m in reps])
+    for m in reps:
+        m.optimizer_G.step()
+    torch.cuda.synchronize()
+    return reps[0], grads
+
+
+def test_data_parallel_truth_differs_from_the_pooled_batch():
+    """Sanity of the single-process restatement itself: per-2-sample BatchNorm groups give D gradients that differ from one pooled
+    batch-4 step (so the comparison in the 2-rank test is not vacuous), while the generator forward (no BatchNorm) is identical."""
+    rep0, grads = data_parallel_truth(world=2, per_rank=2)
+    pooled = _replica(synth.synthetic_train_batch(n=4, seed=7))
+    pooled.optimize_parameters()
+    torch.cuda.synchronize()
+    assert torch.equal(pooled.fake_B_raw[:2], rep0.fake_B_raw)
+    d = [rel(a, b.grad) for a, b in zip(grads["D_1"], pooled.netD_1.parameters())]
+    assert max(d) > 1e-3
+    assert all(torch.isfinite(g).all() for gs in grads.values() for g in gs)
+
+
 def _ddp_worker(rank, world, port, out):
     import torch.distributed as dist
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
@@ -298,7 +415,10 @@ def _ddp_worker(rank, world, port, out):
         torch.cuda.synchronize()
         sd = {k: v.detach().cpu() for k, v in m.netG.state_dict().items()}
         if rank == 0:
-            torch.save(sd, out)
+            torch.save({"G": sd, "D_1": {k: v.detach().cpu() for k, v in m.netD_1.state_dict().items()},
+                        "grad_G": [p.grad.detach().cpu() for p in m.netG.parameters()],
+                        "grad_D_1": [p.grad.detach().cpu() for p in m.netD_1.parameters()],
+                        "grad_D_3": [p.grad.detach().cpu() for p in m.netD_3.parameters()]}, out)
         # replicas must stay bit-identical after the averaged update
         ref = [torch.zeros_like(v, device="cuda") for v in m.netG.parameters()]
         for r, p in zip(ref, m.netG.parameters()):
@@ -311,7 +431,9 @@ def _ddp_worker(rank, world, port, out):
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
 def test_data_parallel_step_two_ranks_nccl(tmp_path):
-    """Config 4 sharding: 2 samples per rank, gradient all-reduce(mean) over NCCL; replicas stay identical and finite."""
+    """Config 4 sharding: 2 samples per rank, gradient all-reduce(mean) over NCCL.  Replicas stay bit-identical, and the averaged
+    gradients / updated weights equal the single-process restatement of the same step (data_parallel_truth: per-2-sample BatchNorm
+    groups, hand-made gradient mean) - i.e. the collective path computes what one process would."""
     import socket
     import torch.multiprocessing as mp
     with socket.socket() as s:
@@ -319,5 +441,13 @@ def test_data_parallel_step_two_ranks_nccl(tmp_path):
         port = s.getsockname()[1]
     out = str(tmp_path / "g.pt")
     mp.spawn(_ddp_worker, args=(2, port, out), nprocs=2, join=True)
-    sd = torch.load(out)
-    assert all(torch.isfinite(v).all() for v in sd.values() if v.dtype.is_floating_point)
+    got = torch.load(out)
+    assert all(torch.isfinite(v).all() for v in got["G"].values() if v.dtype.is_floating_point)
+    rep0, grads = data_parallel_truth(world=2, per_rank=2)
+    for tag in ("G", "D_1", "D_3"):
+        for a, b in zip(got[f"grad_{tag}"], grads[tag]):
+            assert rel(a, b) <= 1e-5, tag        # NCCL sums in a different order than torch.stack(...).sum(0): fp32 rounding only
+    for name, net in (("G", rep0.netG), ("D_1", rep0.netD_1)):
+        for k, v in net.state_dict().items():
+            if v.dtype.is_floating_point:
+                assert float((got[name][k] - v.detach().cpu()).abs().max()) <= 1e-6, (name, k)

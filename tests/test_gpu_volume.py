@@ -167,6 +167,78 @@ def test_file_level_driver_matches_array_driver(gen, tmp_path):
     assert got_seg.get_fdata().any()
 
 
+def test_coronal_driver_against_oracle_and_transposed_sagittal(gen, synthetic_sd):
+    """axis = 1 (coronal slices vol[:, z, :], evaluation/RHLV_quantification_coronal.py:51-54) of a volume == the sagittal driver
+    on the volume with its last two axes swapped (bit-identical: same slices through the same kernels) == the oracle restatement
+    of process_nii_files on that swapped volume."""
+    label, ct, cam = synth.synthetic_volume(seed=6, depth=8)
+    sw = lambda v: np.ascontiguousarray(v.transpose(0, 2, 1))     # [256, 8, 256]: the slicing axis is axis 1
+    vs = VolumeSynthesizer(gen, batch=4)
+    cor_ct, cor_seg = vs.synthesize(sw(ct), sw(label), sw(cam), 20, axis=1)
+    sag_ct, sag_seg = vs.synthesize(ct, label, cam, 20, axis=2)
+    assert cor_ct.shape == (256, 8, 256)
+    assert np.array_equal(cor_ct, sw(sag_ct)) and np.array_equal(cor_seg, sw(sag_seg))
+    ref_ct, ref_seg = _oracle_volume(synthetic_sd, ct, label, cam, 20)
+    assert (cor_seg != sw(ref_seg)).mean() <= 2e-4
+    assert np.abs(cor_ct - sw(ref_ct)).max() <= 2.0 and np.abs(cor_ct - sw(ref_ct)).mean() <= 0.01
+
+
+def test_config3_shape_sagittal_plus_coronal_with_rhlv(gen):
+    """BASELINE.json config 3 at its stated slice shape through the driver: a 256 x 256 x 256 synthetic volume, sagittal AND coronal
+    three-stage synthesis, RHLV features of both orientations (the 2.5D feature vector, SVM_grading_2.5d.py:14-27).  Size-independent
+    properties at full size: the synthesis window is the middle 4/5 of the vertebra's extent along the slicing axis (eval:186-197),
+    slices outside it stay zero, label_fake holds only {0, vert_id}, the CT is whole numbers in [0, 255] (uint8 hand-over), and
+    RHLV(label_fake, label_fake) == 0."""
+    from healthivert_gan_b200 import mask_ops
+    label, ct, cam = synth.synthetic_volume(seed=2, depth=256)
+    vs = VolumeSynthesizer(gen, batch=64)
+    feats = {}
+    for axis in (2, 1):
+        ct_f, lab_f = vs.synthesize(ct, label, cam, 20, axis=axis)
+        assert ct_f.shape == label.shape
+        zs = np.where(label == 20)[axis]
+        z0, z1 = int(zs.min()), int(zs.max())
+        rl = z1 - z0 + 1
+        nl = int(rl * 4 / 5)
+        nz0 = z0 + (rl - nl) // 2
+        done = np.nonzero(lab_f.any(axis=tuple(a for a in range(3) if a != axis)))[0]
+        assert done.min() >= nz0 and done.max() <= nz0 + nl - 1 and done.size >= nl - 2
+        assert set(np.unique(lab_f)) <= {0.0, 20.0}
+        assert np.array_equal(ct_f, np.floor(ct_f)) and ct_f.min() >= 0 and ct_f.max() <= 255
+        fake = (lab_f == 20).astype(np.uint8)
+        real = (label == 20).astype(np.uint8)
+        c, ln = int(np.mean(np.where(real)[axis])), (z1 - z0) // 5
+        feats[axis] = mask_ops.calculate_rhlv(fake, real, c, ln, "v20", 0.7, axis=axis)
+        same = mask_ops.calculate_rhlv(fake, fake, c, ln, "v20", 0.7, axis=axis)
+        assert all(abs(v) <= 1e-12 for v in same[:4])
+    assert all(np.isfinite(v) for ax in feats for v in feats[ax])
+
+
+def test_bf16_volume_loop_tracks_fp32_volume_loop(gen, synthetic_sd):
+    """The three-stage loop feeds thresholded masks and uint8-truncated CT of one stage into the next, so bf16-mode decisions can
+    differ from fp32 mode near 0.5 / near integer CT values.  Measured and bounded here: label flip rate, CT difference and the
+    per-slice vertebral height (rows with any label) of label_fake."""
+    label, ct, cam = synth.synthetic_volume(seed=5, depth=24)
+    g16 = hv.Generator({"input_dim": 1, "ngf": 16}, True)
+    g16.load_state_dict(synthetic_sd)
+    g16 = g16.cuda().eval()
+    g16.precision = "bf16"
+    ct32, lab32 = VolumeSynthesizer(gen, batch=16).synthesize(ct, label, cam, 20)
+    ct16, lab16 = VolumeSynthesizer(g16, batch=16).synthesize(ct, label, cam, 20)
+    done = np.nonzero(lab32.any(axis=(0, 1)))[0]
+    assert np.array_equal(np.nonzero(lab16.any(axis=(0, 1)))[0], done) and done.size >= 10
+    flips = float((lab16[:, :, done] != lab32[:, :, done]).mean())
+    dct = np.abs(ct16[:, :, done] - ct32[:, :, done])
+    h32 = (lab32[:, :, done] != 0).any(axis=1).sum(axis=0)
+    h16 = (lab16[:, :, done] != 0).any(axis=1).sum(axis=0)
+    dh = np.abs(h32.astype(int) - h16.astype(int))
+    print(f"bf16 vs fp32 volume loop: label flip rate {flips:.2e}, CT |diff| mean {dct.mean():.3f} max {dct.max():.1f} (of 255), "
+          f"height |diff| mean {dh.mean():.2f} max {dh.max()} rows over {done.size} slices")
+    assert flips <= 5e-3
+    assert dct.mean() <= 0.5
+    assert dh.mean() <= 1.0 and dh.max() <= 3
+
+
 def test_straightening_against_reference_golden(golden_dir):
     """hv_resample_curve + straighten.straighten_case on the raw case the reference ships (multi-label mask + centroids, synthetic
     smooth CT) == the UNMODIFIED reference (vendored `straighten` package + straighten_mask_3d.py helpers, scipy map_coordinates):
