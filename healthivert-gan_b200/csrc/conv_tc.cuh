@@ -160,6 +160,11 @@ int tc_conv_launch(const TcConv& c, cudaStream_t st);
 void tc_set_trace(long long* dev_buf);  // debug: CTA 0 of every subsequent launch records its event timeline
 void tc_conv_free(TcConv& c);
 
+// dataflow kernel for chains of 64 -> 64 3x3 layers on the 64x64 trunk (trunk_tc.cu): one persistent launch per chain
+bool tc_trunk_eligible(const TcConv& c);
+size_t tc_trunk_counter_ints(int max_images);
+int tc_trunk_launch(const TcConv* const* convs, int count, int n_images, int* counters, cudaStream_t st);
+
 // fp32 NCHW <-> chunked bf16 converters (channel c of the source lands in chunk c/8, lane c%8)
 int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, const TcBuf& dst, int dst_channel0,
                  cudaStream_t st);

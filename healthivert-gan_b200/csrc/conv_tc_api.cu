@@ -64,7 +64,7 @@ int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float*
     const int sc = up2_out ? 2 : 1;
     rc = alloc_buf(out, d->n, d->cout, ho * sc, wo * sc, 1, false, st);
     if (rc) return rc;
-    tc_conv_set_output_chunked(c, out, 0, c.n_pad / 8, up2_out != 0, d->act);
+    tc_conv_set_output_chunked(c, out, 0, c.n_pad / 8 < out.chunks ? c.n_pad / 8 : out.chunks, up2_out != 0, d->act);   // never past the buffer's own chunks
   }
   rc = tc_conv_launch(c, st);
   if (rc) return rc;

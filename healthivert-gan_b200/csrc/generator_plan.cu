@@ -271,7 +271,27 @@ struct TcPlan {
   float* gap_partial = nullptr;      // [2][max_batch * 8] shares of the two height heads
   unsigned int* gap_ticket = nullptr;  // [2][max_batch]
   __nv_bfloat16* blob = nullptr;
+  int* trunk_ctr = nullptr;            // [kNumLayers][tc_trunk_counter_ints(max_batch)]: queue / completion counters of the chain starting at a layer
+  size_t trunk_ctr_stride = 0;
 };
+
+// a run of consecutive 64 -> 64 trunk layers as ONE dataflow launch (trunk_tc.cu); HV_NO_TRUNK=1 falls back to one launch per layer
+static int run_layers(hv_generator* g, const int* layers, int count, int n, cudaStream_t st) {
+  TcPlan* t = g->tc;
+  static const bool no_trunk = getenv("HV_NO_TRUNK") != nullptr;
+  bool ok = !no_trunk && count >= 2 && count <= 8;
+  const TcConv* convs[8];
+  for (int i = 0; i < count; ++i) {
+    tc_conv_set_batch(t->conv[layers[i]], n);
+    if (ok) { convs[i] = &t->conv[layers[i]]; ok = tc_trunk_eligible(*convs[i]) && (i == count - 1 || !t->out_up2[layers[i]]); }
+  }
+  if (ok) return tc_trunk_launch(convs, count, n, t->trunk_ctr + (size_t)layers[0] * t->trunk_ctr_stride, st);
+  for (int i = 0; i < count; ++i) {
+    int rc = tc_conv_launch(t->conv[layers[i]], st);
+    if (rc) return rc;
+  }
+  return HV_OK;
+}
 
 static TcAux make_aux(const TcBuf& b, int channel) {
   TcAux a;
@@ -283,7 +303,7 @@ static TcAux make_aux(const TcBuf& b, int channel) {
 static void tc_plan_destroy(hv_generator* g) {
   if (!g->tc) return;
   for (int i = 0; i < kNumLayers; ++i) if (g->tc->has[i]) tc_conv_free(g->tc->conv[i]);
-  cudaFree(g->tc->blob); cudaFree(g->tc->ca_ws); cudaFree(g->tc->gap_partial); cudaFree(g->tc->gap_ticket);
+  cudaFree(g->tc->blob); cudaFree(g->tc->ca_ws); cudaFree(g->tc->gap_partial); cudaFree(g->tc->gap_ticket); cudaFree(g->tc->trunk_ctr);
   delete g->tc;
   g->tc = nullptr;
 }
@@ -316,6 +336,9 @@ static int tc_plan_create(hv_generator* g) {
   HV_CUDA(cudaMalloc((void**)&t->gap_partial, sizeof(float) * 2 * n * 8));
   HV_CUDA(cudaMalloc((void**)&t->gap_ticket, sizeof(unsigned int) * 2 * n));
   HV_CUDA(cudaMemset(t->gap_ticket, 0, sizeof(unsigned int) * 2 * n));
+  t->trunk_ctr_stride = tc_trunk_counter_ints(n);
+  HV_CUDA(cudaMalloc((void**)&t->trunk_ctr, sizeof(int) * t->trunk_ctr_stride * kNumLayers));
+  HV_CUDA(cudaMemset(t->trunk_ctr, 0, sizeof(int) * t->trunk_ctr_stride * kNumLayers));
   for (int i = 0; i < kNumLayers; ++i) t->out_buf[i] = -1;
   t->out_buf[PM1] = B_P1;
   for (int i = 0; i < kNumTcLayers; ++i) {
@@ -397,10 +420,11 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     if (use_aux) HV_CUDA(cudaEventRecord(g->ev_aux[1], ax));
   }
   // ---- coarse network
-  for (int l : {C1, C2, C3, C4, C5, C6, C7, C8, C9, C10}) RC(run(l, st));
-  RC(fork_aux(2));
+  auto chain = [&](std::initializer_list<int> ls, cudaStream_t s) -> int { return run_layers(g, ls.begin(), (int)ls.size(), n, s); };
+  for (int l : {C1, C2, C3, C4}) RC(run(l, st));
+  RC(chain({C5, C6, C7, C8, C9, C10, C11, C12}, st));   // the 64x64 trunk of the coarse network: one dataflow launch
+  RC(fork_aux(2));   // the height head reads conv10_atrous (:90-93); nothing of the trunk overwrites it
   RC(tc_gap_fc_sigmoid(view(B_C10), g->fc_w[0], g->fc_b[0], pred1_h, t->gap_partial, t->gap_ticket, ax));
-  for (int l : {C11, C12}) RC(run(l, st));
   if (use_aux) HV_CUDA(cudaStreamWaitEvent(st, g->ev_aux[1], 0));
   for (int l : {C20, C13, C14, C19, C15, C16}) RC(run(l, st));
   t->conv[C17].p.head0 = x_stage1; t->conv[C17].p.head1 = coarse_seg;
@@ -415,18 +439,20 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
   HV_CUDA(cudaEventRecord(g->ev_fork, st));
   HV_CUDA(cudaStreamWaitEvent(g->side, g->ev_fork, 0));
   cudaStream_t sa = g->side;
-  for (int l : {PM2, PM3, PM4, PM5, PM6}) RC(run(l, sa));
+  for (int l : {PM2, PM3, PM4}) RC(run(l, sa));
+  RC(chain({PM5, PM6}, sa));
   RC(ctx_attn_fwd_tc(view(B_P6), mask, view(B_CA), offsets, flow, 10.f, 1, per_sample_mask, t->ca_ws, sa, use_aux ? ax : nullptr,
                      use_aux ? &g->ev_aux[6] : nullptr));
-  RC(run(PM9, sa));
-  RC(run(PM10, sa));
+  RC(chain({PM9, PM10}, sa));
   HV_CUDA(cudaEventRecord(g->ev_join, sa));
-  for (int l : {F2, F3, F4, F5, F6, F7, F8, F9, F10}) RC(run(l, st));
+  for (int l : {F2, F3, F4, F5}) RC(run(l, st));
+  RC(chain({F6, F7, F8, F9, F10}, st));
   HV_CUDA(cudaStreamWaitEvent(st, g->ev_join, 0));
   RC(run(A11, st));
   RC(fork_aux(4));
   RC(tc_gap_fc_sigmoid(view(B_A11), g->fc_w[1], g->fc_b[1], pred2_h, t->gap_partial + g->max_batch * 8, t->gap_ticket + g->max_batch, ax));
-  for (int l : {A12, A19, A13, A14, A15, A16}) RC(run(l, st));
+  RC(chain({A12, A19}, st));
+  for (int l : {A13, A14, A15, A16}) RC(run(l, st));
   t->conv[A17].p.head0 = x_stage2; t->conv[A17].p.head1 = fine_seg;
   RC(run(A17, st));
   RC(join_aux(5));
@@ -580,13 +606,12 @@ int hv_generator_run_chain(hv_generator* g, int first, int count, int n, hv_stre
   HV_CHECK_ARG(g && g->tc, "generator_run_chain: needs a bf16 plan");
   if (!g->prepared) { set_error("generator_run_chain: call hv_generator_prepare first"); return HV_ERR_STATE; }
   HV_CHECK_ARG(n >= 1 && n <= g->max_batch && count >= 1 && first >= 0 && first + count <= kNumLayers, "generator_run_chain: bad range");
+  int layers[kNumLayers];
   for (int idx = first; idx < first + count; ++idx) {
     HV_CHECK_ARG(g->tc->has[idx] && g->tc->out_buf[idx] >= 0, "generator_run_chain: layer %d is not a stand-alone tensor-core conv", idx);
-    tc_set_batch(g->tc->conv[idx], n);
-    int rc = tc_conv_launch(g->tc->conv[idx], as_stream(stream));
-    if (rc) return rc;
+    layers[idx - first] = idx;
   }
-  return HV_OK;
+  return run_layers(g, layers, count, n, as_stream(stream));
 }
 
 long long hv_generator_read_tap(hv_generator* g, int idx, float* out, hv_stream_t stream) {

@@ -42,9 +42,9 @@ __device__ __forceinline__ uint8_t pl_ct_u8(float v) {   // (fake_B + 1) * 127.5
 
 __global__ void __launch_bounds__(256) pl_finish_kernel(const float* __restrict__ x2, const float* __restrict__ fine, const float* __restrict__ coarse,
                                                         const float* __restrict__ p1, const float* __restrict__ p2, uint8_t* __restrict__ ct,
-                                                        uint8_t* __restrict__ fine_u8, uint8_t* __restrict__ coarse_u8, float* __restrict__ heights, int n) {
+                                                        uint8_t* __restrict__ fine_u8, uint8_t* __restrict__ coarse_u8, float* __restrict__ heights, int n, int batch) {
   const int i4 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i4 < 2 * n) heights[i4] = i4 < n ? p1[i4] : p2[i4 - n];
+  if (i4 < n) { heights[i4] = p1[i4]; heights[batch + i4] = p2[i4]; }   // [2][batch] like the host view
   if (i4 >= n * (PL_HW / 4)) return;
   const float4 v = reinterpret_cast<const float4*>(x2)[i4], f = reinterpret_cast<const float4*>(fine)[i4], c = reinterpret_cast<const float4*>(coarse)[i4];
   reinterpret_cast<uchar4*>(ct)[i4] = make_uchar4(pl_ct_u8(v.x), pl_ct_u8(v.y), pl_ct_u8(v.z), pl_ct_u8(v.w));
@@ -98,7 +98,7 @@ static int pl_enqueue(hv_pipeline* p, Slot& s, int n) {
   if (rc) return rc;
   uint8_t* o_ct = s.d_out;
   pl_finish_kernel<<<blocks, 256, 0, p->s_main>>>(p->x2, p->fine, p->coarse, p->p1, p->p2, o_ct, o_ct + (size_t)B * PL_HW, o_ct + (size_t)B * PL_HW * 2,
-                                                   reinterpret_cast<float*>(o_ct + (size_t)B * PL_HW * 3), n);
+                                                   reinterpret_cast<float*>(o_ct + (size_t)B * PL_HW * 3), n, B);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }

@@ -584,6 +584,7 @@ class Generator(nn.Module):
     def read_tap(self, idx):
         """Activation of conv block ``idx`` (state_dict order; 47 = attention output) of the last forward."""
         L = _lib.lib()
-        buf = torch.empty(self._plan_key[2] * 16 * 256 * 256, device=self.coarse_generator.fc_height.weight.device)
+        # the largest activation per slice is 32 channels at 256 x 256 (conv19 / the merged fine conv1 | pmconv1 layer)
+        buf = torch.empty(self._plan_key[2] * 32 * 256 * 256, device=self.coarse_generator.fc_height.weight.device)
         cnt = check(L.hv_generator_read_tap(self._plan, idx, ptr(buf), _lib.stream()))
         return buf[:cnt].clone()
