@@ -53,7 +53,16 @@ struct TrunkParams {
   TrunkLayer layers[TR_MAX_LAYERS];
   int nlayers, total_items, n_images;
   int* counters;     // [0] queue head, [1] exit ticket, [2 + l * n_images + i] completion of image i of layer l
+  int debug;         // HV_TRUNK_DEBUG ablation bits (results are WRONG with any of them): 1 no dependency wait, 2 no proxy fence,
+                     // 4 no completion signal (needs 1), 8 no filter-bank reload after the first
+  long long* trace;  // per-role clock stamps of CTA `trace_cta` (hv_debug_trunk_trace), or null
+  int trace_cta;
 };
+
+// trace record: (tag, item, clock64); tags 1x producer, 2x issuer, 3x epilogue warp 0
+__device__ __forceinline__ void tr_ev(long long* tr, int& n, int tag, int item) {
+  if (tr && n < 1300) { tr[3 * n] = tag; tr[3 * n + 1] = item; tr[3 * n + 2] = clock64(); ++n; }
+}
 
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
@@ -109,15 +118,18 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
     if (lane == 0) {
       // the queue / completion counters were reset by the previous launch on them, the activations come from the predecessor
       asm volatile("griddepcontrol.wait;" ::: "memory");
-      int slot = 0, round = 0;
+      int slot = 0, round = 0, ntr = 0;
       uint32_t phase = 0;
       const uint32_t slots_base = smem_u32(s_slots);
+      long long* tr = (p.trace && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
       // the queue pull of the NEXT round is issued before this round's work: its L2 round trip (~0.4 us) stays off the
       // producer's critical path (one thread runs this loop; a tile lasts ~1.3 us)
       int item = atomicAdd(&p.counters[0], 1);
       while (true) {
         const int next = item < p.total_items ? atomicAdd(&p.counters[0], 1) : item;
+        tr_ev(tr, ntr, 10, item);
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+        tr_ev(tr, ntr, 11, item);
         const uint32_t fb = bar_full + 8u * slot;
         if (item >= p.total_items) {          // end of the queue: pass the sentinel down the pipeline
           s_item[round & (TR_RING - 1)] = -1;
@@ -130,7 +142,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
         const TrunkLayer& L = p.layers[l];
         const int tile = item - L.item_base;
         const int img = (int)(((unsigned long long)tile * L.tiles_magic) >> 40);
-        if (L.dep >= 0) {                     // image `img` of the producing layer must be complete (all its tiles stored)
+        if (L.dep >= 0 && !(p.debug & 1)) {   // image `img` of the producing layer must be complete (all its tiles stored)
           const int* flag = p.counters + 2 + L.dep * p.n_images + img;
           if (ld_acquire_gpu(flag) < L.dep_target) {
             const long long t0 = clock64();
@@ -139,13 +151,15 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
               if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug fails the launch instead of hanging the GPU
             }
           }
-          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other SMs -> this thread's TMA reads
+          tr_ev(tr, ntr, 12, item);
+          if (!(p.debug & 2)) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other SMs -> this thread's TMA reads
         }
         s_item[round & (TR_RING - 1)] = item;
         const int c_tile = 2 * ((tile - img * L.tiles_per_image) * L.tile_adv + L.q_first);   // tensor-map inner unit = 8 B
         const int rel2 = 2 * (-L.dil * L.in_pitch - L.dil);
         mbar_expect_tx(fb, TR_BAND_BYTES);
         tma_load_4d(slots_base + (uint32_t)slot * TR_BAND_BYTES, &p.maps[l], fb, c_tile + rel2, 0, 0, img);
+        tr_ev(tr, ntr, 13, item);
         ++round;
         if (++slot == TR_SLOTS) { slot = 0; phase ^= 1u; }
         item = next;
@@ -162,12 +176,16 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
     int slot = 0, acc = 0, round = 0, cur_layer = -1;
     uint32_t phase = 0, acc_phase = 0, w_phase = 0, wfree_phase = 0;
     uint32_t a_step = 1;
+    int ntr = 0;
+    long long* tr = (p.trace && (int)blockIdx.x == p.trace_cta && leader) ? p.trace + 4000 : nullptr;
     while (true) {
       mbar_wait(bar_full + 8u * slot, phase);
       tc_fence_after();
       const int item = s_item[round & (TR_RING - 1)];
+      tr_ev(tr, ntr, 20, item);
       mbar_wait(bar_tempty + 8u * acc, acc_phase ^ 1u);
       tc_fence_after();
+      tr_ev(tr, ntr, 21, item);
       if (item < 0) {                         // sentinel: wake the epilogue with it and stop
         if (leader) mbar_arrive(bar_tfull + 8u * acc);
         break;
@@ -175,7 +193,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
       int l = 0;
 #pragma unroll 1
       while (l + 1 < p.nlayers && item >= p.layers[l + 1].item_base) ++l;
-      if (l != cur_layer) {
+      if (l != cur_layer && !((p.debug & 8) && cur_layer >= 0)) {
         // layer switch of this CTA: wait for the MMAs still reading the old filter bank, then bring the new one (72 KB bulk copy)
         if (cur_layer >= 0) {
           if (leader) umma_commit(bar_wfree);
@@ -191,6 +209,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
         w_phase ^= 1u;
         cur_layer = l;
         a_step = (uint32_t)p.layers[l].dil;
+        tr_ev(tr, ntr, 22, item);
       }
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 64);
       const uint32_t a_row = a_lo_base + (uint32_t)slot * (TR_BAND_BYTES >> 4);
@@ -208,6 +227,7 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
         umma_commit(bar_empty + 8u * slot);   // the band slot is free once these MMAs have read it
         umma_commit(bar_tfull + 8u * acc);    // accumulator complete -> epilogue
       }
+      tr_ev(tr, ntr, 23, item);
       __syncwarp();
       ++round;
       if (++slot == TR_SLOTS) { slot = 0; phase ^= 1u; }
@@ -219,13 +239,15 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
     const int quad = warp & 3;
     const int col0 = (warp >> 2) * 16;
     const int m = quad * 32 + lane;
-    int acc = 0, round = 0;
+    int acc = 0, round = 0, ntr = 0;
     uint32_t acc_phase = 0;
+    long long* tr = (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0) ? p.trace + 8000 : nullptr;
     while (true) {
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
       const int item = s_item[round & (TR_RING - 1)];
       if (item < 0) break;
+      tr_ev(tr, ntr, 30, item);
       int l = 0;
 #pragma unroll 1
       while (l + 1 < p.nlayers && item >= p.layers[l + 1].item_base) ++l;
@@ -268,11 +290,13 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
           }
         }
       }
-      if (L.signal) {                         // publish: this warp's share of the tile is stored
+      tr_ev(tr, ntr, 31, item);
+      if (L.signal && !(p.debug & 4)) {       // publish: this warp's share of the tile is stored
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(p.counters + 2 + l * p.n_images + img, 1);
       }
+      tr_ev(tr, ntr, 32, item);
       ++round;
       if (++acc == TR_ACC) { acc = 0; acc_phase ^= 1u; }
     }
@@ -296,6 +320,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
 }
 
 // ------------------------------------------------------------------------------------------- host
+static long long* g_trunk_trace = nullptr;
+static int g_trunk_trace_cta = 0;
+void tc_trunk_set_trace(long long* dev_buf, int cta) { g_trunk_trace = dev_buf; g_trunk_trace_cta = cta; }
+
 bool tc_trunk_eligible(const TcConv& c) {
   const TcParams& p = c.p;
   return c.n_pad == 64 && c.k == 3 && c.stride == 1 && c.nsrc == 1 && !c.src[0].kxpack && c.src[0].buf.chunks == 8 && c.src[0].buf.xp == 1 &&
@@ -336,6 +364,8 @@ int tc_trunk_launch(const TcConv* const* convs, int count, int n_images, int* co
     }
   }
   q.nlayers = count; q.total_items = base; q.n_images = n_images; q.counters = counters;
+  static const int debug = getenv("HV_TRUNK_DEBUG") ? atoi(getenv("HV_TRUNK_DEBUG")) : 0;
+  q.debug = debug; q.trace = g_trunk_trace; q.trace_cta = g_trunk_trace_cta;
   static bool configured = false;
   if (!configured) {
     HV_CUDA(cudaFuncSetAttribute(trunk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TR_SMEM));
@@ -364,3 +394,10 @@ int tc_trunk_launch(const TcConv* const* convs, int count, int n_images, int* co
 }
 
 }  // namespace hv
+
+// debug hook (not part of the drop-in surface): dev_buf = 12000 int64 on the device (3 roles x 1300 records of (tag, item, clock)),
+// or NULL to switch tracing off; the CTA with index `cta` of every subsequent trunk launch records
+extern "C" int hv_debug_trunk_trace(void* dev_buf, int cta) {
+  hv::tc_trunk_set_trace(reinterpret_cast<long long*>(dev_buf), cta);
+  return HV_OK;
+}
