@@ -699,6 +699,70 @@ int adam_step(float* p, const float* g, float* m, float* v, size_t count, float 
   return HV_OK;
 }
 
+// ------------------------------------------------------------------ multi-tensor variants: ONE launch per optimiser / gradient bucket
+// table rows (device, int64): {p, g, m, v, count, first_chunk} for Adam; {ptr, -, -, -, count, first_chunk} + flat offset = first_chunk *
+// MT_CHUNK for the gradient bucket (every tensor starts on a chunk boundary of the flat buffer).  A CTA owns one MT_CHUNK-element chunk
+// and finds its tensor by bisection over first_chunk.
+constexpr int MT_CHUNK = 4096;
+struct MtRow { long long p, g, m, v, count, first_chunk; };
+
+__device__ __forceinline__ int mt_find(const MtRow* __restrict__ rows, int n, long long chunk) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (rows[mid].first_chunk <= chunk) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) adam_multi_kernel(const MtRow* __restrict__ rows, int n, float lr, float b1, float b2, float eps, float bc1,
+                                                         float bc2_sqrt) {
+  const MtRow r = rows[mt_find(rows, n, blockIdx.x)];
+  float* p = reinterpret_cast<float*>(r.p);
+  const float* g = reinterpret_cast<const float*>(r.g);
+  float* m = reinterpret_cast<float*>(r.m);
+  float* v = reinterpret_cast<float*>(r.v);
+  const long long base = ((long long)blockIdx.x - r.first_chunk) * MT_CHUNK;
+  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+    const long long i = base + k;
+    if (i >= r.count) break;
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= (lr / bc1) * (mi / denom);
+  }
+}
+
+// to_flat != 0: flat[first_chunk * MT_CHUNK + i] = t[i];  else: t[i] = scale * flat[...]
+__global__ void __launch_bounds__(256) bucket_copy_kernel(const MtRow* __restrict__ rows, int n, float* __restrict__ flat, float scale, int to_flat) {
+  const MtRow r = rows[mt_find(rows, n, blockIdx.x)];
+  float* t = reinterpret_cast<float*>(r.p);
+  const long long base = ((long long)blockIdx.x - r.first_chunk) * MT_CHUNK;
+  float* f = flat + (long long)blockIdx.x * MT_CHUNK;
+  for (int k = threadIdx.x; k < MT_CHUNK; k += 256) {
+    const long long i = base + k;
+    if (i >= r.count) { if (to_flat) f[k] = 0.f; continue; }
+    if (to_flat) f[k] = t[i]; else t[i] = scale * f[k];
+  }
+}
+
+int adam_step_multi(const void* table, int n, long long chunks, float lr, float b1, float b2, float eps, int step, cudaStream_t st) {
+  HV_CHECK_ARG(table && n >= 1 && chunks >= 1 && chunks < (1ll << 31) && step >= 1, "adam_step_multi: bad argument");
+  const float bc1 = 1.f - powf(b1, (float)step), bc2 = 1.f - powf(b2, (float)step);
+  adam_multi_kernel<<<(unsigned)chunks, 256, 0, st>>>(static_cast<const MtRow*>(table), n, lr, b1, b2, eps, bc1, sqrtf(bc2));
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
+int bucket_copy(const void* table, int n, long long chunks, float* flat, float scale, int to_flat, cudaStream_t st) {
+  HV_CHECK_ARG(table && flat && n >= 1 && chunks >= 1 && chunks < (1ll << 31), "bucket_copy: bad argument");
+  bucket_copy_kernel<<<(unsigned)chunks, 256, 0, st>>>(static_cast<const MtRow*>(table), n, flat, scale, to_flat);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 }  // namespace hv
 
 // =============================================================================== C ABI
@@ -754,6 +818,13 @@ int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, floa
 }
 int hv_adam_step(float* p, const float* g, float* m, float* v, size_t count, float lr, float b1, float b2, float eps, int step, hv_stream_t s) {
   return adam_step(p, g, m, v, count, lr, b1, b2, eps, step, as_stream(s));
+}
+int hv_multi_tensor_chunk(void) { return MT_CHUNK; }
+int hv_adam_step_multi(const void* table, int n, long long chunks, float lr, float b1, float b2, float eps, int step, hv_stream_t s) {
+  return adam_step_multi(table, n, chunks, lr, b1, b2, eps, step, as_stream(s));
+}
+int hv_bucket_copy(const void* table, int n, long long chunks, float* flat, float scale, int to_flat, hv_stream_t s) {
+  return bucket_copy(table, n, chunks, flat, scale, to_flat, as_stream(s));
 }
 
 }  // extern "C"

@@ -142,22 +142,23 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
         const TrunkLayer& L = p.layers[l];
         const int tile = item - L.item_base;
         const int img = (int)(((unsigned long long)tile * L.tiles_magic) >> 40);
+        s_item[round & (TR_RING - 1)] = item;
+        mbar_expect_tx(fb, TR_BAND_BYTES);    // arms the barrier (release: the item id above is visible to whoever sees the phase complete)
         if (L.dep >= 0 && !(p.debug & 1)) {   // image `img` of the producing layer must be complete (all its tiles stored)
           const int* flag = p.counters + 2 + L.dep * p.n_images + img;
           if (ld_acquire_gpu(flag) < L.dep_target) {
             const long long t0 = clock64();
             while (ld_acquire_gpu(flag) < L.dep_target) {
-              __nanosleep(64);
+              __nanosleep(32);
               if (clock64() - t0 > 4000000000ll) __trap();   // a protocol bug fails the launch instead of hanging the GPU
             }
           }
           tr_ev(tr, ntr, 12, item);
-          if (!(p.debug & 2)) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of other SMs -> this thread's TMA reads
+          // generic-proxy stores of other SMs (observed through the acquire above) -> this thread's async-proxy (TMA) reads of global memory
+          if (!(p.debug & 2)) asm volatile("fence.proxy.async.global;" ::: "memory");
         }
-        s_item[round & (TR_RING - 1)] = item;
         const int c_tile = 2 * ((tile - img * L.tiles_per_image) * L.tile_adv + L.q_first);   // tensor-map inner unit = 8 B
         const int rel2 = 2 * (-L.dil * L.in_pitch - L.dil);
-        mbar_expect_tx(fb, TR_BAND_BYTES);
         tma_load_4d(slots_base + (uint32_t)slot * TR_BAND_BYTES, &p.maps[l], fb, c_tile + rel2, 0, 0, img);
         tr_ev(tr, ntr, 13, item);
         ++round;
@@ -242,7 +243,22 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
     int acc = 0, round = 0, ntr = 0;
     uint32_t acc_phase = 0;
     long long* tr = (p.trace && (int)blockIdx.x == p.trace_cta && threadIdx.x == 0) ? p.trace + 8000 : nullptr;
+    // Completion signal of a tile = fence (the warp's stores are performed at GPU scope) + one RED on the image's counter.  The fence
+    // stalls the warp until its outstanding stores are acknowledged (~1 us right after they were issued), which would double the
+    // epilogue's time per tile; it is therefore issued one round LATER, just before the next tile's stores (by then the old stores
+    // have landed and the fence is cheap) - or at once when the warp would otherwise sit idle waiting for the next accumulator
+    // (which also makes the delay deadlock-free: a warp never blocks with an unpublished tile).
+    int* pend = nullptr;
+    auto flush = [&]() {
+      if (pend) {
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(pend, 1);
+        pend = nullptr;
+      }
+    };
     while (true) {
+      if (pend && !__all_sync(0xffffffffu, mbar_peek(bar_tfull + 8u * acc, acc_phase))) flush();
       mbar_wait(bar_tfull + 8u * acc, acc_phase);
       tc_fence_after();
       const int item = s_item[round & (TR_RING - 1)];
@@ -263,9 +279,9 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
       tmem_ld_wait();
       tc_fence_before();
       mbar_arrive(bar_tempty + 8u * acc);     // this warp's slice is in registers
-      if (valid) {
+      uint4 val[2];
+      {
         const float* bias = s_bias + l * 64 + col0;
-        __nv_bfloat16* out_img = L.out + (size_t)img * L.out_chunks_total * L.out_plane * 8;
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           uint32_t pk[4];
@@ -277,29 +293,34 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
             __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
             pk[e] = *reinterpret_cast<uint32_t*>(&h);
           }
-          const uint4 val = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          val[jj] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      flush();                                 // the previous tile of this warp (its stores were issued a round ago)
+      if (valid) {
+        __nv_bfloat16* out_img = L.out + (size_t)img * L.out_chunks_total * L.out_plane * 8;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
           __nv_bfloat16* plane = out_img + (size_t)((col0 >> 3) + jj) * L.out_plane * 8;
           if (L.up2) {   // nearest x2 upsample fused into the store (inpaint_networks.py:97, :219)
             const size_t o = (size_t)(2 * yy + L.out_border) * L.out_pitch + 2 * xx + L.out_border;
-            *reinterpret_cast<uint4*>(plane + o * 8) = val;
-            *reinterpret_cast<uint4*>(plane + (o + 1) * 8) = val;
-            *reinterpret_cast<uint4*>(plane + (o + L.out_pitch) * 8) = val;
-            *reinterpret_cast<uint4*>(plane + (o + L.out_pitch + 1) * 8) = val;
+            *reinterpret_cast<uint4*>(plane + o * 8) = val[jj];
+            *reinterpret_cast<uint4*>(plane + (o + 1) * 8) = val[jj];
+            *reinterpret_cast<uint4*>(plane + (o + L.out_pitch) * 8) = val[jj];
+            *reinterpret_cast<uint4*>(plane + (o + L.out_pitch + 1) * 8) = val[jj];
           } else {
-            *reinterpret_cast<uint4*>(plane + ((size_t)(yy + L.out_border) * L.out_pitch + xx + L.out_border) * 8) = val;
+            *reinterpret_cast<uint4*>(plane + ((size_t)(yy + L.out_border) * L.out_pitch + xx + L.out_border) * 8) = val[jj];
           }
         }
       }
       tr_ev(tr, ntr, 31, item);
-      if (L.signal && !(p.debug & 4)) {       // publish: this warp's share of the tile is stored
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(p.counters + 2 + l * p.n_images + img, 1);
-      }
+      if (L.signal && !(p.debug & 4)) pend = p.counters + 2 + l * p.n_images + img;
+      if (p.debug & 16) flush();               // ablation: publish at once (the fence then waits for the stores just issued)
       tr_ev(tr, ntr, 32, item);
       ++round;
       if (++acc == TR_ACC) { acc = 0; acc_phase ^= 1u; }
     }
+    flush();
   }
   tc_fence_before();
   __syncthreads();

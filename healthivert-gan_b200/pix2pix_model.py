@@ -101,6 +101,7 @@ class Pix2PixModel(BaseModel):
             raise _lib.HvError("hv_b200 Pix2PixModel needs a CUDA device (no CPU fallback)")
         self.netG = Generator({"input_dim": 1, "ngf": 16}, True).to(self.device)
         self.sobel_edge = Sobel(requires_grad=False).to(self.device)
+        self._buckets = {}
         self.world_size = 1          # set by the launcher for data-parallel training (gradient all-reduce)
         if self.isTrain:
             mk = lambda: networks.define_D(opt.input_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, opt.init_type,
@@ -176,12 +177,14 @@ class Pix2PixModel(BaseModel):
         return out
 
     # ------------------------------------------------------------------------------------------ D updates
-    def _allreduce(self, params):
-        """Data-parallel gradient exchange: one all-reduce(mean) per parameter tensor after each net's backward
-        (4 per step: D_1, D_2, D_3, G), NCCL over NVLink when launched under torchrun."""
-        from . import sharding
-        scale = lambda t, f: check(_lib.lib().hv_axpby(0.0, None, float(f), ptr(t), t.numel(), _lib.stream()))
-        sharding.allreduce_mean_([p.grad for p in params if p.grad is not None], self.world_size, scale)
+    def _allreduce(self, params, tag="G"):
+        """Data-parallel gradient exchange: ONE all-reduce per net on a flat gradient bucket (4 per step: D_1, D_2, D_3, G; NCCL over
+        NVLink when launched under torchrun), averaged on the way back (train_ops.GradientBucket)."""
+        if self.world_size <= 1:
+            return
+        import torch.distributed as dist
+        bucket = self._buckets.setdefault(tag, T.GradientBucket())
+        bucket.allreduce_mean_([p.grad for p in params if p.grad is not None], self.world_size, dist.all_reduce)
 
     def _backward_D(self, netD, fake, real, idx):
         """reference backward_D_k (:267-314): 0.5 * (BCE(D(fake.detach()), 0) + BCE(D(real), 1)), gradients into netD."""
@@ -293,10 +296,10 @@ class Pix2PixModel(BaseModel):
             self.set_requires_grad(net, True)
             opt_.zero_grad()
             bwd()
-            self._allreduce(net.parameters())
+            self._allreduce(net.parameters(), "D_%d" % (k + 1))
             opt_.step()
         self.set_requires_grad([self.netD_1, self.netD_2, self.netD_3], False)
         self.optimizer_G.zero_grad()
         self.backward_G()
-        self._allreduce(self.netG.parameters())
+        self._allreduce(self.netG.parameters(), "G")
         self.optimizer_G.step()

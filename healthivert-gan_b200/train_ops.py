@@ -284,13 +284,51 @@ def dice_grad(gt, sums, g_out, eps=1e-5):
     return d
 
 
+class TensorTable:
+    """Device table of the multi-tensor kernels (hv_adam_step_multi / hv_bucket_copy): n rows of six int64
+    {p, g, m, v, count, first_chunk}.  The table is re-uploaded only when a pointer changed (gradient tensors are re-allocated every
+    step, but the caching allocator hands the same blocks back once the step's allocation pattern has settled)."""
+
+    def __init__(self):
+        self.rows = None
+        self.dev = None
+        self.host = None
+        self.chunks = 0
+
+    def update(self, cols, counts, device):
+        import numpy as np
+        chunk = _L().hv_multi_tensor_chunk()
+        first, c = [], 0
+        for k in counts:
+            first.append(c)
+            c += (k + chunk - 1) // chunk
+        rows = [tuple(col[i] for col in cols) + (counts[i], first[i]) for i in range(len(counts))]
+        if rows != self.rows:
+            arr = np.array(rows, dtype=np.int64)
+            if self.host is None or self.host.shape != arr.shape:
+                self.host = torch.empty(arr.shape, dtype=torch.int64).pin_memory()
+                self.dev = torch.empty(arr.shape, dtype=torch.int64, device=device)
+            else:
+                torch.cuda.current_stream(device).synchronize()   # a previous async upload may still read the pinned staging
+            self.host.copy_(torch.from_numpy(arr))
+            self.dev.copy_(self.host, non_blocking=True)
+            self.rows = rows
+            self.chunks = c
+        return self.dev, len(rows), self.chunks
+
+
 class FusedAdam:
-    """torch.optim.Adam(lr, betas) semantics (pix2pix_model.py:127-130) on hv_adam_step; state keys mirror torch's."""
+    """torch.optim.Adam(lr, betas) semantics (pix2pix_model.py:127-130); state keys mirror torch's.  ONE kernel launch per step for
+    all parameters of the optimiser (hv_adam_step_multi); HV_ADAM_PER_TENSOR=1 keeps the one-launch-per-tensor path (A/B)."""
 
     def __init__(self, params, lr=2e-4, betas=(0.5, 0.999), eps=1e-8):
+        import os
         self.params = [p for p in params]
         self.param_groups = [{"params": self.params, "lr": lr, "initial_lr": lr, "betas": betas, "eps": eps}]
         self.state = {}
+        self._table = TensorTable()
+        self._step = 0
+        self._per_tensor = os.environ.get("HV_ADAM_PER_TENSOR") == "1"
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -299,16 +337,54 @@ class FusedAdam:
     @torch.no_grad()
     def step(self):
         g = self.param_groups[0]
-        for p in self.params:
-            if p.grad is None:
-                continue
-            st = self.state.get(p)
-            if st is None:
-                st = self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
-            st["step"] += 1
-            grad = p.grad.contiguous()
-            check(_L().hv_adam_step(ptr(p.data), ptr(grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(g["lr"]),
-                                    float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), int(st["step"]), _lib.stream()))
-            # the kernel wrote through a raw pointer: tell torch (and the Generator's cached-plan signature, which compares
+        live = [p for p in self.params if p.grad is not None]
+        if not live:
+            return
+        for p in live:
+            if p not in self.state:
+                self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+        steps = {self.state[p]["step"] for p in live}
+        if self._per_tensor or len(steps) != 1:   # parameters with different step counts (some had no gradient earlier): per tensor
+            for p in live:
+                st = self.state[p]
+                st["step"] += 1
+                grad = p.grad.contiguous()
+                check(_L().hv_adam_step(ptr(p.data), ptr(grad), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(g["lr"]),
+                                        float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]), int(st["step"]), _lib.stream()))
+                torch.autograd.graph.increment_version(p)
+            return
+        grads = [p.grad if p.grad.is_contiguous() else p.grad.contiguous() for p in live]
+        cols = ([ptr(p.data) for p in live], [ptr(t) for t in grads], [ptr(self.state[p]["exp_avg"]) for p in live],
+                [ptr(self.state[p]["exp_avg_sq"]) for p in live])
+        table, n, chunks = self._table.update(cols, [p.numel() for p in live], live[0].device)
+        step = steps.pop() + 1
+        check(_L().hv_adam_step_multi(ptr(table), n, chunks, float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                      int(step), _lib.stream()))
+        for p in live:
+            self.state[p]["step"] = step
+            # the kernel wrote through raw pointers: tell torch (and the Generator's cached-plan signature, which compares
             # tensor._version) that the parameter changed in place, exactly as an eager optimizer step would
             torch.autograd.graph.increment_version(p)
+
+
+class GradientBucket:
+    """One flat fp32 buffer per net for the data-parallel gradient exchange (4 all-reduces per step, not one per tensor):
+    gather (1 launch) -> all_reduce(SUM) on the flat buffer (NCCL over NVLink) -> scatter scaled by 1 / world (1 launch)."""
+
+    def __init__(self):
+        self._table = TensorTable()
+        self.flat = None
+
+    @torch.no_grad()
+    def allreduce_mean_(self, grads, world, all_reduce):
+        if world <= 1 or not grads:
+            return
+        grads = [t if t.is_contiguous() else t.contiguous() for t in grads]
+        zero = [0] * len(grads)
+        table, n, chunks = self._table.update(([ptr(t) for t in grads], zero, zero, zero), [t.numel() for t in grads], grads[0].device)
+        size = chunks * _L().hv_multi_tensor_chunk()
+        if self.flat is None or self.flat.numel() != size:
+            self.flat = torch.empty(size, device=grads[0].device, dtype=torch.float32)
+        check(_L().hv_bucket_copy(ptr(table), n, chunks, ptr(self.flat), 1.0, 1, _lib.stream()))
+        all_reduce(self.flat)
+        check(_L().hv_bucket_copy(ptr(table), n, chunks, ptr(self.flat), 1.0 / world, 0, _lib.stream()))

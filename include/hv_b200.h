@@ -279,6 +279,16 @@ int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, floa
 /* ---- A8: torch.optim.Adam step (pix2pix_model.py:127-130), fused, in place */
 int hv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
                  float beta1, float beta2, float eps, int step, hv_stream_t stream);
+/* multi-tensor variants: ONE launch for all parameters of an optimiser / all gradients of a net.
+ * table: DEVICE array of n rows of six int64 {param, grad, exp_avg, exp_avg_sq, count, first_chunk}; tensor r owns the chunks
+ * [first_chunk_r, first_chunk_r + ceil(count_r / hv_multi_tensor_chunk())) of `chunks` chunks in total, rows sorted by first_chunk. */
+int hv_multi_tensor_chunk(void);
+int hv_adam_step_multi(const void* table, int n, long long chunks, float lr, float beta1, float beta2, float eps, int step,
+                       hv_stream_t stream);
+/* gradient bucket of the data-parallel step (4 all-reduces per step: D_1, D_2, D_3, G): to_flat != 0 gathers the
+ * tensors (row field `param`) into flat[chunks * chunk] (tensor r at first_chunk_r * chunk, padding zeroed); to_flat == 0
+ * scatters scale * flat back.  The collective on `flat` in between is torch.distributed / NCCL.                               */
+int hv_bucket_copy(const void* table, int n, long long chunks, float* flat, float scale, int to_flat, hv_stream_t stream);
 
 /* ======================================================================================
  * A9 / N1: device-side slice preparation and post-processing of the iterative eval loop

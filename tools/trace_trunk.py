@@ -14,7 +14,8 @@ import healthivert_gan_b200 as hv
 from healthivert_gan_b200 import _lib
 from oracle import synth
 
-cta = int(sys.argv[1]) if len(sys.argv) > 1 else 0
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+cta = int(args[0]) if args else 0
 torch.cuda.set_device(0)
 g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
 g.load_state_dict(synth.synthetic_generator_state_dict())
