@@ -32,6 +32,7 @@ struct GemmParams {
   const float* colscale;    // [batch][N] or null
   int M, N, K, batch;
   int tiles_m, tiles_n, total_tiles, kblocks;
+  int a_bcast;              // A is shared by every batch entry (batch stride 0): its tensor map has a batch extent of 1
 };
 
 template <int BN, bool OUT_BF16>
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         if (leader) {
           const uint32_t fb = bar_full + 8u * slot, dst = ring + (uint32_t)slot * STAGE_BYTES;
           mbar_expect_tx(fb, STAGE_BYTES);
-          tma_load_3d(dst, &p.map_a, fb, kb * G_BK, mt * G_BM, b);
+          tma_load_3d(dst, &p.map_a, fb, kb * G_BK, mt * G_BM, p.a_bcast ? 0 : b);
           tma_load_3d(dst + A_BYTES, &p.map_b, fb, kb * G_BK, nt * BN, b);
         }
         if (++slot == G_STAGES) { slot = 0; phase ^= 1u; }
@@ -202,6 +203,7 @@ static PFN_encodeTiled gemm_get_encode() {
 static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int batch, long long batch_stride_elems, int box_rows) {
   PFN_encodeTiled enc = gemm_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return HV_ERR_CUDA; }
+  if (batch_stride_elems == 0) { batch = 1; batch_stride_elems = (long long)rows * K; }   // broadcast operand
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
   cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)batch_stride_elems * 2};
   cuuint32_t box[3] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows, 1};
@@ -255,7 +257,7 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
     next = (next + 1) % 4;
     e = Cached{A, B, M, N, K, batch, bn, strideA, strideB, p.map_a, p.map_b};
   }
-  p.c = C; p.colscale = colscale; p.M = M; p.N = N; p.K = K; p.batch = batch;
+  p.c = C; p.colscale = colscale; p.M = M; p.N = N; p.K = K; p.batch = batch; p.a_bcast = strideA == 0 ? 1 : 0;
   p.tiles_m = M / G_BM; p.tiles_n = N / bn; p.total_tiles = p.tiles_m * p.tiles_n * batch; p.kblocks = K / G_BK;
   static int sms = 0;
   if (!sms) {

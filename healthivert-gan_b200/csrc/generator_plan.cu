@@ -275,11 +275,15 @@ struct TcPlan {
   size_t trunk_ctr_stride = 0;
 };
 
-// a run of consecutive 64 -> 64 trunk layers as ONE dataflow launch (trunk_tc.cu); HV_NO_TRUNK=1 falls back to one launch per layer
+// A run of consecutive 64 -> 64 trunk layers, either one launch per layer (programmatic dependent launches) or ONE dataflow launch
+// (trunk_tc.cu).  Measured on B200 (profiles/r2_trunk_dataflow.md): at batch 16 a layer is only 3.7 tile rounds per SM, less than the
+// dependency hop (TMA + MMA + epilogue + publish ~ 3 rounds): the dataflow kernel needs 17 us per layer against 11 us for separate
+// launches, so it is used from HV_TRUNK_MIN_BATCH images on (default: never; HV_TRUNK=1 forces it, for A/B runs and the parity tests).
 static int run_layers(hv_generator* g, const int* layers, int count, int n, cudaStream_t st) {
   TcPlan* t = g->tc;
-  static const bool no_trunk = getenv("HV_NO_TRUNK") != nullptr;
-  bool ok = !no_trunk && count >= 2 && count <= 8;
+  static const int force = getenv("HV_TRUNK") ? atoi(getenv("HV_TRUNK")) : 0;
+  static const int min_batch = getenv("HV_TRUNK_MIN_BATCH") ? atoi(getenv("HV_TRUNK_MIN_BATCH")) : (1 << 30);
+  bool ok = (force == 1 || n >= min_batch) && count >= 2 && count <= 8;
   const TcConv* convs[8];
   for (int i = 0; i < count; ++i) {
     tc_conv_set_batch(t->conv[layers[i]], n);

@@ -124,9 +124,10 @@ __global__ void __launch_bounds__(TR_THREADS, 1) trunk_tc_kernel(const __grid_co
       long long* tr = (p.trace && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
       // the queue pull of the NEXT round is issued before this round's work: its L2 round trip (~0.4 us) stays off the
       // producer's critical path (one thread runs this loop; a tile lasts ~1.3 us)
-      int item = atomicAdd(&p.counters[0], 1);
+      const bool static_q = (p.debug & 32) != 0;   // ablation: static round-robin assignment instead of the atomic queue
+      int item = static_q ? (int)blockIdx.x : atomicAdd(&p.counters[0], 1);
       while (true) {
-        const int next = item < p.total_items ? atomicAdd(&p.counters[0], 1) : item;
+        const int next = static_q ? item + (int)gridDim.x : (item < p.total_items ? atomicAdd(&p.counters[0], 1) : item);
         tr_ev(tr, ntr, 10, item);
         mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
         tr_ev(tr, ntr, 11, item);

@@ -107,6 +107,10 @@ class Pix2PixModel(BaseModel):
             mk = lambda: networks.define_D(opt.input_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, opt.init_type,
                                            opt.init_gain, self.gpu_ids).to(self.device)
             self.netD_1, self.netD_2, self.netD_3 = mk(), mk(), mk()
+            # 'fp32' = parity mode; 'bf16' = discriminator convolutions on the tensor cores (opt.d_precision, default fp32)
+            self.d_precision = getattr(opt, "d_precision", "fp32")
+            for net in (self.netD_1, self.netD_2, self.netD_3):
+                net.precision = self.d_precision
             self.criterionGAN = networks.GANLoss(opt.gan_mode).to(self.device)
             adam = lambda net: T.FusedAdam(net.parameters(), lr=opt.lr, betas=(opt.beta1, 0.999))
             self.optimizer_G, self.optimizer_D_1 = adam(self.netG), adam(self.netD_1)

@@ -134,6 +134,45 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
     return out
 
 
+def conv2d_tc(tape, x, weight, stride, on_weight_grad, param_grads=True):
+    """4x4 / padding-1 convolution without bias or activation (the BatchNorm-followed PatchGAN layers, models/networks.py:583-597) on
+    the tensor cores: bf16 operands, fp32 accumulation (hv_dconv_fwd_bf16 / hv_dconv_bwd_bf16).  x: Var [n,cin,h,w]; weight: fp32
+    [cout,cin,4,4].  The backward recomputes the im2col operand from x instead of keeping it alive."""
+    n, cin, h, w = x.data.shape
+    cout = weight.shape[0]
+    ho, wo = (h + 2 - 4) // stride + 1, (w + 2 - 4) // stride + 1
+    L = _L()
+    dev = x.data.device
+    nbytes = L.hv_dconv_workspace_bytes(n, cin, cout, h, w, stride)
+    if nbytes == 0:
+        raise _lib.HvError(f"conv2d_tc: unsupported geometry cin={cin} cout={cout} stride={stride}")
+    ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+    y = torch.empty(n, cout, ho, wo, device=dev, dtype=torch.float32)
+    check(L.hv_dconv_fwd_bf16(ptr(x.data), ptr(weight), ptr(y), n, cin, cout, h, w, stride, ptr(ws), _lib.stream()))
+    out = Var(y)
+    if tape is None:
+        return out
+
+    def bwd():
+        if out.grad is None:
+            return
+        need_dx = x.requires_grad
+        if not (need_dx or param_grads):
+            return
+        ws2 = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+        dx = torch.empty_like(x.data) if need_dx else None
+        dw = torch.empty_like(weight) if param_grads else None
+        check(L.hv_dconv_bwd_bf16(ptr(x.data), ptr(weight), ptr(out.grad.contiguous()), ptr(dx), ptr(dw), n, cin, cout, h, w, stride,
+                                  ptr(ws2), _lib.stream()))
+        if param_grads:
+            on_weight_grad(dw, None)
+        if need_dx:
+            accumulate(x, dx)
+
+    tape.record(bwd)
+    return out
+
+
 def gap_fc_sigmoid(tape, x, fc):
     """sigmoid(fc(mean_HW(x))) (reference inpaint_networks.py:90-93,:211-214); fc: nn.Linear(c, 1)."""
     n, c, h, w = x.data.shape

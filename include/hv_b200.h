@@ -276,6 +276,16 @@ int hv_dice_fwd(const float* pred, const float* gt, float* sums, float* dice_n, 
 int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, float* dpred, int n, int per,
                 int accumulate, hv_stream_t stream);
 
+/* ---- A7 on the tensor cores: the BatchNorm-followed PatchGAN convolutions (nn.Conv2d(k=4, padding=1, stride 1|2, bias=False),
+ * models/networks.py:583-597) with bf16 operands and fp32 accumulation: batched tcgen05 GEMMs over explicit im2col operands.
+ * Cin % 8 == 0, Cout % 128 == 0.  x [n,cin,h,w], w [cout,cin,4,4], y / dy [n,cout,ho,wo] fp32.  workspace:
+ * hv_dconv_workspace_bytes(...) bytes (0 = unsupported geometry).  bwd: dx and / or dw may be NULL; x may be NULL when dw is.   */
+size_t hv_dconv_workspace_bytes(int n, int cin, int cout, int h, int w, int stride);
+int hv_dconv_fwd_bf16(const float* x, const float* w, float* y, int n, int cin, int cout, int h, int wd, int stride,
+                      void* workspace, hv_stream_t stream);
+int hv_dconv_bwd_bf16(const float* x, const float* w, const float* dy, float* dx, float* dw, int n, int cin, int cout, int h,
+                      int wd, int stride, void* workspace, hv_stream_t stream);
+
 /* ---- A8: torch.optim.Adam step (pix2pix_model.py:127-130), fused, in place */
 int hv_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t count, float lr,
                  float beta1, float beta2, float eps, int step, hv_stream_t stream);

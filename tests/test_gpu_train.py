@@ -277,6 +277,61 @@ def test_two_training_steps_against_reference_golden(golden_dir):
     assert np.abs(got2 - ref2).max() <= 0.05 * np.maximum(1.0, np.abs(ref2)).max(), dict(zip(names, zip(got2, ref2)))
 
 
+@pytest.mark.parametrize("n,cin,cout,h,stride", [(2, 64, 128, 128, 2), (3, 128, 256, 64, 2), (2, 256, 512, 32, 1), (1, 8, 128, 21, 1)])
+def test_dconv_tc_against_torch_on_bf16_rounded_operands(n, cin, cout, h, stride):
+    """The PatchGAN 4x4 convolutions on the tensor cores (hv_dconv_fwd_bf16 / hv_dconv_bwd_bf16: im2col + tcgen05 GEMMs, bf16 operands,
+    fp32 accumulation) against fp64 torch on the bf16-ROUNDED operands (models/networks.py:583-597 geometries + a ragged one: 21 x 21
+    input -> 20 x 20 = 400 pixels, padded to 512 inside)."""
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float64)
+    g = torch.Generator().manual_seed(cin + cout)
+    x = torch.randn(n, cin, h, h, generator=g)
+    w = torch.randn(cout, cin, 4, 4, generator=g) * 0.02
+    xr, wr = bf(x).requires_grad_(), bf(w).requires_grad_()
+    want = F.conv2d(xr, wr, None, stride=stride, padding=1)
+    dy = torch.randn(want.shape, generator=g)
+    want.backward(bf(dy))
+    tape = T.Tape()
+    xv = T.Var(x.cuda())
+    got = {}
+    y = T.conv2d_tc(tape, xv, w.cuda(), stride, lambda dw, db: got.update(dw=dw))
+    y.grad = dy.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    close = lambda a, b, tol: float((a.double().cpu() - b).abs().max()) <= tol * float(b.abs().max())
+    assert y.data.shape == want.shape
+    assert close(y.data, want.detach(), 1e-4)                 # fp32 accumulation of exact bf16 products
+    assert close(got["dw"], wr.grad, 2e-4)                    # per-image fp32 partial sums, then summed over the batch
+    assert close(xv.grad, xr.grad, 1.5e-2)                    # the per-tap gradient planes are stored in bf16 before the col2im sum
+    assert rel(xv.grad, xr.grad) <= 4e-3 and rel(got["dw"], wr.grad) <= 1e-4
+
+
+def test_training_step_with_tensor_core_discriminators(golden_dir):
+    """d_precision = 'bf16' (PatchGAN convolutions on tcgen05) against the same golden step of the unmodified reference, at bf16
+    tolerances: losses within 1 %, gradient norms within 3 %, the generator forward (fp32) unchanged."""
+    gold = np.load(os.path.join(golden_dir, "train_step_n2.npz"))
+    opt = synth.train_options(gpu_ids=[0], d_precision="bf16")
+    m = Pix2PixModel(opt)
+    m.setup(opt)
+    m.netG.load_state_dict(synth.synthetic_generator_state_dict())
+    for k, net in enumerate((m.netD_1, m.netD_2, m.netD_3), start=1):
+        net.load_state_dict(synth.synthetic_discriminator_state_dict(seed=k))
+        assert net.precision == "bf16"
+    m.train()
+    m.set_input(synth.synthetic_train_batch(n=2, seed=7))
+    m.optimize_parameters()
+    torch.cuda.synchronize()
+    names = [str(s) for s in gold["loss_names"]]
+    got = np.array([m.get_current_losses()[k] for k in names])
+    ref = gold["losses_step1"]
+    assert np.abs(got - ref).max() <= 1e-2 * np.maximum(1.0, np.abs(ref)).max(), dict(zip(names, zip(got, ref)))
+    assert np.abs(probe(m.fake_B) - gold["fake_B_probe"]).max() <= 1e-4
+    for tag, net in (("D_1", m.netD_1), ("D_2", m.netD_2), ("D_3", m.netD_3), ("G", m.netG)):
+        params = dict(net.named_parameters())
+        for i, name in enumerate(str(s) for s in gold[f"{tag}_names"]):
+            gn, rn = float(params[name].grad.double().norm()), float(gold[f"{tag}_grad_norm"][i])
+            assert abs(gn - rn) <= 3e-2 * rn + 1e-7, (tag, name, gn, rn)
+
+
 def test_one_training_step_batch16_against_reference_golden(golden_dir):
     """BASELINE.json config 4 at its stated batch size: one optimize_parameters() step on synthetic_train_batch(n=16) against the
     golden vectors of the UNMODIFIED reference Pix2PixModel (oracle/make_golden_train.py --n 16 --steps 1)."""

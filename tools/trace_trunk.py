@@ -16,12 +16,13 @@ from oracle import synth
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 cta = int(args[0]) if args else 0
+BATCH = int(args[1]) if len(args) > 1 else 16
 torch.cuda.set_device(0)
 g = hv.Generator({"input_dim": 1, "ngf": 16}, True)
 g.load_state_dict(synth.synthetic_generator_state_dict())
 g = g.cuda().eval()
 g.precision = "bf16"
-x, mask, cam, ratio = (t.cuda() for t in synth.synthetic_slices(16, seed=1))
+x, mask, cam, ratio = (t.cuda() for t in synth.synthetic_slices(BATCH, seed=1))
 with torch.no_grad():
     for _ in range(3):
         g(x, mask, cam, ratio)
@@ -29,25 +30,25 @@ torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 first, count = 4, 7
 for _ in range(3):
-    g.run_chain(first, count, 16)
+    g.run_chain(first, count, BATCH)
 evs = []
 for _ in range(20):
     flush.fill_(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    g.run_chain(first, count, 16)
+    g.run_chain(first, count, BATCH)
     e1.record()
     evs.append((e0, e1))
 torch.cuda.synchronize()
 us = sum(a.elapsed_time(b) for a, b in evs) / 20 * 1e3
-print(f"HV_TRUNK_DEBUG={os.environ.get('HV_TRUNK_DEBUG', '0')} HV_NO_TRUNK={os.environ.get('HV_NO_TRUNK', '')}: chain of {count} layers {us:.1f} us = {us / count:.2f} us per layer")
-if os.environ.get("HV_NO_TRUNK") or "--no-trace" in sys.argv:
+print(f"batch {BATCH} HV_TRUNK_DEBUG={os.environ.get('HV_TRUNK_DEBUG', '0')} HV_TRUNK={os.environ.get('HV_TRUNK', '')}: chain of {count} layers {us:.1f} us = {us / count:.2f} us per layer")
+if os.environ.get("HV_TRUNK") != "1" or "--no-trace" in sys.argv:
     sys.exit(0)
 buf = torch.zeros(12000, dtype=torch.int64, device="cuda")
 L = _lib.lib()
 L.hv_debug_trunk_trace.argtypes = [ctypes.c_void_p, ctypes.c_int]
 L.hv_debug_trunk_trace(buf.data_ptr(), cta)
-g.run_chain(first, count, 16)
+g.run_chain(first, count, BATCH)
 torch.cuda.synchronize()
 L.hv_debug_trunk_trace(None, 0)
 t = buf.cpu().tolist()
