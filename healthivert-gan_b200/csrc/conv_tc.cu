@@ -798,7 +798,7 @@ void tc_conv_free(TcConv& c) {
 // ------------------------------------------------------------------------------------------- weight packing
 // dst[(tap entry e = (source, ky, kx))][chunk][n_pad][8] bf16; padded channels / filters are zero.
 // kx-packed sources have one entry per kernel row: channel ch of the entry = (kx = ch / real, c = ch % real).
-struct PackSrc { int ch_off, real, chunks, kxpack, xp, cp; };
+struct PackSrc { int ch_off, real, chunks, kxpack, xp, cp; int use_map; short map[32]; };
 __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* __restrict__ ba, int cout_a,
                                     const float* __restrict__ wb, const float* __restrict__ bb, int cout_b, int cin_total,
                                     int k, int n_pad, PackSrc s0, PackSrc s1, int nsrc, __nv_bfloat16* __restrict__ dst,
@@ -824,7 +824,8 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
   const int ch = chunk * 8 + c8;
   int c = ch, tap = entry, co = n;
   bool real = ch < s.real;
-  if (s.kxpack) { const int kx = ch / s.real; c = ch - kx * s.real; tap = entry * k + kx; real = kx < k; }
+  if (s.kxpack && s.use_map) { const int mcode = ch < 32 ? s.map[ch] : -1; real = mcode >= 0; c = mcode & 63; tap = entry * k + (mcode >> 6); }
+  else if (s.kxpack) { const int kx = ch / s.real; c = ch - kx * s.real; tap = entry * k + kx; real = kx < k; }
   if (s.xp > 1) {   // entry = ky * (xp + 2) + view; column n = phase * cp + filter; view v carries tap kx = v - phase
     const int ky = entry / (s.xp + 2), view = entry - ky * (s.xp + 2), ph = n / s.cp;
     co = n - ph * s.cp;
@@ -844,10 +845,18 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
 int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a, const float* wb, const float* bb,
                          int cout_b, cudaStream_t st) {
   HV_CHECK_ARG(cout_a + cout_b == c.cout_real, "tc_conv_pack_weights: filter count mismatch");
-  PackSrc s0{0, c.src[0].real_channels, c.src[0].buf.chunks, c.src[0].kxpack ? 1 : 0, c.p.in_xp, c.p.cp}, s1{0, 0, 1, 0, 1, 0};
+  PackSrc s0, s1;
+  memset(&s0, 0, sizeof(s0)); memset(&s1, 0, sizeof(s1));
+  s0.real = c.src[0].real_channels; s0.chunks = c.src[0].buf.chunks; s0.kxpack = c.src[0].kxpack ? 1 : 0; s0.xp = c.p.in_xp; s0.cp = c.p.cp;
+  s1.chunks = 1; s1.xp = 1;
+  if (c.src[0].chan_map) {
+    HV_CHECK_ARG(c.src[0].kxpack && c.src[0].buf.chunks * 8 <= 32, "tc_conv_pack_weights: a channel map needs a kx-packed source of <= 32 channels");
+    s0.use_map = 1;
+    for (int i = 0; i < 32; ++i) s0.map[i] = i < c.src[0].buf.chunks * 8 ? c.src[0].chan_map[i] : (short)-1;
+  }
   int cin_total = c.src[0].real_channels;
   if (c.nsrc == 2) {
-    s1 = PackSrc{c.src[0].real_channels, c.src[1].real_channels, c.src[1].buf.chunks, c.src[1].kxpack ? 1 : 0, 1, 0};
+    s1.ch_off = c.src[0].real_channels; s1.real = c.src[1].real_channels; s1.chunks = c.src[1].buf.chunks; s1.kxpack = c.src[1].kxpack ? 1 : 0;
     cin_total += c.src[1].real_channels;
   }
   const int total = (int)(c.p.w_bytes / 2);
@@ -1069,6 +1078,7 @@ int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& ds
   const int need = (k * nsrc + 15) / 16 * 2;
   HV_CHECK_ARG(need == dst.chunks, "tc_pack_kx: destination has %d chunks, the packed channels need %d", dst.chunks, need);
   if (nsrc == 1 && k == 3) HV_CUDA(launch_pdl(pack_kx_kernel<1, 3>, grid, dim3(256), 0, st, a, dst));
+  else if (nsrc == 1 && k == 5) HV_CUDA(launch_pdl(pack_kx_kernel<1, 5>, grid, dim3(256), 0, st, a, dst));
   else if (nsrc == 3 && k == 5) HV_CUDA(launch_pdl(pack_kx_kernel<3, 5>, grid, dim3(256), 0, st, a, dst));
   else if (nsrc == 4 && k == 5) HV_CUDA(launch_pdl(pack_kx_kernel<4, 5>, grid, dim3(256), 0, st, a, dst));
   else { set_error("tc_pack_kx: no instance for %d sources, k=%d", nsrc, k); return HV_ERR_UNSUPPORTED; }

@@ -126,6 +126,11 @@ struct TcSource {
   // along x, so the conv needs one tap (and one MMA K-step set) per kernel ROW instead of per tap.  Pays off for
   // sources with few channels (network inputs, the CAM plane): k*real_channels must fit the buffer.
   bool kxpack = false;
+  // optional explicit channel layout of a kx-packed buffer: packed channel ch holds input channel (chan_map[ch] & 63) shifted by
+  // tap kx = chan_map[ch] >> 6, or nothing (-1).  Null = the default layout ch = kx * real_channels + c.  (The fine network's input
+  // keeps the planes known at the start of the forward and the coarse mask in separate chunks, so that only the latter is packed
+  // on the critical path.)
+  const short* chan_map = nullptr;   // [buf.chunks * 8], host memory, must outlive tc_conv_pack_weights
 };
 
 struct TcConv {

@@ -261,6 +261,14 @@ static const TcLayerSpec kTcLayers[] = {
 };
 constexpr int kNumTcLayers = sizeof(kTcLayers) / sizeof(kTcLayers[0]);
 
+// Channel layout of the fine network's kx-packed input buffer B_IN_F (32 channels): chunks 0-1 hold the three planes known when the
+// forward starts - x (input channel 0), mask (2), ratio (3) of xnow = [xin, coarse_seg, mask, ratio] (:179) - as channel kx * 3 + j,
+// chunks 2-3 hold the coarse mask (input channel 1) as channel 16 + kx.  Only the second pair is packed after the coarse heads.
+static const short kFineInputMap[32] = {
+    0 * 64 + 0, 0 * 64 + 2, 0 * 64 + 3, 1 * 64 + 0, 1 * 64 + 2, 1 * 64 + 3, 2 * 64 + 0, 2 * 64 + 2, 2 * 64 + 3, 3 * 64 + 0, 3 * 64 + 2, 3 * 64 + 3,
+    4 * 64 + 0, 4 * 64 + 2, 4 * 64 + 3, -1,
+    0 * 64 + 1, 1 * 64 + 1, 2 * 64 + 1, 3 * 64 + 1, 4 * 64 + 1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+
 struct TcPlan {
   TcBuf buf[B_COUNT];
   TcConv conv[kNumLayers];   // indexed by layer id (heads: C17 / A17 entries only)
@@ -351,6 +359,7 @@ static int tc_plan_create(hv_generator* g) {
     TcSource srcs[2];
     srcs[0].buf = s.layer == F2 ? t->buf[B_F1].chunk_view(0, 2) : t->buf[s.src0];
     srcs[0].real_channels = s.real0; srcs[0].kxpack = s.kx0;
+    if (s.layer == F1) srcs[0].chan_map = kFineInputMap;
     int nsrc = 1;
     if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; srcs[1].kxpack = s.kx1; nsrc = 2; }
     const bool heads = s.out < 0;
@@ -421,6 +430,9 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     const TcPlaneSrc cam128[1] = {{cam, HV_SRC_SUB2}}, cam256[1] = {{cam, HV_SRC_DIRECT}};
     RC(tc_pack_kx(cam128, 1, 3, 1, view(B_CAM128), ax));   // first needed by conv20 / conv19
     RC(tc_pack_kx(cam256, 1, 3, 1, view(B_CAM256), ax));
+    // the fine network's input planes that do not depend on the coarse network (chunks 0-1 of B_IN_F, see kFineInputMap)
+    const TcPlaneSrc in_f0[3] = {{x, HV_SRC_DIRECT}, {mask, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}};
+    RC(tc_pack_kx(in_f0, 3, 5, 1, view(B_IN_F).chunk_view(0, 2), ax));
     if (use_aux) HV_CUDA(cudaEventRecord(g->ev_aux[1], ax));
   }
   // ---- coarse network
@@ -436,8 +448,8 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
   // ---- fine network: xnow = [xin, coarse_seg, mask, ratio]; conv1 | pmconv1 as one 32-filter conv, then the
   // attention branch forks onto the side stream
   {
-    const TcPlaneSrc in_f[4] = {{x, HV_SRC_DIRECT}, {coarse_seg, HV_SRC_DIRECT}, {mask, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}};
-    RC(tc_pack_kx(in_f, 4, 5, 1, view(B_IN_F), st));
+    const TcPlaneSrc in_f1[1] = {{coarse_seg, HV_SRC_DIRECT}};   // chunks 2-3: the only part packed on the critical path
+    RC(tc_pack_kx(in_f1, 1, 5, 1, view(B_IN_F).chunk_view(2, 2), st));
   }
   RC(run(F1, st));
   HV_CUDA(cudaEventRecord(g->ev_fork, st));
