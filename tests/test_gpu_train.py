@@ -512,4 +512,6 @@ def test_data_parallel_step_two_ranks_nccl(tmp_path):
     for name, net in (("G", rep0.netG), ("D_1", rep0.netD_1)):
         for k, v in net.state_dict().items():
             if v.dtype.is_floating_point:
-                assert float((got[name][k] - v.detach().cpu()).abs().max()) <= 1e-6, (name, k)
+                # the first Adam step moves every weight by ~lr = 2e-4 whatever its gradient's size; where |g| ~ eps the step is
+                # sensitive to the last bits of g (summation order of the exchange): a tenth of a step at most
+                assert float((got[name][k] - v.detach().cpu()).abs().max()) <= 2e-5, (name, k)
