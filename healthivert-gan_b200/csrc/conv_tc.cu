@@ -140,7 +140,7 @@ constexpr int TC_BAR_BYTES = 1024;  // mbarriers + TMEM slot (512 B) + bias vect
 // 16 epilogue warps, 16 accumulator columns each: N_PAD/16*4 warps cover one tile (4 TMEM lane quadrants x column groups), so
 // 16/that many tiles are in the epilogue concurrently (4 / 2 / 1 for N_PAD = 16 / 32 / 64); group g owns tiles j % groups == g
 __host__ __device__ constexpr int tc_epi_warps(int) { return 16; }
-__host__ __device__ constexpr int tc_warps_per_tile(int n_pad) { return n_pad / 16 * 4; }
+__host__ __device__ constexpr int tc_warps_per_tile(int n_pad) { return n_pad >= 64 ? 16 : n_pad / 16 * 4; }
 __host__ __device__ constexpr int tc_threads(int n_pad) { return 64 + 32 * tc_epi_warps(n_pad); }
 __host__ __device__ constexpr int tc_acc_stages(int n_pad) { return TC_TMEM_COLS / n_pad > 8 ? 8 : TC_TMEM_COLS / n_pad; }
 // thin layers (N_PAD <= 32) are bound by the single-lane issue / handshake latencies, not by the tensor pipe: two CTAs per SM
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
   constexpr int ACC_STAGES = tc_acc_stages(N_PAD);       // accumulator tiles in flight
   constexpr int EPI_WARPS = tc_epi_warps(N_PAD);
   constexpr int WPT = tc_warps_per_tile(N_PAD), GROUPS = EPI_WARPS / WPT;
-  constexpr int NCOL = 16;                               // accumulator columns per epilogue warp
+  constexpr int NCOL = N_PAD > 64 ? N_PAD / 4 : 16;      // accumulator columns per epilogue warp (16 warps = 4 lane quadrants x 4 slices)
   constexpr int W_PRODUCER = EPI_WARPS, W_MMA = EPI_WARPS + 1;
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -473,11 +473,14 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
 #pragma unroll
       for (int jj = 0; jj < NCOL / 8; ++jj) {
         const int col = col0 + jj * 8;
-        // plain source: column = channel.  x-phase source: column = phase * cp + channel of output pixel in_xp * xx + phase
-        const int ph = k_in_xp > 1 ? col / p.cp : 0;
-        const int c = (k_in_xp > 1 ? col - ph * p.cp : col) >> 3;
+        // plain source: column = channel.  x-phase source: column = phase * cp + channel of output pixel in_xp * xx + phase.
+        // sub-pixel upsample (p.ups): the source is the LOW-resolution map of a nearest-x2-upsampled input; column = parity * cp +
+        // channel of output pixel (2 yy + parity / 2, 2 xx + parity % 2)
+        const int ph = (k_in_xp > 1 || p.ups) ? col / p.cp : 0;
+        const int c = ((k_in_xp > 1 || p.ups) ? col - ph * p.cp : col) >> 3;
         if (c >= p.out_nchunks) continue;
-        const int x = k_in_xp > 1 ? xx * k_in_xp + ph : xx;
+        const int x = p.ups ? 2 * xx + (ph & 1) : (k_in_xp > 1 ? xx * k_in_xp + ph : xx);
+        const int yo = p.ups ? 2 * yy + (ph >> 1) : yy;
         uint32_t pk[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -494,7 +497,7 @@ __global__ void __launch_bounds__(tc_threads(N_PAD), tc_ctas_per_sm(N_PAD)) conv
           *reinterpret_cast<uint4*>(plane + out_pos(2 * yy + 1, 2 * x) * 8) = val;
           *reinterpret_cast<uint4*>(plane + out_pos(2 * yy + 1, 2 * x + 1) * 8) = val;
         } else {
-          *reinterpret_cast<uint4*>(plane + out_pos(yy, x) * 8) = val;
+          *reinterpret_cast<uint4*>(plane + out_pos(yo, x) * 8) = val;
         }
       }
     }
@@ -587,7 +590,7 @@ static int max_chunks_of(const TcSource* srcs, int nsrc) {
 
 static int tc_issue_code(const TcConv& c);
 
-int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images, bool allow_pair) {
+int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real, int n_images, bool allow_pair, bool ups) {
   HV_CHECK_ARG(nsrc >= 1 && nsrc <= 2, "tc_conv: 1 or 2 sources supported");
   HV_CHECK_ARG((k == 3 || k == 5) && (stride == 1 || (stride == 2 && k == 3 && dil == 1)), "tc_conv: unsupported k/stride");
   memset(&c.p, 0, sizeof(c.p));
@@ -601,6 +604,11 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     HV_CHECK_ARG(xp == 4 && nsrc == 1 && stride == 1 && k == 3 && dil == 1 && !srcs[0].kxpack && cout_real <= 16 && (b0.w % 4) == 0,
                  "tc_conv: x-phase sources feed single-source 3x3 stride-1 convs with <= 16 filters");
     cp = cout_real <= 4 ? 4 : (cout_real <= 8 ? 8 : 16);
+    c.n_pad = 4 * cp;
+  } else if (ups) {
+    HV_CHECK_ARG(stride == 1 && k == 3 && dil == 1 && !srcs[0].kxpack && cout_real <= 32 && (nsrc == 1 || srcs[1].nbhd4),
+                 "tc_conv: the sub-pixel upsample mode serves 3x3 stride-1 convs with <= 32 filters (second source: a 4x4-neighbourhood plane)");
+    cp = cout_real <= 8 ? 8 : (cout_real <= 16 ? 16 : 32);
     c.n_pad = 4 * cp;
   } else {
     c.n_pad = cout_real <= 16 ? 16 : (cout_real <= 32 ? 32 : 64);
@@ -627,6 +635,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
   p.s2d_in = stride == 2;
   if (const char* e = getenv("HV_TC_DEBUG")) p.debug = atoi(e);
   p.in_xp = xp; p.cp = cp; p.map5d = (stride == 2 || xp > 1) ? 1 : 0;
+  p.ups = ups ? 1 : 0;
   p.w_img = b0.w;
   p.in_pitch = pitch; p.in_border = b0.border;
   p.pitch_magic = ((1ull << 40) + (unsigned long long)pitch - 1) / (unsigned long long)pitch;
@@ -798,14 +807,14 @@ void tc_conv_free(TcConv& c) {
 // ------------------------------------------------------------------------------------------- weight packing
 // dst[(tap entry e = (source, ky, kx))][chunk][n_pad][8] bf16; padded channels / filters are zero.
 // kx-packed sources have one entry per kernel row: channel ch of the entry = (kx = ch / real, c = ch % real).
-struct PackSrc { int ch_off, real, chunks, kxpack, xp, cp; int use_map; short map[32]; };
+struct PackSrc { int ch_off, real, chunks, kxpack, xp, cp; int use_map; short map[32]; int ups, nbhd4; };
 __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* __restrict__ ba, int cout_a,
                                     const float* __restrict__ wb, const float* __restrict__ bb, int cout_b, int cin_total,
                                     int k, int n_pad, PackSrc s0, PackSrc s1, int nsrc, __nv_bfloat16* __restrict__ dst,
                                     float* __restrict__ bias_pad, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_pad) {
-    const int co = s0.xp > 1 ? i % s0.cp : i;
+    const int co = (s0.xp > 1 || s0.ups) ? i % s0.cp : i;
     float b = 0.f;
     if (co < cout_a) b = ba ? ba[co] : 0.f;
     else if (co < cout_a + cout_b) b = bb ? bb[co - cout_a] : 0.f;
@@ -834,6 +843,27 @@ __global__ void pack_weights_kernel(const float* __restrict__ wa, const float* _
     real = real && kx >= 0 && kx < k;
   }
   float v = 0.f;
+  if (s0.ups) {
+    // sub-pixel upsample conv: column n = parity (py, px) * cp + filter.  Plain source: entry = low-res tap (dy + 1) * 3 + (dx + 1),
+    // weight = sum of the original taps (ky, kx) whose upsampled input pixel falls on that low-res pixel: floor((py + ky - 1) / 2) == dy.
+    // 4x4-neighbourhood source: one entry per kernel row of the (3-row) band, only the centre row carries weights: channel
+    // (ry, rx) of the centre position feeds tap (ky, kx) = (ry - py, rx - px) of parity (py, px).
+    const int pp = n / s0.cp, py = pp >> 1, px = pp & 1;
+    co = n - pp * s0.cp;
+    if (co < cout_a) {
+      if (s.nbhd4) {
+        const int ky = (ch >> 2) - py, kx = (ch & 3) - px;
+        if (entry == 1 && ch < 16 && ky >= 0 && ky < 3 && kx >= 0 && kx < 3) v = wa[((size_t)co * cin_total + s.ch_off) * kk + ky * 3 + kx];
+      } else if (ch < s.real) {
+        const int dy = entry / 3 - 1, dx = entry % 3 - 1;
+        for (int ky = 0; ky < 3; ++ky)
+          for (int kx = 0; kx < 3; ++kx)
+            if (((py + ky - 1) >> 1) == dy && ((px + kx - 1) >> 1) == dx) v += wa[((size_t)co * cin_total + s.ch_off + ch) * kk + ky * 3 + kx];
+      }
+    }
+    dst[i] = __float2bfloat16(v);
+    return;
+  }
   if (real) {
     const int cin = s.ch_off + c;
     if (co < cout_a) v = wa[((size_t)co * cin_total + cin) * kk + tap];
@@ -849,6 +879,8 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
   memset(&s0, 0, sizeof(s0)); memset(&s1, 0, sizeof(s1));
   s0.real = c.src[0].real_channels; s0.chunks = c.src[0].buf.chunks; s0.kxpack = c.src[0].kxpack ? 1 : 0; s0.xp = c.p.in_xp; s0.cp = c.p.cp;
   s1.chunks = 1; s1.xp = 1;
+  s0.ups = c.p.ups;
+  if (c.p.ups) HV_CHECK_ARG(cout_b == 0, "tc_conv_pack_weights: the sub-pixel upsample mode takes one filter bank");
   if (c.src[0].chan_map) {
     HV_CHECK_ARG(c.src[0].kxpack && c.src[0].buf.chunks * 8 <= 32, "tc_conv_pack_weights: a channel map needs a kx-packed source of <= 32 channels");
     s0.use_map = 1;
@@ -857,6 +889,7 @@ int tc_conv_pack_weights(TcConv& c, const float* wa, const float* ba, int cout_a
   int cin_total = c.src[0].real_channels;
   if (c.nsrc == 2) {
     s1.ch_off = c.src[0].real_channels; s1.real = c.src[1].real_channels; s1.chunks = c.src[1].buf.chunks; s1.kxpack = c.src[1].kxpack ? 1 : 0;
+    s1.nbhd4 = c.src[1].nbhd4 ? 1 : 0;
     cin_total += c.src[1].real_channels;
   }
   const int total = (int)(c.p.w_bytes / 2);
@@ -957,7 +990,9 @@ static int tc_issue_code(const TcConv& c) {
   X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(2, 0, 0, 2)) \
   X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(2, 0, 0, 1)) \
   X(16, HV_ACT_ELU, 4 << 16 | tc_shape_code(1, 5, 1, 1)) \
-  X(32, HV_ACT_ELU, 1 << 20 | 4 << 16 | tc_shape_code(1, 5, 1, 2))
+  X(32, HV_ACT_ELU, 1 << 20 | 4 << 16 | tc_shape_code(1, 5, 1, 2)) \
+  X(64, HV_ACT_ELU, 5 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(128, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2))
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {
@@ -988,6 +1023,7 @@ int tc_conv_launch(const TcConv& c, cudaStream_t st) {
     case 16: return tc_launch_n<16>(c, st);
     case 32: return tc_launch_n<32>(c, st);
     case 64: return tc_launch_n<64>(c, st);
+    case 128: return tc_launch_n<128>(c, st);
     default: set_error("tc_conv: bad n_pad %d", c.n_pad); return HV_ERR_INVALID;
   }
 }
@@ -1088,6 +1124,36 @@ int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& ds
 
 // sub = 2 reads every second pixel of every second row: the native-resolution result of a layer whose output is stored
 // nearest-x2-upsampled (the producer's epilogue writes the 2 x 2 replicas)
+// 4x4 neighbourhood of a high-resolution plane at low resolution (TcSource::nbhd4): one thread = one low-res position, 32-byte store
+__global__ void __launch_bounds__(256) pack_nbhd4_kernel(const float* __restrict__ src, TcBuf dst) {
+  pdl_prologue();
+  const int n = blockIdx.y, h = dst.h, w = dst.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int m = i / w, q = i - m * w;
+  const float* plane = src + (size_t)n * (2 * h) * (2 * w);
+  __align__(16) __nv_bfloat16 o[16];
+#pragma unroll
+  for (int ry = 0; ry < 4; ++ry) {
+    const int y = 2 * m - 1 + ry;
+#pragma unroll
+    for (int rx = 0; rx < 4; ++rx) {
+      const int x = 2 * q - 1 + rx;
+      o[ry * 4 + rx] = __float2bfloat16((y >= 0 && y < 2 * h && x >= 0 && x < 2 * w) ? plane[(size_t)y * (2 * w) + x] : 0.f);
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch)
+    *reinterpret_cast<uint4*>(dst.ptr + dst.chunk_base(n, ch) + dst.pos(m, q) * 8) = *reinterpret_cast<const uint4*>(o + ch * 8);
+}
+
+int tc_pack_nbhd4(const float* src, const TcBuf& dst, cudaStream_t st) {
+  HV_CHECK_ARG(src && dst.ptr && dst.chunks == 2 && !dst.s2d && dst.xp == 1, "tc_pack_nbhd4: bad argument");
+  HV_CUDA(launch_pdl(pack_nbhd4_kernel, dim3((dst.h * dst.w + 255) / 256, dst.n), dim3(256), 0, st, src, dst));
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 __global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst, int sub) {
   const int n = blockIdx.z, c = blockIdx.y, h = src.h / sub, w = src.w / sub;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

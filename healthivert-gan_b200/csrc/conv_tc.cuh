@@ -96,6 +96,7 @@ struct TcParams {
   int in_xp;      // sources are x-phase buffers: every accumulator row holds in_xp adjacent output pixels (N = in_xp * cp)
   int cp;         // accumulator columns per output pixel when in_xp > 1
   int out_xp;     // the output buffer is an x-phase buffer (aux outputs of the heads too)
+  int ups;        // sub-pixel upsample conv: sources are LOW-res maps, accumulator columns = 4 output parities x cp channels
   int map5d;      // tensor maps are 5-D (s2d / x-phase sources)
   int pair;       // two consecutive tiles per producer / issuer / barrier round (thin layers: halves the single-thread handshakes)
   int tile_adv;   // valid output positions per 128-row MMA tile (128 - widest tap shift)
@@ -131,6 +132,10 @@ struct TcSource {
   // keeps the planes known at the start of the forward and the coarse mask in separate chunks, so that only the latter is packed
   // on the critical path.)
   const short* chan_map = nullptr;   // [buf.chunks * 8], host memory, must outlive tc_conv_pack_weights
+  // second source of a sub-pixel upsample conv (see tc_conv_setup `ups`): a HIGH-resolution single-channel plane packed at low
+  // resolution, channel ry * 4 + rx of position (m, n) = plane(2m - 1 + ry, 2n - 1 + rx) (tc_pack_nbhd4): all 3x3 taps of the four
+  // output parities of (m, n) read this one position, so the source costs one K = 16 MMA step per tile
+  bool nbhd4 = false;
 };
 
 struct TcConv {
@@ -151,8 +156,12 @@ struct TcConv {
 // geometry + tensor maps + tables; allocates the packed-weight / bias buffers
 // allow_pair: the caller has a tile-pair kernel instance for this layer (the generator plan does for its layers; a stand-alone
 // conv of arbitrary geometry does not and runs the generic instance)
+// ups: the conv reads a nearest-x2-upsampled map (models/inpaint_networks.py:105, :222: F.interpolate(scale_factor=2) before conv19 /
+// allconv15).  Instead of materialising the upsampled map, srcs[0] is the LOW-resolution map: output pixel (2m + py, 2n + px) only
+// sees the 2 x 2 low-res pixels around (m, n), so the conv becomes 3 x 3 low-res taps with per-parity SUMMED weights and
+// N = 4 parities x cp accumulator columns: 4x fewer tiles, band loads and MMAs of 4x the width.  cout <= 32.
 int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, int dil, int cout_real,
-                  int n_images, bool allow_pair = false);
+                  int n_images, bool allow_pair = false, bool ups = false);
 // batch of the next launches (<= the n_images of the setup): tile count and grid
 void tc_conv_set_batch(TcConv& c, int n_images);
 // w_eff_a: [cout_a][cin_total][k][k] fp32 effective weights (cin_total = sum real_channels);
@@ -177,6 +186,8 @@ int tc_pack_nchw(const float* src, int src_channels, int mode /*hv_src_mode*/, c
 // dst channel kx*nsrc + c at (y, x) = source c at (y, x + (kx - k/2)*dil), zero outside the image
 struct TcPlaneSrc { const float* ptr; int mode; };
 int tc_pack_kx(const TcPlaneSrc* srcs, int nsrc, int k, int dil, const TcBuf& dst, cudaStream_t st);
+// dst (16 channels, extent h/2 x w/2): channel ry * 4 + rx of (m, n) = src[n][2m - 1 + ry][2n - 1 + rx] (zero outside), src fp32 [n,1,h,w]
+int tc_pack_nbhd4(const float* src, const TcBuf& dst, cudaStream_t st);
 int tc_unpack_nchw(const TcBuf& src, int channel0, int channels, float* dst, cudaStream_t st, int sub = 1);
 int tc_gap_fc_sigmoid(const TcBuf& x, const float* fc_w, const float* fc_b, float* out, float* partial /*[n*chunks]*/,
                       unsigned int* ticket /*[n], zero-initialised, left zero*/, cudaStream_t st);

@@ -210,28 +210,29 @@ namespace hv {
 
 // chunked bf16 activation buffers of the plan (channels, extent, zero border = padding of the consumer)
 enum BufId {
-  B_IN_C, B_C1, B_C2, B_C3, B_C4, B_C5, B_C6, B_C7, B_C8, B_C9, B_C10, B_C11, B_C12U, B_CAM128, B_C20, B_C13, B_C14U,
-  B_CAM256, B_C19, B_C15, B_C16,
+  B_IN_C, B_C1, B_C2, B_C3, B_C4, B_C5, B_C6, B_C7, B_C8, B_C9, B_C10, B_C11, B_C12U, B_CAM128, B_C20, B_C13, B_C14,
+  B_CAM4, B_C19, B_C15, B_C16,
   B_IN_F, B_F1, B_F2, B_F3, B_F4, B_F5, B_F6, B_F7, B_F8, B_F9, B_F10,
   B_P1, B_P2, B_P3, B_P4, B_P5, B_P6, B_CA, B_P9, B_P10,
-  B_A11, B_A12, B_A19U, B_A13, B_A14U, B_A15, B_A16CAT, B_COUNT
+  B_A11, B_A12, B_A19U, B_A13, B_A14, B_A15, B_A16CAT, B_COUNT
 };
 struct BufSpec { int channels, extent, border; };
 static const BufSpec kBufs[B_COUNT] = {
-    // B_IN_C (kx-packed 5 x [x, ratio, mask]), C1 .. C12U, CAM128 (kx-packed 3 x CAM), C20 .. C14U, CAM256 (kx-packed), C19, C15, C16
+    // B_IN_C (kx-packed 5 x [x, ratio, mask]), C1 .. C12U, CAM128 (kx-packed 3 x CAM), C20, C13, C14 (LOW-res input of conv19, which runs
+    // in the sub-pixel upsample mode), CAM4 (4x4 CAM neighbourhoods at 128 x 128), C19, C15, C16
     {16, 256, 2}, {16, 256, 1}, {32, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
     {64, 64, 8}, {64, 64, 16}, {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {16, 128, 1}, {64, 128, 1}, {32, 128, 1},
-    {32, 256, 1}, {16, 256, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
+    {32, 128, 1}, {16, 128, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
     // B_IN_F (kx-packed 5 x [x, coarse_seg, mask, ratio]), B_F1 = conv1 | pmconv1 (merged layer, 16 + 16 channels), F2 ..
     {32, 256, 2}, {32, 256, 1}, {16, 128, 1}, {32, 128, 1}, {32, 64, 1}, {64, 64, 1}, {64, 64, 2}, {64, 64, 4},
     {64, 64, 8}, {64, 64, 16}, {64, 64, 1},
     // B_P1 is a chunk view of B_F1 (no storage of its own)
     {0, 256, 1}, {16, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1},
-    {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {32, 128, 1}, {32, 256, 1}, {16, 256, 1}, {16, 256, 1},
+    {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {32, 128, 1}, {32, 128, 1}, {16, 256, 1}, {16, 256, 1},   // ... A13, A14 (low-res input of allconv15), A15, A16CAT
 };
 
 // layer -> (sources, output).  real = channels of the source that carry weights.
-struct TcLayerSpec { int layer; int src0, real0, src1, real1; int out; bool up2; int out_chunks; bool kx0, kx1; };
+struct TcLayerSpec { int layer; int src0, real0, src1, real1; int out; bool up2; int out_chunks; bool kx0, kx1; bool ups; };
 static const TcLayerSpec kTcLayers[] = {
     {C1, B_IN_C, 3, -1, 0, B_C1, false, 2, true, false},  {C2, B_C1, 16, -1, 0, B_C2, false, 4},
     {C3, B_C2, 32, -1, 0, B_C3, false, 4},      {C4, B_C3, 32, -1, 0, B_C4, false, 8},
@@ -240,7 +241,8 @@ static const TcLayerSpec kTcLayers[] = {
     {C9, B_C8, 64, -1, 0, B_C9, false, 8},      {C10, B_C9, 64, -1, 0, B_C10, false, 8},
     {C11, B_C10, 64, -1, 0, B_C11, false, 8},   {C12, B_C11, 64, -1, 0, B_C12U, true, 8},
     {C20, B_C12U, 64, B_CAM128, 1, B_C20, false, 8, false, true}, {C13, B_C20, 64, -1, 0, B_C13, false, 4},
-    {C14, B_C13, 32, -1, 0, B_C14U, true, 4},   {C19, B_C14U, 32, B_CAM256, 1, B_C19, false, 4, false, true},
+    // conv19 / allconv15 read a nearest-x2-upsampled map (:105, :222): sub-pixel upsample mode on the LOW-res producer output
+    {C14, B_C13, 32, -1, 0, B_C14, false, 4},   {C19, B_C14, 32, B_CAM4, 1, B_C19, false, 4, false, true, true},
     {C15, B_C19, 32, -1, 0, B_C15, false, 2},   {C16, B_C15, 16, -1, 0, B_C16, false, 2},
     {C17, B_C16, 8, -1, 0, -1, false, 0},       // heads conv17 + conv18
     // fine conv1 and pmconv1 read the same input: ONE conv with 16 + 16 filters writes B_F1 (chunks 0-1 | 2-3 = B_P1)
@@ -255,7 +257,7 @@ static const TcLayerSpec kTcLayers[] = {
     {PM9, B_CA, 64, -1, 0, B_P9, false, 8},     {PM10, B_P9, 64, -1, 0, B_P10, false, 8},
     {A11, B_F10, 64, B_P10, 64, B_A11, false, 8}, {A12, B_A11, 64, -1, 0, B_A12, false, 8},
     {A19, B_A12, 64, -1, 0, B_A19U, true, 8},   {A13, B_A19U, 64, -1, 0, B_A13, false, 4},
-    {A14, B_A13, 32, -1, 0, B_A14U, true, 4},   {A15, B_A14U, 32, -1, 0, B_A15, false, 2},
+    {A14, B_A13, 32, -1, 0, B_A14, false, 4},   {A15, B_A14, 32, -1, 0, B_A15, false, 2, false, false, true},
     {A16, B_A15, 16, -1, 0, B_A16CAT, false, 1}, // writes chunk 0 only; chunk 1 holds x_stage1
     {A17, B_A16CAT, 9, -1, 0, -1, false, 0},    // heads allconv17 + allconv18
 };
@@ -332,7 +334,7 @@ static int tc_plan_create(hv_generator* g) {
     // buffers consumed by a stride-2 conv are stored space-to-depth
     b.s2d = (i == B_C1 || i == B_C3 || i == B_F1 || i == B_F3 || i == B_P1 || i == B_P3);
     // inputs of the thin 256x256 tail layers (<= 16 filters: conv15/16/17+18, allconv15/16/17+18) are stored in 4 x-phases
-    b.xp = (!no_xp && (i == B_C19 || i == B_C15 || i == B_C16 || i == B_A14U || i == B_A15 || i == B_A16CAT)) ? 4 : 1;
+    b.xp = (!no_xp && (i == B_C19 || i == B_C15 || i == B_C16 || i == B_A15 || i == B_A16CAT)) ? 4 : 1;
     total += (b.bytes() + 255) & ~(size_t)255;
   }
   total += TcBuf::kSlackBytes;
@@ -361,11 +363,11 @@ static int tc_plan_create(hv_generator* g) {
     srcs[0].real_channels = s.real0; srcs[0].kxpack = s.kx0;
     if (s.layer == F1) srcs[0].chan_map = kFineInputMap;
     int nsrc = 1;
-    if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; srcs[1].kxpack = s.kx1; nsrc = 2; }
+    if (s.src1 >= 0) { srcs[1].buf = t->buf[s.src1]; srcs[1].real_channels = s.real1; srcs[1].kxpack = s.kx1; srcs[1].nbhd4 = s.ups; nsrc = 2; }
     const bool heads = s.out < 0;
     TcConv& c = t->conv[s.layer];
     const int cout = heads ? 2 : (s.layer == F1 ? kLayers[F1].cout + kLayers[PM1].cout : L.cout);
-    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, cout, n, /*allow_pair=*/true);
+    int rc = tc_conv_setup(c, srcs, nsrc, L.k, L.stride, L.dil, cout, n, /*allow_pair=*/true, s.ups);
     if (rc) return rc;
     t->has[s.layer] = true;
     if (heads) {
@@ -427,9 +429,9 @@ static int forward_bf16(hv_generator* g, const float* x, const float* mask, cons
     RC(fork_aux(0));
     const TcPlaneSrc in_c[3] = {{x, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}, {mask, HV_SRC_DIRECT}};
     RC(tc_pack_kx(in_c, 3, 5, 1, view(B_IN_C), st));
-    const TcPlaneSrc cam128[1] = {{cam, HV_SRC_SUB2}}, cam256[1] = {{cam, HV_SRC_DIRECT}};
+    const TcPlaneSrc cam128[1] = {{cam, HV_SRC_SUB2}};
     RC(tc_pack_kx(cam128, 1, 3, 1, view(B_CAM128), ax));   // first needed by conv20 / conv19
-    RC(tc_pack_kx(cam256, 1, 3, 1, view(B_CAM256), ax));
+    RC(tc_pack_nbhd4(cam, view(B_CAM4), ax));              // the full-resolution CAM plane for conv19's sub-pixel form
     // the fine network's input planes that do not depend on the coarse network (chunks 0-1 of B_IN_F, see kFineInputMap)
     const TcPlaneSrc in_f0[3] = {{x, HV_SRC_DIRECT}, {mask, HV_SRC_DIRECT}, {ratio, HV_SRC_SCALAR}};
     RC(tc_pack_kx(in_f0, 3, 5, 1, view(B_IN_F).chunk_view(0, 2), ax));

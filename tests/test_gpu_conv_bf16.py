@@ -133,6 +133,27 @@ def gen_bf16(synthetic_sd):
     return g
 
 
+def _subpixel_expected(lo, cam_hi, w, b):
+    """conv3x3(cat[nearest_x2(lo), cam_hi]) exactly as the sub-pixel upsample mode of the kernel computes it (tc_conv_setup `ups`):
+    output parity (py, px) is a 3x3 conv over the LOW-res map whose tap (dy, dx) carries the fp32 SUM (in kernel order, then rounded to
+    bf16) of the original taps landing on that low-res pixel; the full-resolution plane keeps its original (rounded) taps."""
+    n, cin, h, wd = lo.shape
+    cout = w.shape[0]
+    out = torch.zeros(n, cout, 2 * h, 2 * wd, dtype=torch.float64)
+    for py in range(2):
+        for px in range(2):
+            wl = torch.zeros(cout, cin, 3, 3, dtype=torch.float32)
+            for ky in range(3):
+                for kx in range(3):
+                    dy, dx = (py + ky - 1) // 2, (px + kx - 1) // 2
+                    wl[:, :, dy + 1, dx + 1] = wl[:, :, dy + 1, dx + 1] + w[:, :cin, ky, kx]
+            y = F.conv2d(lo.double(), _bf(wl).double(), None, padding=1)
+            if cam_hi is not None:
+                y = y + F.conv2d(cam_hi.double(), _bf(w[:, cin:]).double(), None, padding=1)[:, :, py::2, px::2]
+            out[:, :, py::2, px::2] = y
+    return out + b.double().view(1, -1, 1, 1)
+
+
 def _w_eff(sd, net, name):
     p = f"{net}.{name}.conv."
     w = sd[p + "weight_orig"]
@@ -186,7 +207,12 @@ def test_every_plan_instance_against_bf16_rounded_torch(gen_bf16, synthetic_sd, 
         src = inputs[full]() if full in inputs else T(prev)
         assert src.shape[1] == cin, (full, src.shape)
         w, b = _w_eff(synthetic_sd, net, name)
-        want = F.conv2d(src.double(), _bf(w).double(), b.double(), stride=stride, padding=pad, dilation=dil)
+        if full == C + "conv19":      # sub-pixel upsample mode: per-parity summed taps over the low-res map of conv14 + the CAM plane
+            want = _subpixel_expected(T(C + "conv14"), camb, w, b)
+        elif full == Fi + "allconv15":
+            want = _subpixel_expected(T(Fi + "allconv14"), None, w, b)
+        else:
+            want = F.conv2d(src.double(), _bf(w).double(), b.double(), stride=stride, padding=pad, dilation=dil)
         head = act in ("none", "sigmoid")
         # conv17 / allconv17 ('none') are followed by torch.clamp(-1, 1) (:115, :230), fused into the head epilogue
         want = want.clamp(-1, 1) if act == "none" else _act(want, act)
