@@ -606,7 +606,7 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     cp = cout_real <= 4 ? 4 : (cout_real <= 8 ? 8 : 16);
     c.n_pad = 4 * cp;
   } else if (ups) {
-    HV_CHECK_ARG(stride == 1 && k == 3 && dil == 1 && !srcs[0].kxpack && cout_real <= 32 && (nsrc == 1 || srcs[1].nbhd4),
+    HV_CHECK_ARG(stride == 1 && k == 3 && dil == 1 && !srcs[0].kxpack && cout_real <= 32 && (nsrc == 1 || srcs[1].nbhd4) && srcs[0].buf.xp == 1,
                  "tc_conv: the sub-pixel upsample mode serves 3x3 stride-1 convs with <= 32 filters (second source: a 4x4-neighbourhood plane)");
     cp = cout_real <= 8 ? 8 : (cout_real <= 16 ? 16 : 32);
     c.n_pad = 4 * cp;
@@ -992,7 +992,8 @@ static int tc_issue_code(const TcConv& c) {
   X(16, HV_ACT_ELU, 4 << 16 | tc_shape_code(1, 5, 1, 1)) \
   X(32, HV_ACT_ELU, 1 << 20 | 4 << 16 | tc_shape_code(1, 5, 1, 2)) \
   X(64, HV_ACT_ELU, 5 << 16 | tc_shape_code(1, 3, 3, 2)) \
-  X(128, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2))
+  X(128, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2)) \
+  X(128, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 1, 3, 4))
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {

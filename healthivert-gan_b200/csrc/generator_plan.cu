@@ -214,7 +214,7 @@ enum BufId {
   B_CAM4, B_C19, B_C15, B_C16,
   B_IN_F, B_F1, B_F2, B_F3, B_F4, B_F5, B_F6, B_F7, B_F8, B_F9, B_F10,
   B_P1, B_P2, B_P3, B_P4, B_P5, B_P6, B_CA, B_P9, B_P10,
-  B_A11, B_A12, B_A19U, B_A13, B_A14, B_A15, B_A16CAT, B_COUNT
+  B_A11, B_A12, B_A19, B_A13, B_A14, B_A15, B_A16CAT, B_COUNT
 };
 struct BufSpec { int channels, extent, border; };
 static const BufSpec kBufs[B_COUNT] = {
@@ -228,7 +228,7 @@ static const BufSpec kBufs[B_COUNT] = {
     {64, 64, 8}, {64, 64, 16}, {64, 64, 1},
     // B_P1 is a chunk view of B_F1 (no storage of its own)
     {0, 256, 1}, {16, 128, 1}, {32, 128, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {64, 64, 1},
-    {64, 64, 1}, {64, 64, 1}, {64, 128, 1}, {32, 128, 1}, {32, 128, 1}, {16, 256, 1}, {16, 256, 1},   // ... A13, A14 (low-res input of allconv15), A15, A16CAT
+    {64, 64, 1}, {64, 64, 1}, {64, 64, 1}, {32, 128, 1}, {32, 128, 1}, {16, 256, 1}, {16, 256, 1},   // A11, A12, A19 (low-res input of allconv13), A13, A14 (low-res input of allconv15), A15, A16CAT
 };
 
 // layer -> (sources, output).  real = channels of the source that carry weights.
@@ -256,7 +256,7 @@ static const TcLayerSpec kTcLayers[] = {
     {PM5, B_P4, 64, -1, 0, B_P5, false, 8},     {PM6, B_P5, 64, -1, 0, B_P6, false, 8},
     {PM9, B_CA, 64, -1, 0, B_P9, false, 8},     {PM10, B_P9, 64, -1, 0, B_P10, false, 8},
     {A11, B_F10, 64, B_P10, 64, B_A11, false, 8}, {A12, B_A11, 64, -1, 0, B_A12, false, 8},
-    {A19, B_A12, 64, -1, 0, B_A19U, true, 8},   {A13, B_A19U, 64, -1, 0, B_A13, false, 4},
+    {A19, B_A12, 64, -1, 0, B_A19, false, 8},   {A13, B_A19, 64, -1, 0, B_A13, false, 4, false, false, true},   // allconv13 after x2 (:219): sub-pixel mode
     {A14, B_A13, 32, -1, 0, B_A14, false, 4},   {A15, B_A14, 32, -1, 0, B_A15, false, 2, false, false, true},
     {A16, B_A15, 16, -1, 0, B_A16CAT, false, 1}, // writes chunk 0 only; chunk 1 holds x_stage1
     {A17, B_A16CAT, 9, -1, 0, -1, false, 0},    // heads allconv17 + allconv18

@@ -211,6 +211,8 @@ def test_every_plan_instance_against_bf16_rounded_torch(gen_bf16, synthetic_sd, 
             want = _subpixel_expected(T(C + "conv14"), camb, w, b)
         elif full == Fi + "allconv15":
             want = _subpixel_expected(T(Fi + "allconv14"), None, w, b)
+        elif full == Fi + "allconv13":
+            want = _subpixel_expected(T(Fi + "allconv19"), None, w, b)
         else:
             want = F.conv2d(src.double(), _bf(w).double(), b.double(), stride=stride, padding=pad, dilation=dil)
         head = act in ("none", "sigmoid")
