@@ -230,7 +230,7 @@ def _torch_gpu_train_baseline(dev, steps=3):
             "what": f"unmodified reference Pix2PixModel.optimize_parameters on cuda, batch {BATCH}, fp32 (TF32 off), eager PyTorch"}
 
 
-def _train_step_rate(rank, world, local, steps=5, warmup=2, d_precision="bf16"):
+def _train_step_rate(rank, world, local, steps=5, warmup=2, precision="bf16"):
     """BASELINE.json config 4: pix2pix training step, GLOBAL batch 16 sharded over the ranks (2 samples per rank at 8 GPUs),
     gradient all-reduce(mean) over NCCL; device time per step, max over ranks."""
     import torch
@@ -238,7 +238,7 @@ def _train_step_rate(rank, world, local, steps=5, warmup=2, d_precision="bf16"):
     from healthivert_gan_b200 import _lib, sharding
     from healthivert_gan_b200.pix2pix_model import Pix2PixModel
     from oracle import synth
-    opt = synth.train_options(gpu_ids=[local], d_precision=d_precision)
+    opt = synth.train_options(gpu_ids=[local], precision=precision)
     m = Pix2PixModel(opt)
     m.setup(opt)
     m.netG.load_state_dict(synth.synthetic_generator_state_dict())
@@ -275,7 +275,8 @@ def _train_step_rate(rank, world, local, steps=5, warmup=2, d_precision="bf16"):
     return {"workload": "pix2pix optimize_parameters, global batch 16 (BASELINE.json configs[3])", "n_gpus": world,
             "samples_per_rank": len(idx), "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": BATCH / ms * 1e3,
             "launches_per_step_rank0": launches,
-            "dtype": "generator fp32 SIMT; discriminator convs " + ("bf16 tcgen05 (fp32 accumulate)" if d_precision == "bf16" else "fp32 SIMT (parity mode)"),
+            "dtype": ("generator forward fp32 SIMT; generator conv backward and discriminator convs: bf16 operands on tcgen05, fp32 accumulate"
+                      if precision == "bf16" else "fp32 SIMT kernels everywhere (parity mode)"),
             "collective": "4 NCCL all-reduces per step on flat gradient buckets (D_1, D_2, D_3, G)" if world > 1 else "none",
             "losses_rank0": losses}
 
@@ -500,8 +501,8 @@ def run_ours(args, rank, world, local_rank):
             guarded("torch_gpu_baseline", lambda: _torch_gpu_baselines(dev))
             guarded("torch_gpu_train_baseline", lambda: _torch_gpu_train_baseline(dev))
             guarded("config3_volume", lambda: _volume_rate(g, rank, world, 1, 256))
-        guarded("config4_train", lambda: _train_step_rate(rank, world, local_rank, d_precision="bf16"))
-        guarded("config4_train_fp32_parity_mode", lambda: _train_step_rate(rank, world, local_rank, steps=3, d_precision="fp32"))
+        guarded("config4_train", lambda: _train_step_rate(rank, world, local_rank, precision="bf16"))
+        guarded("config4_train_fp32_parity_mode", lambda: _train_step_rate(rank, world, local_rank, steps=3, precision="fp32"))
         guarded("config5_volumes", lambda: _volume_rate(g, rank, world, 2 * world, 64))
 
     if rank == 0:

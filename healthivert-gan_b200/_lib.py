@@ -78,6 +78,10 @@ SIGNATURES = {
     "hv_multi_tensor_chunk": (c_int, []),
     "hv_adam_step_multi": (c_int, [c_void_p, c_int, c_longlong, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "hv_bucket_copy": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_float, c_int, c_void_p]),
+    "hv_conv2d_wgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),
+    "hv_conv2d_dgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),
+    "hv_conv2d_wgrad_bf16": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "hv_conv2d_dgrad_bf16": (c_int, [POINTER(hv_conv_desc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "hv_dconv_workspace_bytes": (c_size_t, [c_int] * 6),
     "hv_dconv_fwd_bf16": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_void_p, c_void_p]),
     "hv_dconv_bwd_bf16": (c_int, [c_void_p] * 5 + [c_int] * 6 + [c_void_p, c_void_p]),

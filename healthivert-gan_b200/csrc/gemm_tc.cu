@@ -37,7 +37,7 @@ struct GemmParams {
 
 template <int BN, bool OUT_BF16>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int ACC_STAGES = G_TMEM_COLS / BN;
+  constexpr int ACC_STAGES = G_TMEM_COLS / BN > 4 ? 4 : G_TMEM_COLS / BN;   // BN = 32 / 64 (narrow outputs): four stages are plenty
   constexpr int G_STAGES = gemm_stages(BN);
   constexpr uint32_t A_BYTES = G_BM * 128, B_BYTES = BN * 128, STAGE_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -231,7 +231,8 @@ static int gemm_launch(const GemmParams& p, int grid, cudaStream_t st) {
 int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const float* colscale, int M, int N, int K, int batch,
                long long strideA, long long strideB, int out_bf16, cudaStream_t st) {
   HV_CHECK_ARG(A && B && C, "gemm_tc: null argument");
-  HV_CHECK_ARG(M % G_BM == 0 && N % 128 == 0 && K % G_BK == 0 && batch >= 1, "gemm_tc: M %% 128, N %% 128, K %% 64 must be 0 (got %d,%d,%d)", M, N, K);
+  HV_CHECK_ARG(M % G_BM == 0 && (N % 128 == 0 || N == 32 || N == 64) && K % G_BK == 0 && batch >= 1,
+               "gemm_tc: M %% 128, N %% 128 (or N = 32 / 64), K %% 64 must be 0 (got %d,%d,%d)", M, N, K);
   // the attention module calls with the same workspace operands every forward: keep the encoded tensor maps of the last few
   // distinct problems (encoding costs several microseconds of host time per map)
   struct Cached { const void *a, *b; int M, N, K, batch, bn; long long sa, sb; CUtensorMap ma, mb; };
@@ -239,7 +240,7 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
   static thread_local int next = 0;
   static const bool bn128 = getenv("HV_GEMM_BN128") != nullptr;
   GemmParams p;
-  const int bn_pick = (N % 256 == 0 && out_bf16 && !bn128) ? 256 : 128;
+  const int bn_pick = N < 128 ? N : ((N % 256 == 0 && out_bf16 && !bn128) ? 256 : 128);   // N = 32 / 64: one narrow tile column
   const Cached* hit = nullptr;
   for (const Cached& e : cache)
     if (e.a == A && e.b == B && e.M == M && e.N == N && e.K == K && e.batch == batch && e.bn == bn_pick && e.sa == strideA && e.sb == strideB) hit = &e;
@@ -267,6 +268,8 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
   }
   const int grid = p.total_tiles < sms ? p.total_tiles : sms;
   if (bn == 256) return out_bf16 ? gemm_launch<256, true>(p, grid, st) : gemm_launch<256, false>(p, grid, st);
+  if (bn == 64) { HV_CHECK_ARG(!out_bf16, "gemm_tc: narrow tiles write fp32"); return gemm_launch<64, false>(p, grid, st); }
+  if (bn == 32) { HV_CHECK_ARG(!out_bf16, "gemm_tc: narrow tiles write fp32"); return gemm_launch<32, false>(p, grid, st); }
   return out_bf16 ? gemm_launch<128, true>(p, grid, st) : gemm_launch<128, false>(p, grid, st);
 }
 

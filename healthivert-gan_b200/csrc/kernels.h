@@ -30,6 +30,9 @@ int conv2d_fwd_fp32_sub(const hv_conv_desc* d, const float* w, const float* bias
 // internal source mode: [N,ch,H/2,W/2] read through zero insertion (value at even (y,x) only) - stride-2 data gradient
 #define HV_SRC_ZEROINS2 4
 
+// out[ch] = sum over (n, hw) of x[n][ch][:] (deterministic two-pass sum; bias gradients)
+int channel_sum(const float* x, float* out, int n, int c, int hw, cudaStream_t st);
+
 int gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* out, int n, int c,
                    int hw, cudaStream_t st);
 

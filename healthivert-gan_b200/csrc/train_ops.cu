@@ -222,6 +222,8 @@ static int channel_sum_launch(const float* x, float* out, int n, int c, int hw, 
   return HV_OK;
 }
 
+int channel_sum(const float* x, float* out, int n, int c, int hw, cudaStream_t st) { return channel_sum_launch(x, out, n, c, hw, st); }
+
 int conv2d_wgrad_fp32(const hv_conv_desc* d, const float* dy, float* dw, float* db, cudaStream_t st) {
   HV_CHECK_ARG(d && dy && dw, "conv2d_wgrad: null argument");
   HV_CHECK_ARG(d->nsrc >= 1 && d->nsrc <= 4, "conv2d_wgrad: nsrc out of range");

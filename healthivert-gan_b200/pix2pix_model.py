@@ -107,8 +107,13 @@ class Pix2PixModel(BaseModel):
             mk = lambda: networks.define_D(opt.input_nc, opt.ndf, opt.netD, opt.n_layers_D, opt.norm, opt.init_type,
                                            opt.init_gain, self.gpu_ids).to(self.device)
             self.netD_1, self.netD_2, self.netD_3 = mk(), mk(), mk()
-            # 'fp32' = parity mode; 'bf16' = discriminator convolutions on the tensor cores (opt.d_precision, default fp32)
-            self.d_precision = getattr(opt, "d_precision", "fp32")
+            # opt.precision: 'fp32' = parity mode (SIMT kernels, gradients within 1e-4 of autograd); 'bf16' = tensor-core training mode:
+            # the discriminators' convolutions (forward, data and weight gradients) and the generator's conv backward run as tcgen05
+            # GEMMs with bf16 operands and fp32 accumulation; the generator forward stays fp32.  opt.d_precision overrides the
+            # discriminator part alone.
+            self.precision = getattr(opt, "precision", "fp32")
+            T.BACKWARD_PRECISION = self.precision
+            self.d_precision = getattr(opt, "d_precision", self.precision)
             for net in (self.netD_1, self.netD_2, self.netD_3):
                 net.precision = self.d_precision
             self.criterionGAN = networks.GANLoss(opt.gan_mode).to(self.device)

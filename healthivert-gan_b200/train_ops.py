@@ -10,6 +10,22 @@ from . import _lib
 from ._lib import HV_ACT, HV_SRC_DIRECT, HV_SRC_SCALAR, HV_SRC_SUB2, HV_SRC_UP2, check, ptr
 
 
+# 'fp32': SIMT parity kernels for the conv backward (hv_conv2d_dgrad / _wgrad); 'bf16': im2col + tcgen05 GEMMs with bf16 operands and
+# fp32 accumulation (hv_conv2d_dgrad_bf16 / _wgrad_bf16).  Set by Pix2PixModel from opt.precision; a process-wide switch because the
+# tape closures of every net consult it when they run.
+BACKWARD_PRECISION = "fp32"
+_WS = {}
+
+
+def _workspace(nbytes, dev):
+    """One grow-only scratch buffer per device for the tensor-core backward (up to ~1 GB at batch 16: the im2col operands)."""
+    key = (dev.type, dev.index)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        _WS[key] = buf = torch.empty(int(nbytes * 1.25) + 4096, device=dev, dtype=torch.uint8)
+    return buf
+
+
 class Var:
     """A tensor on the tape: ``data`` plus an accumulated gradient (None until something flows back)."""
     __slots__ = ("data", "grad", "requires_grad")
@@ -105,16 +121,25 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
             dpre = torch.empty_like(y)
             check(L.hv_act_bwd(ptr(y), ptr(out.grad), ptr(dpre), HV_ACT[act], y.numel(), st))
         dd, keep2 = _desc(srcs, cin, cout, k, stride, pad, dil, "none", hin, win, n)
+        tc = BACKWARD_PRECISION == "bf16"
         if param_grads:
             dw = torch.empty_like(weight)
             db = torch.empty(cout, device=y.device, dtype=torch.float32) if bias is not None else None
-            check(L.hv_conv2d_wgrad(dd, ptr(dpre), ptr(dw), ptr(db), st))
+            if tc:
+                ws = _workspace(L.hv_conv2d_wgrad_bf16_workspace_bytes(dd), y.device)
+                check(L.hv_conv2d_wgrad_bf16(dd, ptr(dpre), ptr(dw), ptr(db), ptr(ws), st))
+            else:
+                check(L.hv_conv2d_wgrad(dd, ptr(dpre), ptr(dw), ptr(db), st))
             on_weight_grad(dw, db)
         need = [isinstance(s, Var) and s.requires_grad for s, _ in sources]
         if any(need):
-            ws = torch.empty(cin * cout * k * k, device=y.device, dtype=torch.float32)
             dx = torch.empty(n, cin, hin, win, device=y.device, dtype=torch.float32)
-            check(L.hv_conv2d_dgrad(dd, ptr(weight), ptr(dpre), ptr(dx), ptr(ws), st))
+            if tc:
+                ws = _workspace(L.hv_conv2d_dgrad_bf16_workspace_bytes(dd), y.device)
+                check(L.hv_conv2d_dgrad_bf16(dd, ptr(weight), ptr(dpre), ptr(dx), ptr(ws), st))
+            else:
+                ws = torch.empty(cin * cout * k * k, device=y.device, dtype=torch.float32)
+                check(L.hv_conv2d_dgrad(dd, ptr(weight), ptr(dpre), ptr(dx), ptr(ws), st))
             c0 = 0
             for (s, m), (t, _), nd in zip(sources, srcs, need):
                 ch = 1 if m == HV_SRC_SCALAR else t.shape[1]

@@ -276,6 +276,14 @@ int hv_dice_fwd(const float* pred, const float* gt, float* sums, float* dice_n, 
 int hv_dice_bwd(const float* gt, const float* sums, float g_out, float eps, float* dpred, int n, int per,
                 int accumulate, hv_stream_t stream);
 
+/* bf16 tensor-core variants of hv_conv2d_wgrad / hv_conv2d_dgrad (same descriptor, same fp32 NCHW tensors, same meaning of dx / dw / db):
+ * operands rounded to bf16, fp32 accumulation, im2col + batched tcgen05 GEMMs (csrc/gconv_tc.cu).  workspace: the matching
+ * *_workspace_bytes(d) bytes of device memory.  The training mode that uses them: Pix2PixModel(opt.precision = 'bf16').          */
+size_t hv_conv2d_wgrad_bf16_workspace_bytes(const hv_conv_desc* d);
+size_t hv_conv2d_dgrad_bf16_workspace_bytes(const hv_conv_desc* d);
+int hv_conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* db, void* workspace, hv_stream_t stream);
+int hv_conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, float* dx, void* workspace, hv_stream_t stream);
+
 /* ---- A7 on the tensor cores: the BatchNorm-followed PatchGAN convolutions (nn.Conv2d(k=4, padding=1, stride 1|2, bias=False),
  * models/networks.py:583-597) with bf16 operands and fp32 accumulation: batched tcgen05 GEMMs over explicit im2col operands.
  * Cin % 8 == 0, Cout % 128 == 0.  x [n,cin,h,w], w [cout,cin,4,4], y / dy [n,cout,ho,wo] fp32.  workspace:

@@ -94,6 +94,76 @@ def test_conv_backward_through_fused_sources():
     assert rel(got["dw"], wt.grad) <= 1e-4 and rel(got["db"], b.grad) <= 1e-4
 
 
+@pytest.fixture
+def bf16_backward():
+    T.BACKWARD_PRECISION = "bf16"
+    yield
+    T.BACKWARD_PRECISION = "fp32"
+
+
+@pytest.mark.parametrize("n,cin,cout,k,stride,pad,dil,h,w,act", [
+    (2, 8, 16, 3, 1, 2, 2, 24, 40, "elu"),
+    (2, 16, 32, 3, 2, 1, 1, 32, 64, "elu"),
+    (2, 1, 64, 4, 2, 1, 1, 64, 64, "lrelu"),       # PatchGAN first layer
+    (2, 512, 1, 4, 1, 1, 1, 31, 31, "none"),       # PatchGAN logit layer
+    (2, 3, 16, 5, 1, 2, 1, 32, 32, "elu"),
+    (2, 8, 1, 3, 1, 1, 1, 32, 32, "clamp1"),
+    (2, 70, 20, 3, 1, 1, 1, 17, 33, "sigmoid"),    # ragged channel counts, odd extents (pixel padding)
+    (3, 64, 64, 3, 1, 16, 16, 64, 64, "elu"),      # the trunk geometry, dilation 16
+    (2, 33, 32, 3, 1, 1, 1, 128, 128, "elu"),      # split-K over the pixels of an image
+])
+def test_conv_backward_bf16_against_autograd(bf16_backward, n, cin, cout, k, stride, pad, dil, h, w, act):
+    """hv_conv2d_dgrad_bf16 / hv_conv2d_wgrad_bf16 (im2col + tcgen05 GEMMs) against fp64 autograd on the bf16-ROUNDED operands
+    (x, w, and the pre-activation gradient): what is left is fp32 accumulation order, and for dx one bf16 rounding per tap plane."""
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float64)
+    g = torch.Generator().manual_seed(cin + cout + k)
+    x = torch.randn(n, cin, h, w, generator=g)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g)
+    tape = T.Tape()
+    xv = T.Var(x.cuda())
+    got = {}
+    out = T.conv2d(tape, [(xv, 0)], wt.cuda(), b.cuda(), k, stride, pad, dil, act, (h, w), lambda dw, db: got.update(dw=dw, db=db))
+    dy = torch.randn(out.data.shape, generator=g)
+    out.grad = dy.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    # pre-activation gradient exactly as the kernel sees it (fp32 forward, fp32 act'), then rounded operands in fp64
+    xr = x.double().requires_grad_()
+    pre = F.conv2d(xr, wt.double(), b.double(), stride=stride, padding=pad, dilation=dil)
+    y = ACT[act](pre)
+    dpre = torch.autograd.grad(y, pre, dy.double())[0]
+    xb, wb = bf(x).requires_grad_(), bf(wt).requires_grad_()
+    F.conv2d(xb, wb, None, stride=stride, padding=pad, dilation=dil).backward(bf(dpre.float()))
+    assert rel(got["dw"], wb.grad) <= 2e-4, rel(got["dw"], wb.grad)
+    assert rel(xv.grad, xb.grad) <= 4e-3, rel(xv.grad, xb.grad)
+    assert rel(got["db"], dpre.sum(dim=(0, 2, 3))) <= 1e-4
+
+
+def test_conv_backward_bf16_through_fused_sources(bf16_backward):
+    g = torch.Generator().manual_seed(3)
+    a = torch.randn(2, 6, 16, 16, generator=g, requires_grad=True)
+    c = torch.randn(2, 3, 32, 32, generator=g, requires_grad=True)
+    cam = torch.rand(2, 1, 64, 64, generator=g)
+    ratio = torch.rand(2, generator=g)
+    wt = (torch.randn(8, 11, 3, 3, generator=g) * 0.1).requires_grad_()
+    b = torch.randn(8, generator=g, requires_grad=True)
+    up = a.repeat_interleave(2, 2).repeat_interleave(2, 3)
+    cat = torch.cat([up, c, cam[:, :, ::2, ::2], ratio.view(2, 1, 1, 1).expand(-1, -1, 32, 32)], 1)
+    y = F.elu(F.conv2d(cat, wt, b, padding=1))
+    dy = torch.randn(y.shape, generator=g)
+    y.backward(dy)
+    tape = T.Tape()
+    av, cv = T.Var(a.detach().cuda()), T.Var(c.detach().cuda())
+    got = {}
+    out = T.conv2d(tape, [(av, 1), (cv, 0), (cam.cuda(), 2), (ratio.cuda(), 3)], wt.detach().cuda(), b.detach().cuda(), 3, 1, 1, 1,
+                   "elu", (32, 32), lambda dw, db: got.update(dw=dw, db=db))
+    out.grad = dy.cuda()
+    tape.backward()
+    assert rel(av.grad, a.grad) <= 1e-2 and rel(cv.grad, c.grad) <= 1e-2          # bf16 operands vs the fp32 reference
+    assert rel(got["dw"], wt.grad) <= 1e-2 and rel(got["db"], b.grad) <= 1e-4
+
+
 def test_spectral_norm_backward():
     g = torch.Generator().manual_seed(4)
     w = torch.randn(32, 16, 3, 3, generator=g, requires_grad=True)
@@ -305,11 +375,13 @@ def test_dconv_tc_against_torch_on_bf16_rounded_operands(n, cin, cout, h, stride
     assert rel(xv.grad, xr.grad) <= 4e-3 and rel(got["dw"], wr.grad) <= 1e-4
 
 
-def test_training_step_with_tensor_core_discriminators(golden_dir):
-    """d_precision = 'bf16' (PatchGAN convolutions on tcgen05) against the same golden step of the unmodified reference, at bf16
-    tolerances: losses within 1 %, gradient norms within 3 %, the generator forward (fp32) unchanged."""
+@pytest.mark.parametrize("mode", ["d_only", "full"])
+def test_training_step_in_tensor_core_mode(golden_dir, mode):
+    """opt.precision = 'bf16' (PatchGAN convolutions and the generator's conv backward on tcgen05; 'd_only': the discriminators alone)
+    against the same golden step of the unmodified reference, at bf16 tolerances: losses within 1 %, single gradient norms within
+    10 %, 1 % on average; the generator forward (fp32) unchanged."""
     gold = np.load(os.path.join(golden_dir, "train_step_n2.npz"))
-    opt = synth.train_options(gpu_ids=[0], d_precision="bf16")
+    opt = synth.train_options(gpu_ids=[0], **({"d_precision": "bf16"} if mode == "d_only" else {"precision": "bf16"}))
     m = Pix2PixModel(opt)
     m.setup(opt)
     m.netG.load_state_dict(synth.synthetic_generator_state_dict())
@@ -334,6 +406,7 @@ def test_training_step_with_tensor_core_discriminators(golden_dir):
     dev.sort(reverse=True)
     print("bf16 discriminators: worst gradient-norm deviations", [(round(d, 4), t, n) for d, t, n, _, _ in dev[:6]],
           "mean", float(np.mean([d[0] for d in dev])))
+    T.BACKWARD_PRECISION = "fp32"
     # bf16 rounding of the D activations moves LeakyReLU / BatchNorm decisions: single tensors deviate by a few per cent
     assert dev[0][0] <= 0.10, dev[0]
     assert float(np.mean([d[0] for d in dev])) <= 0.01

@@ -20,13 +20,14 @@ def main():
     ap.add_argument("--batch", type=int, default=16, help="global batch")
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--d-precision", default="fp32", choices=["fp32", "bf16"], help="bf16: PatchGAN convolutions on the tensor cores")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="bf16: tensor-core training mode (D convs + G conv backward)")
+    ap.add_argument("--d-precision", default=None, choices=["fp32", "bf16"], help="override for the PatchGAN convolutions alone")
     args = ap.parse_args()
     rank, world, local = sharding.world_from_env()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    opt = synth.train_options(gpu_ids=[local], d_precision=args.d_precision)
+    opt = synth.train_options(gpu_ids=[local], precision=args.precision, **({'d_precision': args.d_precision} if args.d_precision else {}))
     m = Pix2PixModel(opt)
     m.setup(opt)
     m.netG.load_state_dict(synth.synthetic_generator_state_dict())
@@ -61,7 +62,7 @@ def main():
     if rank == 0:
         print(json.dumps({"workload": "pix2pix optimize_parameters (BASELINE.json configs[3])", "global_batch": args.batch, "n_gpus": world,
                           "ms_per_step_device": ms, "ms_per_step_wall": wall, "samples_per_s": args.batch / ms * 1e3,
-                          "launches_per_step": (_lib.launch_count() - l0) / args.steps, "d_precision": args.d_precision,
+                          "launches_per_step": (_lib.launch_count() - l0) / args.steps, "precision": args.precision, "d_precision": args.d_precision or args.precision,
                           "losses": {k: round(v, 4) for k, v in m.get_current_losses().items()}}))
     if world > 1:
         dist.destroy_process_group()
