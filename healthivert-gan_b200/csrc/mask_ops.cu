@@ -179,6 +179,121 @@ int edge_xor_loss(const float* fake, const float* real, unsigned long long* xor_
   return HV_OK;
 }
 
+// ------------------------------------------------------------------ the whole tail of Pix2PixModel.forward in ONE pass
+// models/pix2pix_model.py:201-264 + the edge loss of :349: threshold of both segmentation heads, height-adaptive stitch of both CT
+// heads, the masked centre crops, Sobel of the real and of the thresholded fake mask and the XOR-count edge loss.  Seven planes in,
+// eight planes out, one launch: the separate kernels are launch-bound at this size (8 - 12 MB each in ~10 us = 0.1 - 0.15 of the HBM
+// peak, profiles/r2_hbm_kernels.md); every output is bit-identical to theirs (tests/test_gpu_ops.py).
+struct PostArgs {
+  const float *fine, *coarse, *x2s, *x1s, *real, *real_mask, *mask, *pred2, *pred1;
+  const int32_t *x1, *x2, *height;
+  float *fake_mask, *coarse_bin, *fake_B, *fake_B_coarse, *fake_local, *real_local, *real_edges, *fake_edges;
+  int32_t *rows_fine, *rows_coarse;
+  double* sq_sum;                    // scratch: {double sq_sum; u64 xor; u32 ticket}
+  unsigned long long* xor_out;
+  float* loss_out;
+  int maxheight, c0, c1, h, w, n;
+};
+
+__device__ __forceinline__ float thr01(float v) { return v > 0.5f ? 1.f : 0.f; }
+// sobel_at on the thresholded plane
+__device__ __forceinline__ float sobel_thr_at(const float* __restrict__ img, int y, int x, int h, int w) {
+  const int ym = max(y - 1, 0), yp = min(y + 1, h - 1), xm = max(x - 1, 0), xp = min(x + 1, w - 1);
+  const float a = thr01(img[ym * w + xm]), b = thr01(img[ym * w + x]), c = thr01(img[ym * w + xp]);
+  const float d = thr01(img[y * w + xm]), f = thr01(img[y * w + xp]);
+  const float g = thr01(img[yp * w + xm]), hh = thr01(img[yp * w + x]), i = thr01(img[yp * w + xp]);
+  const float gx = (-a + c) + (-2.f * d + 2.f * f) + (-g + i);
+  const float gy = (a + 2.f * b + c) - (g + 2.f * hh + i);
+  return fminf(sqrtf(gx * gx + gy * gy), 1.f);
+}
+
+__device__ __forceinline__ float stitch_at(const float* __restrict__ gen, const float* __restrict__ real, int r, int x, int xu, int xb, int d,
+                                           int x2, int h, int w) {
+  int sr;
+  const float* src;
+  if (r >= xu && r < xb) { src = gen; sr = r; }
+  else if (r < xu) { src = real; sr = d / 2 + r; }
+  else { src = real; sr = x2 + (r - xb); }
+  return (sr < 0 || sr >= h) ? 0.f : src[(size_t)sr * w + x];
+}
+
+__global__ void __launch_bounds__(256) post_forward_kernel(const PostArgs p) {
+  const int n = blockIdx.y, h = p.h, w = p.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t plane = (size_t)h * w, o = (size_t)n * plane + i;
+  // integer row arithmetic of the two stitches (the same expressions as stitch_kernel)
+  const int hh = p.height[n];
+  const int pf = (int)ceilf(p.pred2[n] * (float)p.maxheight), pc = (int)ceilf(p.pred1[n] * (float)p.maxheight);
+  const int hf = pf < hh ? hh : pf, hc = pc < hh ? hh : pc;
+  const int df = hf - hh, dc = hc - hh;
+  const int xuf = p.x1[n] - df / 2, xbf = xuf + hf, xuc = p.x1[n] - dc / 2, xbc = xuc + hc;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    p.rows_fine[n * 4 + 0] = hf; p.rows_fine[n * 4 + 1] = df; p.rows_fine[n * 4 + 2] = xuf; p.rows_fine[n * 4 + 3] = xbf;
+    p.rows_coarse[n * 4 + 0] = hc; p.rows_coarse[n * 4 + 1] = dc; p.rows_coarse[n * 4 + 2] = xuc; p.rows_coarse[n * 4 + 3] = xbc;
+  }
+  float sq = 0.f;
+  int xr = 0;
+  if (i < h * w) {
+    const int r = i / w, x = i - r * w;
+    const float* real = p.real + n * plane;
+    p.fake_mask[o] = thr01(p.fine[o]);
+    p.coarse_bin[o] = thr01(p.coarse[o]);
+    const float fb = stitch_at(p.x2s + n * plane, real, r, x, xuf, xbf, df, p.x2[n], h, w);
+    p.fake_B[o] = fb;
+    p.fake_B_coarse[o] = stitch_at(p.x1s + n * plane, real, r, x, xuc, xbc, dc, p.x2[n], h, w);
+    const bool centre = x >= p.c0 && x < p.c1;
+    const float m = p.mask[o];
+    p.fake_local[o] = centre ? fb * m : 0.f;
+    p.real_local[o] = centre ? real[i] * m : 0.f;
+    const float er = sobel_at(p.real_mask + n * plane, r, x, h, w);
+    const float ef = sobel_thr_at(p.fine + n * plane, r, x, h, w);
+    p.real_edges[o] = er;
+    p.fake_edges[o] = ef;
+    const float dd = ef - er;
+    sq = dd * dd;
+    xr = (ef > 0.f) != (er > 0.f);
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, xr);
+  sq = warp_sum(sq);
+  __shared__ float s_sq[8];
+  __shared__ int s_x[8];
+  __shared__ bool last;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { s_sq[warp] = sq; s_x[warp] = __popc(bal); }
+  __syncthreads();
+  unsigned long long* xor_acc = reinterpret_cast<unsigned long long*>(p.sq_sum + 1);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(p.sq_sum + 2);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    int c = 0;
+    for (int k = 0; k < 8; ++k) { t += s_sq[k]; c += s_x[k]; }
+    if (c) atomicAdd(xor_acc, (unsigned long long)c);
+    if (t != 0.f) atomicAdd(p.sq_sum, (double)t);
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+    if (last) {   // every CTA has added its share: finish the loss (800 * mean squared difference, pix2pix_model.py:109, :349)
+      __threadfence();
+      *p.loss_out = (float)(800.0 * __ldcg(p.sq_sum) / ((double)p.n * h * w));
+      *p.xor_out = __ldcg(xor_acc);
+    }
+  }
+}
+
+int post_forward(const PostArgs& a, cudaStream_t st) {
+  HV_CHECK_ARG(a.fine && a.coarse && a.x2s && a.x1s && a.real && a.real_mask && a.mask && a.pred2 && a.pred1 && a.x1 && a.x2 && a.height &&
+                   a.fake_mask && a.coarse_bin && a.fake_B && a.fake_B_coarse && a.fake_local && a.real_local && a.real_edges && a.fake_edges &&
+                   a.rows_fine && a.rows_coarse && a.xor_out && a.loss_out,
+               "post_forward: null argument");
+  HV_CHECK_ARG(a.n > 0 && a.n <= 65535 && a.h > 0 && a.w > 0, "post_forward: bad extent");
+  PostArgs q = a;
+  q.sq_sum = static_cast<double*>(stream_scratch(st, 24));
+  HV_CHECK_ARG(q.sq_sum, "post_forward: scratch allocation failed");
+  HV_CUDA(cudaMemsetAsync(q.sq_sum, 0, 24, st));
+  post_forward_kernel<<<dim3((a.h * a.w + 255) / 256, a.n), 256, 0, st>>>(q);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 // ------------------------------------------------------------------ per-column heights (RHLV_quantification.py:41-73)
 // The slice z of a [d0,d1,d2] u8 volume is viewed as [rows = d0][cols]: sagittal (axis 2)
 // cols = d1, coronal (axis 1) cols = d2.  Pass 1 counts non-zeros per (slice, column) with the
@@ -275,3 +390,19 @@ int column_heights(const uint8_t* vf, const uint8_t* vl, int d0, int d1, int d2,
 }
 
 }  // namespace hv
+
+extern "C" int hv_post_forward(const float* fine_seg, const float* coarse_seg, const float* x_stage2, const float* x_stage1, const float* real_B,
+                               const float* real_B_mask, const float* mask, const float* pred2_h, const float* pred1_h, const int32_t* x1,
+                               const int32_t* x2, const int32_t* height, int maxheight, int c0, int c1, float* fake_B_mask_raw,
+                               float* coarse_seg_binary, float* fake_B, float* fake_B_coarse, float* fake_B_local, float* real_B_local,
+                               float* real_edges, float* fake_edges, int32_t* rows_fine, int32_t* rows_coarse, unsigned long long* xor_count,
+                               float* edge_loss, int n, int h, int w, hv_stream_t stream) {
+  hv::PostArgs a;
+  a.fine = fine_seg; a.coarse = coarse_seg; a.x2s = x_stage2; a.x1s = x_stage1; a.real = real_B; a.real_mask = real_B_mask; a.mask = mask;
+  a.pred2 = pred2_h; a.pred1 = pred1_h; a.x1 = x1; a.x2 = x2; a.height = height;
+  a.fake_mask = fake_B_mask_raw; a.coarse_bin = coarse_seg_binary; a.fake_B = fake_B; a.fake_B_coarse = fake_B_coarse;
+  a.fake_local = fake_B_local; a.real_local = real_B_local; a.real_edges = real_edges; a.fake_edges = fake_edges;
+  a.rows_fine = rows_fine; a.rows_coarse = rows_coarse; a.sq_sum = nullptr; a.xor_out = xor_count; a.loss_out = edge_loss;
+  a.maxheight = maxheight; a.c0 = c0; a.c1 = c1; a.h = h; a.w = w; a.n = n;
+  return hv::post_forward(a, hv::as_stream(stream));
+}

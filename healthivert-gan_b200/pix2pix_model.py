@@ -166,18 +166,28 @@ class Pix2PixModel(BaseModel):
         self.coarse_seg_sigmoid, self.fake_B_mask_sigmoid, self.x_stage1, self.fake_B_raw, self.offset_flow = cs, fs, x1t, x2t, flow
         self._pred1_raw, self._pred2_raw = p1t, p2t                  # sigmoid outputs in (0, 1), [N, 1]
         maxh = self._maxh
-        self.fake_B_mask_raw = mask_ops.threshold(fs)                # :201
-        self.coarse_seg_binary = mask_ops.threshold(cs)              # :202
-        # height-adaptive stitching on the device, no .item() syncs (:206-252)
-        self.fake_B, self._rows_fine = mask_ops.stitch(x2t, self.real_B, p2t, self.x1, self.x2, self.height, maxh, return_rows=True)
-        self.fake_B_coarse, self._rows_coarse = mask_ops.stitch(x1t, self.real_B, p1t, self.x1, self.x2, self.height, maxh,
-                                                                return_rows=True)
         w = self.mask.shape[-1]
         self._center = (w // 2 - 35, w // 2 + 35)                    # :254-260
-        self.fake_B_local = self._local(self.fake_B)
-        self.real_B_local = self._local(self.real_B)
-        self.real_edges = self.sobel_edge(self.real_B_mask)          # :263
-        self.fake_edges = self.sobel_edge(self.fake_B_mask_raw)      # :264
+        # :201-264 + the edge loss of :349 in ONE pass (hv_post_forward): thresholds, both height-adaptive stitches (device-side row
+        # arithmetic, no .item() syncs), the masked centre crops, both Sobel maps and the XOR-count edge loss
+        h = self.mask.shape[-2]
+        dev = cs.device
+        new = lambda: torch.empty(n, 1, h, w, device=dev, dtype=torch.float32)
+        (self.fake_B_mask_raw, self.coarse_seg_binary, self.fake_B, self.fake_B_coarse, self.fake_B_local, self.real_B_local,
+         self.real_edges, self.fake_edges) = (new() for _ in range(8))
+        self._rows_fine = torch.empty(n, 4, device=dev, dtype=torch.int32)
+        self._rows_coarse = torch.empty(n, 4, device=dev, dtype=torch.int32)
+        self._edge_xor = torch.empty(1, device=dev, dtype=torch.int64)
+        self._edge_loss_dev = torch.empty(1, device=dev, dtype=torch.float32)
+        i32 = lambda t: t.to(device=dev, dtype=torch.int32).contiguous()
+        x1d, x2d, hd = i32(self.x1), i32(self.x2), i32(self.height)
+        p1c, p2c = p1t.reshape(-1).contiguous(), p2t.reshape(-1).contiguous()
+        check(_lib.lib().hv_post_forward(
+            ptr(fs.contiguous()), ptr(cs.contiguous()), ptr(x2t.contiguous()), ptr(x1t.contiguous()), ptr(self.real_B), ptr(self.real_B_mask),
+            ptr(self.mask), ptr(p2c), ptr(p1c), ptr(x1d), ptr(x2d), ptr(hd), int(maxh), self._center[0], self._center[1],
+            ptr(self.fake_B_mask_raw), ptr(self.coarse_seg_binary), ptr(self.fake_B), ptr(self.fake_B_coarse), ptr(self.fake_B_local),
+            ptr(self.real_B_local), ptr(self.real_edges), ptr(self.fake_edges), ptr(self._rows_fine), ptr(self._rows_coarse),
+            ptr(self._edge_xor), ptr(self._edge_loss_dev), n, h, w, _lib.stream()))
 
     def _local(self, x):
         out = torch.empty_like(x)
@@ -282,8 +292,7 @@ class Pix2PixModel(BaseModel):
         self._tape.backward()
 
     def _edge_loss(self):
-        loss, _ = edge_mse_loss(self.fake_B_mask_raw, self.real_B_mask)
-        return loss[0]
+        return self._edge_loss_dev[0]      # computed by hv_post_forward together with the edge maps
 
     def _height_loss(self):
         """loss_h (:350) and its gradients w.r.t. the two sigmoid height outputs, one small kernel."""

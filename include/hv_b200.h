@@ -284,6 +284,18 @@ size_t hv_conv2d_dgrad_bf16_workspace_bytes(const hv_conv_desc* d);
 int hv_conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* db, void* workspace, hv_stream_t stream);
 int hv_conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, float* dx, void* workspace, hv_stream_t stream);
 
+/* ---- A4 + A5 fused: the whole tail of Pix2PixModel.forward (models/pix2pix_model.py:201-264) and the edge loss (:109, :349) in one
+ * pass over the planes: threshold of both segmentation heads, height-adaptive stitch of both CT heads (rows_* as hv_stitch), masked
+ * centre crops (columns [c0, c1)), Sobel of real_B_mask and of the thresholded fine mask, XOR count and 800 * MSE of the two edge
+ * maps.  All planes [n,1,h,w] fp32; every output is bit-identical to hv_threshold / hv_stitch / hv_masked_center / hv_sobel /
+ * hv_edge_xor_loss on the same inputs.                                                                                          */
+int hv_post_forward(const float* fine_seg, const float* coarse_seg, const float* x_stage2, const float* x_stage1, const float* real_B,
+                    const float* real_B_mask, const float* mask, const float* pred2_h, const float* pred1_h, const int32_t* x1,
+                    const int32_t* x2, const int32_t* height, int maxheight, int c0, int c1, float* fake_B_mask_raw,
+                    float* coarse_seg_binary, float* fake_B, float* fake_B_coarse, float* fake_B_local, float* real_B_local,
+                    float* real_edges, float* fake_edges, int32_t* rows_fine, int32_t* rows_coarse, unsigned long long* xor_count,
+                    float* edge_loss, int n, int h, int w, hv_stream_t stream);
+
 /* ---- A7 on the tensor cores: the BatchNorm-followed PatchGAN convolutions (nn.Conv2d(k=4, padding=1, stride 1|2, bias=False),
  * models/networks.py:583-597) with bf16 operands and fp32 accumulation: batched tcgen05 GEMMs over explicit im2col operands.
  * Cin % 8 == 0, Cout % 128 == 0.  x [n,cin,h,w], w [cout,cin,4,4], y / dy [n,cout,ho,wo] fp32.  workspace:

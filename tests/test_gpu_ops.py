@@ -6,6 +6,7 @@ import torch.nn.functional as F
 
 import healthivert_gan_b200 as hv
 from healthivert_gan_b200 import _lib, mask_ops
+from healthivert_gan_b200._lib import check, ptr
 from healthivert_gan_b200.inpaint_networks import conv2d_fused
 from oracle import generator_ref as gr
 from oracle import mask_ops_ref as mo
@@ -248,3 +249,43 @@ def test_rhlv_table_from_nifti_files(axis, golden_dir, tmp_path):
     assert np.allclose(got, known["rhlv"], rtol=0, atol=1e-12)
     grading.write_table(rows, str(tmp_path / "t.csv"))
     assert grading.read_table(str(tmp_path / "t.csv"))["Mid RHLV"][0] == rows[0]["Mid RHLV"]
+
+
+def test_fused_post_forward_equals_the_separate_kernels():
+    """hv_post_forward (one pass over the planes: thresholds, both stitches, centre crops, both Sobel maps, XOR-count edge loss) ==
+    hv_threshold / hv_stitch / hv_masked_center / hv_sobel / hv_edge_xor_loss, bit for bit (models/pix2pix_model.py:201-264, :349)."""
+    from healthivert_gan_b200 import mask_ops
+    from healthivert_gan_b200.edge_operator import Sobel, edge_mse_loss
+    g = torch.Generator().manual_seed(5)
+    n, h, w = 5, 256, 256
+    r = lambda *s: torch.rand(*s, generator=g).cuda()
+    fine, coarse = r(n, 1, h, w), r(n, 1, h, w)
+    fine[0, 0, 3, 7] = 0.5                                   # exactly 0.5 is NOT above the threshold
+    x2s, x1s, real = r(n, 1, h, w) * 2 - 1, r(n, 1, h, w) * 2 - 1, r(n, 1, h, w) * 2 - 1
+    real_mask = (r(n, 1, h, w) > 0.6).float()
+    mask = torch.zeros(n, 1, h, w, device="cuda")
+    mask[:, :, 100:140] = 1
+    p1, p2 = r(n, 1), r(n, 1)
+    x1 = torch.tensor([100, 98, 102, 96, 5], dtype=torch.int32).cuda()
+    hh = torch.tensor([28, 30, 26, 33, 39], dtype=torch.int32).cuda()
+    x2 = x1 + hh
+    c0, c1 = w // 2 - 35, w // 2 + 35
+    new = lambda: torch.empty(n, 1, h, w, device="cuda")
+    outs = [new() for _ in range(8)]
+    rows_f, rows_c = (torch.empty(n, 4, dtype=torch.int32, device="cuda") for _ in range(2))
+    xor, loss = torch.empty(1, dtype=torch.int64, device="cuda"), torch.empty(1, device="cuda")
+    check(_lib.lib().hv_post_forward(ptr(fine), ptr(coarse), ptr(x2s), ptr(x1s), ptr(real), ptr(real_mask), ptr(mask), ptr(p2.reshape(-1)),
+                                     ptr(p1.reshape(-1)), ptr(x1), ptr(x2), ptr(hh), 40, c0, c1, *[ptr(o) for o in outs], ptr(rows_f),
+                                     ptr(rows_c), ptr(xor), ptr(loss), n, h, w, _lib.stream()))
+    torch.cuda.synchronize()
+    fake_mask, coarse_bin, fake_B, fake_Bc, fake_loc, real_loc, real_e, fake_e = outs
+    assert torch.equal(fake_mask, mask_ops.threshold(fine)) and torch.equal(coarse_bin, mask_ops.threshold(coarse))
+    wf, rf = mask_ops.stitch(x2s, real, p2, x1, x2, hh, 40, return_rows=True)
+    wc, rc = mask_ops.stitch(x1s, real, p1, x1, x2, hh, 40, return_rows=True)
+    assert torch.equal(fake_B, wf) and torch.equal(fake_Bc, wc) and torch.equal(rows_f, rf) and torch.equal(rows_c, rc)
+    loc = lambda t: torch.where((torch.arange(w, device="cuda") >= c0) & (torch.arange(w, device="cuda") < c1), t * mask, torch.zeros_like(t))
+    assert torch.equal(fake_loc, loc(wf)) and torch.equal(real_loc, loc(real))
+    sob = Sobel().cuda()
+    assert torch.equal(real_e, sob(real_mask)) and torch.equal(fake_e, sob(mask_ops.threshold(fine)))
+    want_loss, want_xor = edge_mse_loss(mask_ops.threshold(fine), real_mask)
+    assert int(xor) == int(want_xor) and float(loss) == float(want_loss)
