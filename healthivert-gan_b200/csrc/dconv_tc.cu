@@ -131,16 +131,17 @@ __global__ void __launch_bounds__(256) dc_reduce_b_kernel(const float* __restric
   dw[i] = s;
 }
 
-// dx[b][ci][y][x] = sum over the taps (ky, kx) whose output pixel exists: dcolT[b][ci*16 + ky*4 + kx][oy*wo + ox], oy = (y + 1 - ky) / s
+// dx[b][ci][y][x] = sum over the taps (ky, kx) whose output pixel exists: dcolT[b][ci*16 + ky*4 + kx][oy*wo + ox], oy = (y + 1 - ky) / s.
+// One thread = 4 consecutive x (one 16-byte store).
 __global__ void __launch_bounds__(256) dc_col2im_kernel(const __nv_bfloat16* __restrict__ dcolT, float* __restrict__ dx, DcGeom g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long total = (long long)g.n * g.cin * g.h * g.w;
-  if (i >= total) return;
-  const int x = (int)(i % g.w), y = (int)((i / g.w) % g.h);
-  const long long bc = i / ((long long)g.w * g.h);     // b * cin + ci
+  const int W4 = (g.w + 3) >> 2;
+  if (i >= (long long)g.n * g.cin * g.h * W4) return;
+  const int x0 = (int)(i % W4) * 4, y = (int)((i / W4) % g.h);
+  const long long bc = i / ((long long)W4 * g.h);     // b * cin + ci
   const int ci = (int)(bc % g.cin), b = (int)(bc / g.cin);
   const __nv_bfloat16* src = dcolT + ((size_t)b * g.K + (size_t)ci * 16) * g.Pp;
-  float acc = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int ky = 0; ky < 4; ++ky) {
     const int ty = y + 1 - ky;
@@ -149,14 +150,20 @@ __global__ void __launch_bounds__(256) dc_col2im_kernel(const __nv_bfloat16* __r
     if (oy >= g.ho) continue;
 #pragma unroll
     for (int kx = 0; kx < 4; ++kx) {
-      const int tx = x + 1 - kx;
-      if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
-      const int ox = g.stride == 2 ? tx >> 1 : tx;
-      if (ox >= g.wo) continue;
-      acc += __bfloat162float(src[(size_t)(ky * 4 + kx) * g.Pp + oy * g.wo + ox]);
+      const __nv_bfloat16* tap = src + (size_t)(ky * 4 + kx) * g.Pp + (size_t)oy * g.wo;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tx = x0 + j + 1 - kx;
+        if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
+        const int ox = g.stride == 2 ? tx >> 1 : tx;
+        if (ox < g.wo) acc[j] += __bfloat162float(tap[ox]);
+      }
     }
   }
-  dx[i] = acc;
+  float* out = dx + ((size_t)bc * g.h + y) * g.w + x0;
+  if ((g.w & 3) == 0) *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  else
+    for (int j = 0; j < 4 && x0 + j < g.w; ++j) out[j] = acc[j];
 }
 
 static inline unsigned dc_blocks(long long n) { return (unsigned)((n + 255) / 256); }
@@ -234,7 +241,7 @@ int dconv_bwd_bf16(const float* x, const float* w, const float* dy, float* dx, f
     HV_LAUNCH_CHECK();
     rc = gemm_tc_nt(ws.wt, ws.dyT, ws.dcolT, nullptr, g.K, g.Pp, cout, n, 0, (long long)g.Pp * cout, 1, st);
     if (rc) return rc;
-    dc_col2im_kernel<<<dc_blocks((long long)n * cin * h * wd), 256, 0, st>>>(ws.dcolT, dx, g);
+    dc_col2im_kernel<<<dc_blocks((long long)n * cin * h * ((wd + 3) >> 2)), 256, 0, st>>>(ws.dcolT, dx, g);
     HV_LAUNCH_CHECK();
   }
   return HV_OK;

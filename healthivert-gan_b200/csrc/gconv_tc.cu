@@ -53,51 +53,64 @@ static int gc_geom(GcGeom& g, const hv_conv_desc* d) {
   return HV_OK;
 }
 
-// fused source gather of the forward conv (conv_fp32.cu): value of virtual input channel ch at (gy, gx), zero outside
-__device__ __forceinline__ float gc_load(const GcGeom& g, int n, int ch, int gy, int gx) {
-  if (gy < 0 || gy >= g.hin || gx < 0 || gx >= g.win) return 0.f;
+// colT[b][s][r][pc]: row r = ci * kk + tap of image b, pixel s * Pc + pc.  One thread = (b, ci, 8 consecutive pixels): the source of
+// the channel is resolved once, every tap gathers 8 values and writes ONE 16-byte store (the kernel is pure data movement: 9 - 25x
+// the bytes of the input; 2-byte stores per thread ran at a tenth of the HBM rate).
+struct GcSrc { const float* base; int mode, sh, sw; };   // plane of (image, channel) in its own tensor
+__device__ __forceinline__ GcSrc gc_resolve(const GcGeom& g, int n, int ch) {
   int s = 0;
   while (s < g.nsrc - 1 && ch >= g.src[s].channels) { ch -= g.src[s].channels; ++s; }
-  const float* sp = g.src[s].ptr;
-  const int mode = g.src[s].mode, sch = g.src[s].channels;
-  if (mode == HV_SRC_SCALAR) return sp[n];
-  int sh = g.hin, sw = g.win;
-  if (mode == HV_SRC_UP2) { sh >>= 1; sw >>= 1; gy >>= 1; gx >>= 1; }
-  else if (mode == HV_SRC_SUB2) { sh <<= 1; sw <<= 1; gy <<= 1; gx <<= 1; }
-  return __ldg(sp + (((size_t)n * sch + ch) * sh + gy) * sw + gx);
+  GcSrc r;
+  r.mode = g.src[s].mode;
+  r.sh = g.hin; r.sw = g.win;
+  if (r.mode == HV_SRC_UP2) { r.sh >>= 1; r.sw >>= 1; }
+  else if (r.mode == HV_SRC_SUB2) { r.sh <<= 1; r.sw <<= 1; }
+  r.base = r.mode == HV_SRC_SCALAR ? g.src[s].ptr + n : g.src[s].ptr + ((size_t)n * g.src[s].channels + ch) * r.sh * r.sw;
+  return r;
+}
+__device__ __forceinline__ float gc_fetch(const GcGeom& g, const GcSrc& r, int gy, int gx) {
+  if (gy < 0 || gy >= g.hin || gx < 0 || gx >= g.win) return 0.f;
+  if (r.mode == HV_SRC_SCALAR) return __ldg(r.base);
+  if (r.mode == HV_SRC_UP2) { gy >>= 1; gx >>= 1; }
+  else if (r.mode == HV_SRC_SUB2) { gy <<= 1; gx <<= 1; }
+  return __ldg(r.base + (size_t)gy * r.sw + gx);
 }
 
-// colT[b][s][r][pc]: row r = ci * kk + tap of image b, pixel s * Pc + pc.  One thread = (b, ci, p): kk gathers, kk coalesced stores.
 __global__ void __launch_bounds__(256) gc_im2col_kernel(GcGeom g, __nv_bfloat16* __restrict__ colT) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)g.n * g.cin * g.Pp) return;
-  const int p = (int)(i % g.Pp), ci = (int)((i / g.Pp) % g.cin), b = (int)(i / ((long long)g.Pp * g.cin));
-  const int oy = p / g.wout, ox = p - oy * g.wout;
-  const int s = p / g.Pc, pc = p - s * g.Pc;
+  const int P8 = g.Pp >> 3;
+  if (i >= (long long)g.n * g.cin * P8) return;
+  const int p0 = (int)(i % P8) * 8, ci = (int)((i / P8) % g.cin), b = (int)(i / ((long long)P8 * g.cin));
+  const GcSrc src = gc_resolve(g, b, ci);
+  const int s = p0 / g.Pc, pc = p0 - s * g.Pc;            // Pc is a multiple of 64: the 8 pixels stay in one chunk
   __nv_bfloat16* dst = colT + (((size_t)b * g.nsplit + s) * g.Rp + (size_t)ci * g.kk) * g.Pc + pc;
+  int oy[8], ox[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { const int p = p0 + j; oy[j] = p / g.wout; ox[j] = p - oy[j] * g.wout; }
   for (int ky = 0; ky < g.k; ++ky)
     for (int kx = 0; kx < g.k; ++kx) {
-      const float v = p < g.P ? gc_load(g, b, ci, oy * g.stride + ky * g.dil - g.pad, ox * g.stride + kx * g.dil - g.pad) : 0.f;
-      dst[(size_t)(ky * g.k + kx) * g.Pc] = __float2bfloat16(v);
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = __float2bfloat16(p0 + j < g.P ? gc_fetch(g, src, oy[j] * g.stride + ky * g.dil - g.pad, ox[j] * g.stride + kx * g.dil - g.pad) : 0.f);
+      *reinterpret_cast<uint4*>(dst + (size_t)(ky * g.k + kx) * g.Pc) = *reinterpret_cast<const uint4*>(v);
     }
 }
-// padding rows R .. Rp of every (b, s) block are zero
-__global__ void __launch_bounds__(256) gc_zero_rows_kernel(__nv_bfloat16* __restrict__ colT, int blocks, int R, int Rp, int Pc) {
-  const long long per = (long long)(Rp - R) * Pc;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= per * blocks) return;
-  const long long blk = i / per, off = i - blk * per;
-  colT[((size_t)blk * Rp + R) * Pc + off] = __float2bfloat16(0.f);
-}
 
-// dy fp32 [b][cout][P] -> dyb bf16 [b][s][Np][Pc] (wgrad B operand; rows >= cout and pixels >= P are zero)
+// dy fp32 [b][cout][P] -> dyb bf16 [b][s][Np][Pc] (wgrad B operand).  Only the rows of real filters are written: rows >= cout feed
+// output columns >= cout of the GEMM, which nobody reads (a padding ROW or COLUMN of an operand may hold anything; only padding along
+// K - pixels >= P here - must be zero, and is).  One thread = 8 consecutive pixels.
 __global__ void __launch_bounds__(256) gc_cast_dy_kernel(const float* __restrict__ dy, __nv_bfloat16* __restrict__ dyb, GcGeom g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)g.n * g.Np * g.Pp) return;
-  const int p = (int)(i % g.Pp), co = (int)((i / g.Pp) % g.Np), b = (int)(i / ((long long)g.Pp * g.Np));
-  const int s = p / g.Pc, pc = p - s * g.Pc;
-  const float v = (co < g.cout && p < g.P) ? dy[((size_t)b * g.cout + co) * g.P + p] : 0.f;
-  dyb[(((size_t)b * g.nsplit + s) * g.Np + co) * g.Pc + pc] = __float2bfloat16(v);
+  const int P8 = g.Pp >> 3;
+  if (i >= (long long)g.n * g.cout * P8) return;
+  const int p0 = (int)(i % P8) * 8, co = (int)((i / P8) % g.cout), b = (int)(i / ((long long)P8 * g.cout));
+  const int s = p0 / g.Pc, pc = p0 - s * g.Pc;
+  const float* src = dy + ((size_t)b * g.cout + co) * g.P;
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(p0 + j < g.P ? src[p0 + j] : 0.f);
+  *reinterpret_cast<uint4*>(dyb + (((size_t)b * g.nsplit + s) * g.Np + co) * g.Pc + pc) = *reinterpret_cast<const uint4*>(v);
 }
 
 // dw[co][r] = sum over the (b, s) blocks of part[blk][r][co]   (part: fp32 [blocks][Rp][Np])
@@ -133,29 +146,38 @@ __global__ void __launch_bounds__(256) gc_dyT_kernel(const float* __restrict__ d
   for (int r = ty; r < 32; r += 8) dyT[((size_t)b * Pp + p0 + r) * Kc + c0 + tx] = __float2bfloat16(tile[tx][r]);
 }
 
-// dx[b][ci][y][x] = sum over the taps whose output pixel exists: dcolT[b][ci * kk + t][oy * wout + ox], oy = (y + pad - ky * dil) / stride
+// dx[b][ci][y][x] = sum over the taps whose output pixel exists: dcolT[b][ci * kk + t][oy * wout + ox], oy = (y + pad - ky * dil) / stride.
+// One thread = 4 consecutive x of one input row (one 16-byte store; the row / tap arithmetic is shared by the four).
 __global__ void __launch_bounds__(256) gc_col2im_kernel(const __nv_bfloat16* __restrict__ dcolT, float* __restrict__ dx, GcGeom g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)g.n * g.cin * g.hin * g.win) return;
-  const int x = (int)(i % g.win), y = (int)((i / g.win) % g.hin);
-  const long long bc = i / ((long long)g.win * g.hin);
+  const int W4 = (g.win + 3) >> 2;
+  if (i >= (long long)g.n * g.cin * g.hin * W4) return;
+  const int x0 = (int)(i % W4) * 4, y = (int)((i / W4) % g.hin);
+  const long long bc = i / ((long long)W4 * g.hin);
   const int ci = (int)(bc % g.cin), b = (int)(bc / g.cin);
   const __nv_bfloat16* src = dcolT + ((size_t)b * g.Rp + (size_t)ci * g.kk) * g.Pp;
-  float acc = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int ky = 0; ky < g.k; ++ky) {
     const int ty = y + g.pad - ky * g.dil;
     if (ty < 0 || (g.stride == 2 && (ty & 1))) continue;
     const int oy = g.stride == 2 ? ty >> 1 : ty;
     if (oy >= g.hout) continue;
+    const __nv_bfloat16* row = src + (size_t)oy * g.wout;
     for (int kx = 0; kx < g.k; ++kx) {
-      const int tx = x + g.pad - kx * g.dil;
-      if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
-      const int ox = g.stride == 2 ? tx >> 1 : tx;
-      if (ox >= g.wout) continue;
-      acc += __bfloat162float(src[(size_t)(ky * g.k + kx) * g.Pp + oy * g.wout + ox]);
+      const __nv_bfloat16* tap = row + (size_t)(ky * g.k + kx) * g.Pp;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int tx = x0 + j + g.pad - kx * g.dil;
+        if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
+        const int ox = g.stride == 2 ? tx >> 1 : tx;
+        if (ox < g.wout) acc[j] += __bfloat162float(tap[ox]);
+      }
     }
   }
-  dx[i] = acc;
+  float* out = dx + ((size_t)bc * g.hin + y) * g.win + x0;
+  if ((g.win & 3) == 0) *reinterpret_cast<float4*>(out) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  else
+    for (int j = 0; j < 4 && x0 + j < g.win; ++j) out[j] = acc[j];
 }
 
 static inline unsigned gc_blocks(long long n) { return (unsigned)((n + 255) / 256); }
@@ -183,13 +205,10 @@ int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* 
   __nv_bfloat16* colT = (__nv_bfloat16*)base;
   __nv_bfloat16* dyb = (__nv_bfloat16*)(base + gc_al((size_t)blocks * g.Rp * g.Pc * 2));
   float* part = (float*)((char*)dyb + gc_al((size_t)blocks * g.Np * g.Pc * 2));
-  gc_im2col_kernel<<<gc_blocks((long long)g.n * g.cin * g.Pp), 256, 0, st>>>(g, colT);
+  // rows R .. Rp of colT (padding of the GEMM's M) stay unwritten: they only produce output rows that gc_reduce_dw_kernel never reads
+  gc_im2col_kernel<<<gc_blocks((long long)g.n * g.cin * (g.Pp >> 3)), 256, 0, st>>>(g, colT);
   HV_LAUNCH_CHECK();
-  if (g.Rp > g.R) {
-    gc_zero_rows_kernel<<<gc_blocks((long long)blocks * (g.Rp - g.R) * g.Pc), 256, 0, st>>>(colT, blocks, g.R, g.Rp, g.Pc);
-    HV_LAUNCH_CHECK();
-  }
-  gc_cast_dy_kernel<<<gc_blocks((long long)g.n * g.Np * g.Pp), 256, 0, st>>>(dy, dyb, g);
+  gc_cast_dy_kernel<<<gc_blocks((long long)g.n * g.cout * (g.Pp >> 3)), 256, 0, st>>>(dy, dyb, g);
   HV_LAUNCH_CHECK();
   rc = gemm_tc_nt(colT, dyb, part, nullptr, g.Rp, g.Np, g.Pc, blocks, (long long)g.Rp * g.Pc, (long long)g.Np * g.Pc, 0, st);
   if (rc) return rc;
@@ -214,7 +233,7 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
   HV_LAUNCH_CHECK();
   rc = gemm_tc_nt(wt, dyT, dcolT, nullptr, g.Rp, g.Pp, g.Kc, g.n, 0, (long long)g.Pp * g.Kc, 1, st);
   if (rc) return rc;
-  gc_col2im_kernel<<<gc_blocks((long long)g.n * g.cin * g.hin * g.win), 256, 0, st>>>(dcolT, dx, g);
+  gc_col2im_kernel<<<gc_blocks((long long)g.n * g.cin * g.hin * ((g.win + 3) >> 2)), 256, 0, st>>>(dcolT, dx, g);
   HV_LAUNCH_CHECK();
   return HV_OK;
 }
