@@ -78,6 +78,9 @@ SIGNATURES = {
     "hv_multi_tensor_chunk": (c_int, []),
     "hv_adam_step_multi": (c_int, [c_void_p, c_int, c_longlong, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "hv_bucket_copy": (c_int, [c_void_p, c_int, c_longlong, c_void_p, c_float, c_int, c_void_p]),
+    "hv_debug_conv_trace": (c_int, [c_void_p]),
+    "hv_debug_conv_timeline": (c_int, [c_void_p]),
+    "hv_debug_trunk_trace": (c_int, [c_void_p, c_int]),
     "hv_post_forward": (c_int, [c_void_p] * 12 + [c_int, c_int, c_int] + [c_void_p] * 12 + [c_int, c_int, c_int, c_void_p]),
     "hv_conv2d_wgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),
     "hv_conv2d_dgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),

@@ -469,22 +469,45 @@ int gap_fc_sigmoid_bwd(const float* x, const float* s, const float* ds, const fl
 
 // ------------------------------------------------------------------ BatchNorm2d (train) + LeakyReLU (networks.py:583-597)
 // stats[c] = (mean, invstd) of the batch; running stats: momentum update with the unbiased variance (torch semantics)
+// One CTA per channel (two passes: mean, then centred squares - torch's numerics); 16-byte loads with four independent accumulators
+// per thread keep enough bytes in flight for a channel's n * hw * 4 B (the scalar version ran at 0.06 of the HBM peak).
+__device__ __forceinline__ bool bn_vec_ok(const float* x, int hw) { return (hw & 3) == 0 && (reinterpret_cast<size_t>(x) & 15) == 0; }
+
 __global__ void __launch_bounds__(512) bn_stats_kernel(const float* __restrict__ x, float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                                        float* __restrict__ running_mean, float* __restrict__ running_var, int n, int c,
                                                        int hw, float momentum, float eps) {
   __shared__ float red[32];
   const int ch = blockIdx.x;
   const float cnt = (float)n * hw;
+  const bool vec = bn_vec_ok(x, hw);
   float s = 0.f;
   for (int i = 0; i < n; ++i) {
     const float* p = x + ((size_t)i * c + ch) * hw;
-    for (int j = threadIdx.x; j < hw; j += blockDim.x) s += p[j];
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int j = threadIdx.x; j < hw / 4; j += blockDim.x) { const float4 v = __ldg(p4 + j); a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w; }
+      s += (a0 + a1) + (a2 + a3);
+    } else {
+      for (int j = threadIdx.x; j < hw; j += blockDim.x) s += p[j];
+    }
   }
   const float mean = block_sum(s, red) / cnt;
   float q = 0.f;
   for (int i = 0; i < n; ++i) {
     const float* p = x + ((size_t)i * c + ch) * hw;
-    for (int j = threadIdx.x; j < hw; j += blockDim.x) { const float d = p[j] - mean; q = fmaf(d, d, q); }
+    if (vec) {
+      const float4* p4 = reinterpret_cast<const float4*>(p);
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      for (int j = threadIdx.x; j < hw / 4; j += blockDim.x) {
+        const float4 v = __ldg(p4 + j);
+        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+        a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+      }
+      q += (a0 + a1) + (a2 + a3);
+    } else {
+      for (int j = threadIdx.x; j < hw; j += blockDim.x) { const float d = p[j] - mean; q = fmaf(d, d, q); }
+    }
   }
   const float var = block_sum(q, red) / cnt;
   if (threadIdx.x == 0) {
@@ -528,12 +551,26 @@ __global__ void __launch_bounds__(512) bn_bwd_reduce_kernel(const float* __restr
   const int ch = blockIdx.x;
   const float m = mean[ch], is = invstd[ch];
   float sg = 0.f, sgx = 0.f;
+  const bool vec = bn_vec_ok(x, hw) && bn_vec_ok(y, hw) && bn_vec_ok(dy, hw);
   for (int i = 0; i < n; ++i) {
     const size_t base = ((size_t)i * c + ch) * hw;
-    for (int j = threadIdx.x; j < hw; j += blockDim.x) {
-      const float g = dy[base + j] * (y[base + j] > 0.f ? 1.f : slope);
-      sg += g;
-      sgx = fmaf(g, (x[base + j] - m) * is, sgx);
+    if (vec) {
+      const float4 *x4 = reinterpret_cast<const float4*>(x + base), *y4 = reinterpret_cast<const float4*>(y + base),
+                   *d4 = reinterpret_cast<const float4*>(dy + base);
+      for (int j = threadIdx.x; j < hw / 4; j += blockDim.x) {
+        const float4 xv = __ldg(x4 + j), yv = __ldg(y4 + j), dv = __ldg(d4 + j);
+        const float g0 = dv.x * (yv.x > 0.f ? 1.f : slope), g1 = dv.y * (yv.y > 0.f ? 1.f : slope), g2 = dv.z * (yv.z > 0.f ? 1.f : slope),
+                    g3 = dv.w * (yv.w > 0.f ? 1.f : slope);
+        sg += (g0 + g1) + (g2 + g3);
+        sgx = fmaf(g0, (xv.x - m) * is, sgx); sgx = fmaf(g1, (xv.y - m) * is, sgx);
+        sgx = fmaf(g2, (xv.z - m) * is, sgx); sgx = fmaf(g3, (xv.w - m) * is, sgx);
+      }
+    } else {
+      for (int j = threadIdx.x; j < hw; j += blockDim.x) {
+        const float g = dy[base + j] * (y[base + j] > 0.f ? 1.f : slope);
+        sg += g;
+        sgx = fmaf(g, (x[base + j] - m) * is, sgx);
+      }
     }
   }
   sg = block_sum(sg, red);

@@ -355,6 +355,18 @@ int hv_slice_finish(const float* fake_ct, const float* fine_seg, const int32_t* 
 int hv_resample_curve(const double* vol, int d0, int d1, int d2, const double* knots, const double* basis, int npts, int s0,
                       int s1, int order, double cval, double* out, hv_stream_t stream);
 
+/* ======================================================================================
+ * Debug / measurement hooks.  NOT part of the drop-in surface: no reference interface stands behind them; they only
+ * make the library's own kernels observable (tools/trace_conv.py, tools/timeline_forward.py, tools/trace_trunk.py).
+ * dev_buf = NULL switches a hook off.
+ * ==================================================================================== */
+/* CTA 0 of every subsequent conv_tc launch appends (tag, clock64) stamps per role: dev_buf = 12000 + 4 * 400 int64 */
+int hv_debug_conv_trace(void* dev_buf);
+/* conv_tc launch i (host launch order) records {first CTA entry, last CTA exit} globaltimer ns at dev_buf[4 i], [4 i + 1] */
+int hv_debug_conv_timeline(void* dev_buf);
+/* CTA `cta` of every subsequent trunk_tc launch appends (tag, item, clock64) stamps per role: dev_buf = 12000 int64 */
+int hv_debug_trunk_trace(void* dev_buf, int cta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, s), f"{s} declared in include/hv_b200.h but not exported"
     assert set(syms) == set(_lib.SIGNATURES), set(syms) ^ set(_lib.SIGNATURES)
     assert _lib.lib().hv_version() >= 100
+    # ... and nothing else: every extern "C" hv_* symbol of the library is declared (debug hooks included)
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.split()[-1].startswith("hv_") and " T " in l}
+    assert exported == set(syms), exported ^ set(syms)
 
 
 def test_layer_table_matches_reference_architecture():

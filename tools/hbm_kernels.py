@@ -67,6 +67,18 @@ algo["sobel_kernel"] = px * 8
 timed("edge_loss_kernel", lambda: edge_mse_loss(mask_a, mask_b))
 algo["edge_loss_kernel"] = px * 8                       # two mask planes in, a scalar out
 
+# ---- A4 + A5 fused: the whole tail of Pix2PixModel.forward + the edge loss in one pass (hv_post_forward)
+new = lambda: torch.empty(N, 1, H, W, device=dev)
+post_out = [new() for _ in range(8)]
+rows_f, rows_c = (torch.empty(N, 4, dtype=torch.int32, device=dev) for _ in range(2))
+xor_c, loss_c = torch.empty(1, dtype=torch.int64, device=dev), torch.empty(1, device=dev)
+mask_rows = torch.zeros(N, 1, H, W, device=dev)
+mask_rows[:, :, 100:140] = 1
+timed("post_forward_kernel", lambda: check(L.hv_post_forward(
+    ptr(seg_a), ptr(seg_b), ptr(ct), ptr(real), ptr(real), ptr(mask_b), ptr(mask_rows), ptr(pred_h), ptr(pred_h), ptr(x1), ptr(x2), ptr(hh),
+    40, W // 2 - 35, W // 2 + 35, *[ptr(o) for o in post_out], ptr(rows_f), ptr(rows_c), ptr(xor_c), ptr(loss_c), N, H, W, st())))
+algo["post_forward_kernel"] = px * (7 + 8) * 4          # seven fp32 planes in, eight out
+
 # ---- A10 column heights (RHLV): 256^3 uint8 volumes, sagittal and coronal window of 2 * (extent // 5) slices
 label, _, _ = synth.synthetic_volume(seed=2, depth=256)
 lab = torch.as_tensor((label == 20).astype(np.uint8)).cuda()
