@@ -113,8 +113,8 @@ algo["bn_bwd_apply_kernel"] = el * 16                   # x, y, dy read, dx writ
 p = torch.nn.Parameter(torch.randn(512 * 256 * 16, generator=g).cuda())
 p.grad = torch.randn(512 * 256 * 16, generator=g).cuda()
 opt = T.FusedAdam([p])
-timed("adam_kernel", lambda: opt.step())
-algo["adam_kernel"] = p.numel() * 28                    # p, g, m, v read; p, m, v written
+timed("adam_multi_kernel", lambda: opt.step())
+algo["adam_multi_kernel"] = p.numel() * 28              # p, g, m, v read; p, m, v written
 
 # ---- N1 slice preparation (CCL + bounds + plane build), volume -> u8, uint8 pipeline kernels, input packing (inside a forward)
 from healthivert_gan_b200.volume import VolumeSynthesizer
@@ -136,8 +136,9 @@ timed("pipeline step (pl_unpack / pl_finish inside)", lambda: (pipe.submit(0), p
 algo["pl_unpack_kernel"] = px * (2 + 12)                # two u8 planes in, three fp32 planes out
 algo["pl_finish_kernel"] = px * (12 + 3)                # three fp32 planes in, three u8 planes out
 algo["pack_kx_kernel<3, 5>"] = px * (8 + 32)            # 2 fp32 planes (+ a scalar) in, 16 bf16 channels out
-algo["pack_kx_kernel<4, 5>"] = px * (12 + 64)           # 3 fp32 planes in, 32 bf16 channels out
+algo["pack_kx_kernel<1, 5>"] = px * (4 + 32)            # the coarse mask plane in, 16 bf16 channels out
 algo["pack_kx_kernel<1, 3>"] = None
+algo["pack_nbhd4_kernel"] = px * 4 + (px // 4) * 32     # the CAM plane in, its 4x4 neighbourhood per low-res position out
 pipe.close()
 torch.cuda.synchronize()
 print(json.dumps({"algorithmic_bytes": algo, "warm_us_cuda_events": warm}))
