@@ -109,10 +109,12 @@ class Pix2PixModel(BaseModel):
             self.netD_1, self.netD_2, self.netD_3 = mk(), mk(), mk()
             # opt.precision: 'fp32' = parity mode (SIMT kernels, gradients within 1e-4 of autograd); 'bf16' = tensor-core training mode:
             # the discriminators' convolutions (forward, data and weight gradients) and the generator's conv backward run as tcgen05
-            # GEMMs with bf16 operands and fp32 accumulation; the generator forward stays fp32.  opt.d_precision overrides the
-            # discriminator part alone.
+            # GEMMs with bf16 operands and fp32 accumulation, and the generator's conv forward runs on the tcgen05 conv kernel
+            # (opt.g_forward_precision = 'fp32' keeps that part on the SIMT kernels).  opt.d_precision overrides the discriminator part
+            # alone.
             self.precision = getattr(opt, "precision", "fp32")
             T.BACKWARD_PRECISION = self.precision
+            T.FORWARD_PRECISION = getattr(opt, "g_forward_precision", self.precision)
             self.d_precision = getattr(opt, "d_precision", self.precision)
             for net in (self.netD_1, self.netD_2, self.netD_3):
                 net.precision = self.d_precision

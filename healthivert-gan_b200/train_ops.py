@@ -14,6 +14,10 @@ from ._lib import HV_ACT, HV_SRC_DIRECT, HV_SRC_SCALAR, HV_SRC_SUB2, HV_SRC_UP2,
 # fp32 accumulation (hv_conv2d_dgrad_bf16 / _wgrad_bf16).  Set by Pix2PixModel from opt.precision; a process-wide switch because the
 # tape closures of every net consult it when they run.
 BACKWARD_PRECISION = "fp32"
+# 'bf16': the generator's convolution FORWARD runs on the tcgen05 kernel too (hv_conv2d_bf16: operands and the stored activation rounded
+# to bf16, fp32 accumulation); the single-filter output heads (conv17 / conv18, allconv17 / allconv18) stay fp32 so that the images and
+# masks the losses read are not quantised to 8 mantissa bits.
+FORWARD_PRECISION = "fp32"
 _WS = {}
 
 
@@ -105,7 +109,12 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
     hout, wout = (hin + 2 * pad - eff) // stride + 1, (win + 2 * pad - eff) // stride + 1
     d, keep = _desc(srcs, cin, cout, k, stride, pad, dil, act, hin, win, n)
     y = torch.empty(n, cout, hout, wout, device=first.device, dtype=torch.float32)
-    check(_L().hv_conv2d_fwd(d, ptr(weight), ptr(bias), ptr(y), None, _lib.stream()))
+    tc_fwd = (FORWARD_PRECISION == "bf16" and k in (3, 5) and pad == (k - 1) // 2 * dil and 8 <= cout <= 64
+              and (stride == 1 or (stride == 2 and k == 3 and dil == 1 and hin % 2 == 0 and win % 2 == 0)))
+    if tc_fwd:
+        check(_L().hv_conv2d_bf16(d, ptr(weight), ptr(bias), ptr(y), None, 0, _lib.stream()))
+    else:
+        check(_L().hv_conv2d_fwd(d, ptr(weight), ptr(bias), ptr(y), None, _lib.stream()))
     out = Var(y)
     if tape is None:
         return out

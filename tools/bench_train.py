@@ -22,12 +22,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="bf16: tensor-core training mode (D convs + G conv backward)")
     ap.add_argument("--d-precision", default=None, choices=["fp32", "bf16"], help="override for the PatchGAN convolutions alone")
+    ap.add_argument("--g-forward", default=None, choices=["fp32", "bf16"], help="override for the generator's conv forward alone")
     args = ap.parse_args()
     rank, world, local = sharding.world_from_env()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    opt = synth.train_options(gpu_ids=[local], precision=args.precision, **({'d_precision': args.d_precision} if args.d_precision else {}))
+    opt = synth.train_options(gpu_ids=[local], precision=args.precision, **({'d_precision': args.d_precision} if args.d_precision else {}),
+                              **({'g_forward_precision': args.g_forward} if args.g_forward else {}))
     m = Pix2PixModel(opt)
     m.setup(opt)
     m.netG.load_state_dict(synth.synthetic_generator_state_dict())

@@ -43,7 +43,10 @@ def main():
         a["wr"] += d.get("dram__bytes_write.sum", 0.0)
     print(f"| kernel | launches | us (last launch, cold caches) | DRAM read MB | DRAM write MB | algorithmic MB | achieved GB/s | of {peak:.0f} GB/s measured |")
     print("|---|---|---|---|---|---|---|---|")
+    skip = ("at::", "conv_tc_kernel", "gemm_tc_kernel", "ca_tc_", "ca_mask", "ca_offsets", "ca_flow", "sn_prepare", "pack_weights", "tc_gap_fc")
     for name, a in agg.items():
+        if any(k in name for k in skip):      # torch fills / copies of the harness and the tensor-pipe kernels: not this table's subject
+            continue
         ab = None
         for pat, b in algo.items():
             if re.search(pat.replace("<", r"<").replace(">", r">"), name) or pat in name:
