@@ -745,8 +745,15 @@ int tc_conv_setup(TcConv& c, const TcSource* srcs, int nsrc, int k, int stride, 
     if (rc) return rc;
   }
   if (nsrc == 1) p.maps[1] = p.maps[0];
-  HV_CUDA(cudaMalloc(&c.w_packed, p.w_bytes));
-  HV_CUDA(cudaMalloc(&c.bias_pad, c.n_pad * sizeof(float)));
+  if (c.arena) {
+    const size_t wb = ((size_t)p.w_bytes + 255) & ~(size_t)255;
+    HV_CHECK_ARG(wb + c.n_pad * sizeof(float) <= TcConv::kArenaBytes, "tc_conv: packed weights (%zu bytes) exceed the caller's arena", wb);
+    c.w_packed = c.arena;
+    c.bias_pad = reinterpret_cast<float*>(static_cast<char*>(c.arena) + wb);
+  } else {
+    HV_CUDA(cudaMalloc(&c.w_packed, p.w_bytes));
+    HV_CUDA(cudaMalloc(&c.bias_pad, c.n_pad * sizeof(float)));
+  }
   p.w_packed = c.w_packed;
   p.bias = c.bias_pad;
   int dev = 0, sms = 148;

@@ -151,6 +151,10 @@ struct TcConv {
   TcSource src[2];
   int cout_real = 0;
   bool force_generic = false;   // run the FIXED = 0 kernel instance even when a specialised one matches (parity tests)
+  // caller-provided memory for the packed weights + bias (>= kArenaBytes, 256-byte aligned); null: tc_conv_setup allocates (cudaMalloc,
+  // which synchronises the device - fine at plan creation, not inside a training step)
+  void* arena = nullptr;
+  static constexpr size_t kArenaBytes = 4u << 20;
 };
 
 // geometry + tensor maps + tables; allocates the packed-weight / bias buffers

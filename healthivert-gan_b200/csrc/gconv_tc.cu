@@ -10,6 +10,8 @@
 // dx is the gradient over the VIRTUAL concatenated input [n, cin, hin, win] of the forward descriptor, exactly like hv_conv2d_dgrad;
 // the host routes channel ranges back to their source tensors.  fp32 SIMT kernels (train_ops.cu) remain the parity path.
 #include <cuda_bf16.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include "hv_common.cuh"
 #include "kernels.h"
 
@@ -17,6 +19,8 @@ namespace hv {
 
 int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const float* colscale, int M, int N, int K, int batch,
                long long strideA, long long strideB, int out_bf16, cudaStream_t st);
+int gemm_tc_taps(const __nv_bfloat16* DY, const __nv_bfloat16* X, float* part, int n, int cout, int cin, int plane, const int* tap_off,
+                 const int* tap_rep, int nrep, int ntaps, int tpm, int co8, int bn, int nkc, int kb0, int kblocks, cudaStream_t st);
 
 struct GcGeom {
   hv_conv_src src[4];
@@ -180,19 +184,156 @@ __global__ void __launch_bounds__(256) gc_col2im_kernel(const __nv_bfloat16* __r
     for (int j = 0; j < 4 && x0 + j < g.win; ++j) out[j] = acc[j];
 }
 
+// wf[ci][co][kk - 1 - t] = w[co][ci][t]: the data gradient of a stride-1 'same' convolution is the convolution of dy with these
+__global__ void __launch_bounds__(256) gc_flip_w_kernel(const float* __restrict__ w, float* __restrict__ wf, int cout, int cin, int kk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * kk) return;
+  const int t = i % kk, ci = (i / kk) % cin, co = i / (kk * cin);
+  wf[((size_t)ci * cout + co) * kk + (kk - 1 - t)] = w[i];
+}
+
 static inline unsigned gc_blocks(long long n) { return (unsigned)((n + 255) / 256); }
 static inline size_t gc_al(size_t b) { return (b + 255) & ~(size_t)255; }
+
+// ---- weight gradient of the stride-1 'same' convolutions without an im2col operand (gemm_tc_taps) -----------------------------------
+// Both operands are bf16 PLANES: the (virtual, concatenated) input X[b][ci] and the output gradient DY[b][co] on the same zero-bordered
+// grid - `pad` zero rows above and below, ONE zero gap of bl = roundup(pad, 8) columns between consecutive rows (it is the right border
+// of one row and the left border of the next), pixel (y, x) at position (y + pad) * pitch + bl + x.  A filter tap is then a constant
+// shift of the position, and dW[co][ci][tap] = sum_k DY[co][k - off(tap)] * X[ci][k] is a GEMM whose A operand is read through shifted
+// TMA boxes: 1x the input bytes instead of the k*k x of an im2col operand.  The innermost TMA coordinate must be 16-byte aligned, so
+// the part of a shift below 8 positions (the horizontal tap offset (kx - c) * dil mod 8; pitch is a multiple of 8) is taken out of
+// pre-shifted REPLICAS of the DY planes: replica j holds DY moved right by r_j positions, one replica per distinct r_j (k of them, or
+// one when dil is a multiple of 8).
+struct GpGeom {
+  int bl, pitch, rows, plane;     // plane: positions per (image, channel), a multiple of 8
+  int co8, tpm, ntg, bn;          // filter rows per tap (cout rounded up to 8), taps per 128-row tile, tap groups, GEMM N (cin padded)
+  int kb0, kblocks, nkc;          // first 64-position block holding a real pixel, blocks per K chunk, K chunks per image
+  int tap_off[25];                // aligned part of the tap shift (multiple of 8 positions)
+  int tap_rep[25];                // replica of the DY planes that carries the rest of it
+  int nrep, rep_shift[5];         // replica j = DY moved right by rep_shift[j] (0 .. 7) positions
+};
+
+// A/B switches (environment HV_DGRAD_GEMM / HV_WGRAD_IM2COL, or hv_debug_backward_paths): bit 0: data gradient through the GEMM +
+// col2im path for every layer, bit 1: weight gradient through the explicit im2col operand for every layer
+static int g_backward_paths = -1;
+
+static bool gp_eligible(const hv_conv_desc* d) {
+  if (g_backward_paths < 0) g_backward_paths = (getenv("HV_DGRAD_GEMM") ? 1 : 0) | (getenv("HV_WGRAD_IM2COL") ? 2 : 0);
+  const bool off = (g_backward_paths & 2) != 0;
+  return !off && (d->win & 7) == 0 && d->stride == 1 && (d->k == 3 || d->k == 5) && d->pad == (d->k - 1) / 2 * d->dil && d->cout <= 128 && d->cin <= 256;
+}
+
+static void gp_geom(GpGeom& q, const GcGeom& g) {
+  q.bl = (g.pad + 7) & ~7;
+  q.pitch = g.win + q.bl;
+  q.rows = g.hin + 2 * g.pad;
+  q.plane = (q.rows * q.pitch + q.bl + 7) & ~7;
+  q.co8 = (g.cout + 7) & ~7;
+  q.tpm = 128 / q.co8 < g.kk ? 128 / q.co8 : g.kk;
+  q.ntg = (g.kk + q.tpm - 1) / q.tpm;
+  q.bn = g.cin <= 32 ? 32 : (g.cin <= 64 ? 64 : (g.cin <= 128 ? 128 : 256));
+  const int first = g.pad * q.pitch + q.bl, last = (g.pad + g.hin - 1) * q.pitch + q.bl + g.win;   // real pixels of X: [first, last)
+  q.kb0 = first / 64;
+  const int kb_total = (last + 63) / 64 - q.kb0;
+  int nkc = (296 + g.n * q.ntg - 1) / (g.n * q.ntg);
+  if (nkc > kb_total / 8) nkc = kb_total / 8;
+  if (nkc < 1) nkc = 1;
+  q.kblocks = (kb_total + nkc - 1) / nkc;
+  q.nkc = (kb_total + q.kblocks - 1) / q.kblocks;
+  const int c = g.k / 2;
+  q.nrep = 0;
+  for (int kx = 0; kx < g.k; ++kx) {
+    const int sx = (kx - c) * g.dil, r = ((sx % 8) + 8) % 8;   // DY[k - off] = replica[k - (off - r)], off - r a multiple of 8
+    int j = 0;
+    while (j < q.nrep && q.rep_shift[j] != r) ++j;
+    if (j == q.nrep) q.rep_shift[q.nrep++] = r;
+    for (int ky = 0; ky < g.k; ++ky) {
+      q.tap_off[ky * g.k + kx] = (ky - c) * g.dil * q.pitch + sx - r;
+      q.tap_rep[ky * g.k + kx] = j;
+    }
+  }
+}
+
+// X planes: one thread = 8 consecutive positions of one (image, channel) plane (one 16-byte store); borders and the tail are zeros
+__global__ void __launch_bounds__(256) gp_planes_x_kernel(GcGeom g, GpGeom q, __nv_bfloat16* __restrict__ X) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P8 = q.plane >> 3;
+  if (i >= (long long)g.n * g.cin * P8) return;
+  const int pos0 = (int)(i % P8) * 8, ci = (int)((i / P8) % g.cin), b = (int)(i / ((long long)P8 * g.cin));
+  const GcSrc src = gc_resolve(g, b, ci);
+  int row = pos0 / q.pitch, col = pos0 - row * q.pitch;
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[j] = __float2bfloat16(gc_fetch(g, src, row - g.pad, col - q.bl));   // 0 outside the image
+    if (++col == q.pitch) { col = 0; ++row; }
+  }
+  *reinterpret_cast<uint4*>(X + ((size_t)b * g.cin + ci) * q.plane + pos0) = *reinterpret_cast<const uint4*>(v);
+}
+
+// DY planes [b][replica][cout][plane] from the fp32 pre-activation gradient [b][cout][hin * win] (stride 1: output extent == input
+// extent); replica j holds the plane moved right by rep_shift[j] positions.  One thread = 8 positions of one (image, filter) plane.
+__global__ void __launch_bounds__(256) gp_planes_dy_kernel(const float* __restrict__ dy, GcGeom g, GpGeom q, __nv_bfloat16* __restrict__ DY) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int P8 = q.plane >> 3;
+  if (i >= (long long)g.n * g.cout * P8) return;
+  const int pos0 = (int)(i % P8) * 8;
+  const long long bc = i / P8;
+  const int co = (int)(bc % g.cout), b = (int)(bc / g.cout);
+  const float* src = dy + (size_t)bc * g.hin * g.win;
+  // positions pos0 - 7 .. pos0 + 7 cover every replica's 8 values
+  float w[15];
+  int row = (pos0 - 7 + q.pitch) / q.pitch - 1, col = pos0 - 7 - row * q.pitch;   // floor division for pos0 - 7 >= -7
+#pragma unroll
+  for (int j = 0; j < 15; ++j) {
+    const int y = row - g.pad, x = col - q.bl;
+    w[j] = (y >= 0 && y < g.hin && x >= 0 && x < g.win) ? __ldg(src + (size_t)y * g.win + x) : 0.f;
+    if (++col == q.pitch) { col = 0; ++row; }
+  }
+  for (int r = 0; r < q.nrep; ++r) {
+    const int sh = q.rep_shift[r];
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t = (sh == u) ? w[7 + j - u] : t;     // replica[pos] = plane[pos - sh]
+      v[j] = __float2bfloat16(t);
+    }
+    *reinterpret_cast<uint4*>(DY + (((size_t)b * q.nrep + r) * g.cout + co) * q.plane + pos0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+// dw[co][ci][t] = sum over the (image, K chunk) blocks of part[(blk * ntg + t / tpm)][(t % tpm) * co8 + co][ci]; ci fastest: coalesced reads
+__global__ void __launch_bounds__(256) gp_reduce_dw_kernel(const float* __restrict__ part, float* __restrict__ dw, int blocks, int cout, int cin, int kk,
+                                                           int tpm, int ntg, int co8, int bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * cin * kk) return;
+  const int ci = i % cin, co = (i / cin) % cout, t = i / (cin * cout);
+  const float* src = part + ((size_t)(t / tpm) * 128 + (size_t)(t % tpm) * co8 + co) * bn + ci;
+  const size_t step = (size_t)ntg * 128 * bn;
+  float s = 0.f;
+  for (int b = 0; b < blocks; ++b) s += src[(size_t)b * step];
+  dw[((size_t)co * cin + ci) * kk + t] = s;
+}
 
 size_t gconv_wgrad_workspace_bytes(const hv_conv_desc* d) {
   GcGeom g;
   if (gc_geom(g, d)) return 0;
+  if (gp_eligible(d)) {
+    GpGeom q;
+    gp_geom(q, g);
+    return gc_al((size_t)g.n * g.cin * q.plane * 2) + gc_al((size_t)g.n * q.nrep * g.cout * q.plane * 2) + gc_al((size_t)g.n * q.nkc * q.ntg * 128 * q.bn * 4);
+  }
   const size_t blocks = (size_t)g.n * g.nsplit;
   return gc_al(blocks * g.Rp * g.Pc * 2) + gc_al(blocks * g.Np * g.Pc * 2) + gc_al(blocks * g.Rp * g.Np * 4);
 }
 size_t gconv_dgrad_workspace_bytes(const hv_conv_desc* d) {
   GcGeom g;
   if (gc_geom(g, d)) return 0;
-  return gc_al((size_t)g.Rp * g.Kc * 2) + gc_al((size_t)g.n * g.Pp * g.Kc * 2) + gc_al((size_t)g.n * g.Rp * g.Pp * 2);
+  const size_t gemm_path = gc_al((size_t)g.Rp * g.Kc * 2) + gc_al((size_t)g.n * g.Pp * g.Kc * 2) + gc_al((size_t)g.n * g.Rp * g.Pp * 2);
+  const size_t flipped = gc_al((size_t)g.cout * g.R * 4);
+  return gemm_path > flipped ? gemm_path : flipped;
 }
 
 int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* db, void* workspace, cudaStream_t st) {
@@ -200,8 +341,37 @@ int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* 
   GcGeom g;
   int rc = gc_geom(g, d);
   if (rc) return rc;
-  const int blocks = g.n * g.nsplit;
   char* base = (char*)workspace;
+  if (gp_eligible(d)) {
+    GpGeom q;
+    gp_geom(q, g);
+    __nv_bfloat16* X = (__nv_bfloat16*)base;
+    __nv_bfloat16* DY = (__nv_bfloat16*)(base + gc_al((size_t)g.n * g.cin * q.plane * 2));
+    float* part = (float*)((char*)DY + gc_al((size_t)g.n * q.nrep * g.cout * q.plane * 2));
+    static const bool dbg = getenv("HV_GP_DEBUG") != nullptr;
+#define GP_DBG(what)                                                                                                        \
+  if (dbg) {                                                                                                                \
+    cudaError_t e = cudaStreamSynchronize(st);                                                                              \
+    fprintf(stderr, "gp wgrad: %s -> %s (plane %d pitch %d co8 %d tpm %d ntg %d bn %d kb0 %d kblocks %d nkc %d)\n", what,  \
+            cudaGetErrorString(e), q.plane, q.pitch, q.co8, q.tpm, q.ntg, q.bn, q.kb0, q.kblocks, q.nkc);                   \
+  }
+    gp_planes_x_kernel<<<gc_blocks((long long)g.n * g.cin * (q.plane >> 3)), 256, 0, st>>>(g, q, X);
+    HV_LAUNCH_CHECK();
+    GP_DBG("planes_x");
+    gp_planes_dy_kernel<<<gc_blocks((long long)g.n * g.cout * (q.plane >> 3)), 256, 0, st>>>(dy, g, q, DY);
+    HV_LAUNCH_CHECK();
+    GP_DBG("planes_dy");
+    rc = gemm_tc_taps(DY, X, part, g.n, g.cout, g.cin, q.plane, q.tap_off, q.tap_rep, q.nrep, g.kk, q.tpm, q.co8, q.bn, q.nkc, q.kb0, q.kblocks, st);
+    if (rc) return rc;
+    GP_DBG("gemm_tc_taps");
+    gp_reduce_dw_kernel<<<gc_blocks((long long)g.cout * g.cin * g.kk), 256, 0, st>>>(part, dw, g.n * q.nkc, g.cout, g.cin, g.kk, q.tpm, q.ntg, q.co8, q.bn);
+    HV_LAUNCH_CHECK();
+    GP_DBG("reduce");
+#undef GP_DBG
+    if (db) return channel_sum(dy, db, g.n, g.cout, g.P, st);
+    return HV_OK;
+  }
+  const int blocks = g.n * g.nsplit;
   __nv_bfloat16* colT = (__nv_bfloat16*)base;
   __nv_bfloat16* dyb = (__nv_bfloat16*)(base + gc_al((size_t)blocks * g.Rp * g.Pc * 2));
   float* part = (float*)((char*)dyb + gc_al((size_t)blocks * g.Np * g.Pc * 2));
@@ -224,6 +394,19 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
   int rc = gc_geom(g, d);
   if (rc) return rc;
   char* base = (char*)workspace;
+  if (g_backward_paths < 0) g_backward_paths = (getenv("HV_DGRAD_GEMM") ? 1 : 0) | (getenv("HV_WGRAD_IM2COL") ? 2 : 0);
+  const bool gemm_dgrad = (g_backward_paths & 1) != 0;   // A/B switch: the GEMM + col2im path for every layer
+  if (!gemm_dgrad && d->stride == 1 && (d->k == 3 || d->k == 5) && d->pad == (d->k - 1) / 2 * d->dil && d->cin <= 64) {
+    // stride-1 'same' convolution (41 of the generator's 47 layers): dx = conv(dy, flipped / transposed filters) on the implicit-GEMM
+    // tcgen05 kernel of the forward - no dyT / dcolT operands, no col2im pass.  fp32 accumulation over all taps, ONE rounding to bf16.
+    float* wf = reinterpret_cast<float*>(base);
+    gc_flip_w_kernel<<<gc_blocks((long long)g.cout * g.cin * g.kk), 256, 0, st>>>(w, wf, g.cout, g.cin, g.kk);
+    HV_LAUNCH_CHECK();
+    hv_conv_desc t = *d;
+    t.cin = d->cout; t.cout = d->cin; t.act = HV_ACT_NONE; t.nsrc = 1;
+    t.src[0].ptr = dy; t.src[0].channels = d->cout; t.src[0].mode = HV_SRC_DIRECT;
+    return conv2d_bf16(&t, wf, nullptr, dx, nullptr, 0, st);
+  }
   __nv_bfloat16* wt = (__nv_bfloat16*)base;
   __nv_bfloat16* dyT = (__nv_bfloat16*)(base + gc_al((size_t)g.Rp * g.Kc * 2));
   __nv_bfloat16* dcolT = (__nv_bfloat16*)((char*)dyT + gc_al((size_t)g.n * g.Pp * g.Kc * 2));
@@ -241,6 +424,7 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
 }  // namespace hv
 
 extern "C" {
+int hv_debug_backward_paths(int bits) { hv::g_backward_paths = bits; return 0; }
 size_t hv_conv2d_wgrad_bf16_workspace_bytes(const hv_conv_desc* d) { return hv::gconv_wgrad_workspace_bytes(d); }
 size_t hv_conv2d_dgrad_bf16_workspace_bytes(const hv_conv_desc* d) { return hv::gconv_dgrad_workspace_bytes(d); }
 int hv_conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* db, void* workspace, hv_stream_t s) {

@@ -33,6 +33,13 @@ struct GemmParams {
   int M, N, K, batch;
   int tiles_m, tiles_n, total_tiles, kblocks;
   int a_bcast;              // A is shared by every batch entry (batch stride 0): its tensor map has a batch extent of 1
+  // tap mode (weight gradient of a stride-1 convolution without an im2col operand, gemm_tc_taps below): a tile is
+  // (image, K chunk, tap group); its A rows are (tap, filter): one TMA box of co8 filter rows per tap, each read at its own SHIFT
+  // along K (K = positions of the zero-bordered plane; a tap is a constant shift of the flattened position); B = the input planes
+  int tap_mode, ntaps, tpm, co8, ntg, nkc, kb0;   // kb0: first K block (the planes start with all-zero border rows)
+  int tap_off[25];           // multiples of 8 positions: the innermost TMA coordinate must be 16-byte aligned (an odd element offset
+  int tap_rep[25];           // raises "illegal instruction"); the sub-8 part of a shift selects a pre-shifted REPLICA of the A planes
+  int nrep;
 };
 
 template <int BN, bool OUT_BF16>
@@ -79,6 +86,25 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     uint32_t phase = 0;
     const uint32_t ring = smem_u32(smem);
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      if (p.tap_mode) {
+        const int tg = tile % p.ntg, blk = tile / p.ntg;
+        const int kc = blk % p.nkc, img = blk / p.nkc;
+        const int t0 = tg * p.tpm, nt_here = min(p.tpm, p.ntaps - t0);
+        const uint32_t bytes = (uint32_t)(nt_here * p.co8 + BN) * 128u;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(bar_empty + 8u * slot, phase ^ 1u);
+          if (leader) {
+            const uint32_t fb = bar_full + 8u * slot, dst = ring + (uint32_t)slot * STAGE_BYTES;
+            const int k0 = (p.kb0 + kc * p.kblocks + kb) * G_BK;
+            mbar_expect_tx(fb, bytes);
+            for (int tl = 0; tl < nt_here; ++tl)   // out-of-range positions (before / after the plane) are zero-filled by TMA
+              tma_load_3d(dst + (uint32_t)(tl * p.co8) * 128u, &p.map_a, fb, k0 - p.tap_off[t0 + tl], 0, img * p.nrep + p.tap_rep[t0 + tl]);
+            tma_load_3d(dst + A_BYTES, &p.map_b, fb, k0, 0, img);
+          }
+          if (++slot == G_STAGES) { slot = 0; phase ^= 1u; }
+        }
+        continue;
+      }
       const int b = tile / tiles_per_batch, r = tile - b * tiles_per_batch;
       const int mt = r / p.tiles_n, nt = r - mt * p.tiles_n;
       for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -200,12 +226,14 @@ static PFN_encodeTiled gemm_get_encode() {
   return fn;
 }
 
-static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int batch, long long batch_stride_elems, int box_rows) {
+static int gemm_map(CUtensorMap* map, const void* base, int rows, int K, int batch, long long batch_stride_elems, int box_rows,
+                    long long row_stride_elems = 0) {
   PFN_encodeTiled enc = gemm_get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable"); return HV_ERR_CUDA; }
+  if (row_stride_elems == 0) row_stride_elems = K;
   if (batch_stride_elems == 0) { batch = 1; batch_stride_elems = (long long)rows * K; }   // broadcast operand
   cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)batch};
-  cuuint64_t strides[2] = {(cuuint64_t)K * 2, (cuuint64_t)batch_stride_elems * 2};
+  cuuint64_t strides[2] = {(cuuint64_t)row_stride_elems * 2, (cuuint64_t)batch_stride_elems * 2};
   cuuint32_t box[3] = {(cuuint32_t)G_BK, (cuuint32_t)box_rows, 1};
   cuuint32_t es[3] = {1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
@@ -258,6 +286,7 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
     next = (next + 1) % 4;
     e = Cached{A, B, M, N, K, batch, bn, strideA, strideB, p.map_a, p.map_b};
   }
+  p.tap_mode = 0;
   p.c = C; p.colscale = colscale; p.M = M; p.N = N; p.K = K; p.batch = batch; p.a_bcast = strideA == 0 ? 1 : 0;
   p.tiles_m = M / G_BM; p.tiles_n = N / bn; p.total_tiles = p.tiles_m * p.tiles_n * batch; p.kblocks = K / G_BK;
   static int sms = 0;
@@ -271,6 +300,42 @@ int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const fl
   if (bn == 64) { HV_CHECK_ARG(!out_bf16, "gemm_tc: narrow tiles write fp32"); return gemm_launch<64, false>(p, grid, st); }
   if (bn == 32) { HV_CHECK_ARG(!out_bf16, "gemm_tc: narrow tiles write fp32"); return gemm_launch<32, false>(p, grid, st); }
   return out_bf16 ? gemm_launch<128, true>(p, grid, st) : gemm_launch<128, false>(p, grid, st);
+}
+
+// Weight gradient of a stride-1 convolution as shifted-operand GEMMs (no im2col):
+//   part[(img, kc, tg)][tl * co8 + co][ci] = sum over the positions k of K chunk kc of  DY[img][rep[t]][co][k - off[t]] * X[img][ci][k],   t = tg * tpm + tl
+// DY: bf16 [n][nrep][cout][plane], X: bf16 [n][cin][plane], zero-bordered planes of `plane` positions (a multiple of 8); off[t] are
+// multiples of 8; part: fp32 [n * nkc * ntg][128][bn].  Rows of filters >= cout and of inputs >= cin are zero-filled by TMA (the boxes
+// are taller than the tensors).
+int gemm_tc_taps(const __nv_bfloat16* DY, const __nv_bfloat16* X, float* part, int n, int cout, int cin, int plane, const int* tap_off,
+                 const int* tap_rep, int nrep, int ntaps, int tpm, int co8, int bn, int nkc, int kb0, int kblocks, cudaStream_t st) {
+  HV_CHECK_ARG(DY && X && part && tap_off && tap_rep && nrep >= 1, "gemm_tc_taps: null argument");
+  for (int i = 0; i < ntaps && i < 25; ++i)
+    HV_CHECK_ARG((tap_off[i] & 7) == 0 && tap_rep[i] >= 0 && tap_rep[i] < nrep, "gemm_tc_taps: tap %d: offset %d / replica %d", i, tap_off[i], tap_rep[i]);
+  HV_CHECK_ARG(ntaps >= 1 && ntaps <= 25 && tpm >= 1 && tpm * co8 <= G_BM && (co8 & 7) == 0 && (plane & 7) == 0 && cout <= co8,
+               "gemm_tc_taps: bad tap tiling (taps %d, per tile %d, filter rows %d, plane %d)", ntaps, tpm, co8, plane);
+  HV_CHECK_ARG(bn == 32 || bn == 64 || bn == 128 || bn == 256, "gemm_tc_taps: bn = %d", bn);
+  GemmParams p;
+  int rc = gemm_map(&p.map_a, DY, cout, plane, n * nrep, (long long)cout * plane, co8);
+  if (rc) return rc;
+  rc = gemm_map(&p.map_b, X, cin, plane, n, (long long)cin * plane, bn);
+  if (rc) return rc;
+  p.tap_mode = 1; p.ntaps = ntaps; p.tpm = tpm; p.co8 = co8; p.ntg = (ntaps + tpm - 1) / tpm; p.nkc = nkc; p.kb0 = kb0;
+  for (int i = 0; i < 25; ++i) p.tap_off[i] = i < ntaps ? tap_off[i] : 0;
+  for (int i = 0; i < 25; ++i) p.tap_rep[i] = i < ntaps ? tap_rep[i] : 0;
+  p.nrep = nrep;
+  p.c = part; p.colscale = nullptr; p.M = G_BM; p.N = bn; p.K = kblocks * G_BK; p.a_bcast = 0;
+  p.tiles_m = p.tiles_n = 1; p.batch = p.total_tiles = n * nkc * p.ntg; p.kblocks = kblocks;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  const int grid = p.total_tiles < sms ? p.total_tiles : sms;
+  switch (bn) {
+    case 32: return gemm_launch<32, false>(p, grid, st);
+    case 64: return gemm_launch<64, false>(p, grid, st);
+    case 128: return gemm_launch<128, false>(p, grid, st);
+    default: return gemm_launch<256, false>(p, grid, st);
+  }
 }
 
 }  // namespace hv

@@ -32,6 +32,8 @@ int conv2d_fwd_fp32_sub(const hv_conv_desc* d, const float* w, const float* bias
 
 // out[ch] = sum over (n, hw) of x[n][ch][:] (deterministic two-pass sum; bias gradients)
 int channel_sum(const float* x, float* out, int n, int c, int hw, cudaStream_t st);
+// stand-alone tcgen05 convolution on fp32 NCHW tensors (conv_tc_api.cu); buffers come from the stream's scratch
+int conv2d_bf16(const hv_conv_desc* d, const float* w, const float* bias, float* y, float* y2, int flags, cudaStream_t st);
 
 int gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* out, int n, int c,
                    int hw, cudaStream_t st);

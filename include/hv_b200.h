@@ -366,6 +366,9 @@ int hv_debug_conv_trace(void* dev_buf);
 int hv_debug_conv_timeline(void* dev_buf);
 /* CTA `cta` of every subsequent trunk_tc launch appends (tag, item, clock64) stamps per role: dev_buf = 12000 int64 */
 int hv_debug_trunk_trace(void* dev_buf, int cta);
+/* A/B switch of the bf16 conv backward: bit 0 = data gradient through the GEMM + col2im path for every layer, bit 1 = weight
+ * gradient through the explicit im2col operand for every layer (0: the shifted-operand paths where they apply)            */
+int hv_debug_backward_paths(int bits);
 
 #ifdef __cplusplus
 }
