@@ -1052,8 +1052,31 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int src_channels
   dst.ptr[dst.chunk_base(n, ch >> 3) + dst.pos(y, x) * 8 + (ch & 7)] = __float2bfloat16(v);
 }
 
+// whole chunks: one thread = one pixel of one 8-channel chunk - eight plane reads (each coalesced across the warp), ONE 16-byte store
+// (the scalar kernel above writes 2 bytes per thread at a 16-byte stride: an eighth of every sector per warp instruction)
+__global__ void __launch_bounds__(256) pack_nchw_chunks_kernel(const float* __restrict__ src, int src_channels, int mode, TcBuf dst, int chunk0) {
+  const int n = blockIdx.z, cc = blockIdx.y, h = dst.h, w = dst.w;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w;
+  int sh = h, sw = w, sy = y, sx = x;
+  if (mode == HV_SRC_SUB2) { sh = 2 * h; sw = 2 * w; sy = 2 * y; sx = 2 * x; }
+  else if (mode == HV_SRC_UP2) { sh = h / 2; sw = w / 2; sy = y / 2; sx = x / 2; }
+  const float* p = src + (((size_t)n * src_channels + cc * 8) * sh + sy) * sw + sx;
+  const size_t plane = (size_t)sh * sw;
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16(__ldg(p + j * plane));
+  *reinterpret_cast<uint4*>(dst.ptr + dst.chunk_base(n, chunk0 + cc) + dst.pos(y, x) * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
 int tc_pack_nchw(const float* src, int src_channels, int mode, const TcBuf& dst, int ch0, cudaStream_t st) {
   HV_CHECK_ARG(src && dst.ptr && ch0 + src_channels <= dst.chunks * 8, "tc_pack_nchw: bad argument");
+  if ((ch0 & 7) == 0 && (src_channels & 7) == 0 && mode != HV_SRC_SCALAR) {
+    pack_nchw_chunks_kernel<<<dim3((dst.h * dst.w + 255) / 256, src_channels / 8, dst.n), 256, 0, st>>>(src, src_channels, mode, dst, ch0 >> 3);
+    HV_LAUNCH_CHECK();
+    return HV_OK;
+  }
   dim3 grid((dst.h * dst.w + 255) / 256, src_channels, dst.n);
   pack_nchw_kernel<<<grid, 256, 0, st>>>(src, src_channels, mode, dst, ch0);
   HV_LAUNCH_CHECK();
@@ -1172,8 +1195,26 @@ __global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __re
       __bfloat162float(src.ptr[src.chunk_base(n, ch >> 3) + src.pos(y * sub, x * sub) * 8 + (ch & 7)]);
 }
 
+// whole chunks: one 16-byte load per thread, eight plane stores (each coalesced across the warp)
+__global__ void __launch_bounds__(256) unpack_nchw_chunks_kernel(TcBuf src, int chunk0, int channels, float* __restrict__ dst, int sub) {
+  const int n = blockIdx.z, cc = blockIdx.y, h = src.h / sub, w = src.w / sub;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= h * w) return;
+  const int y = i / w, x = i - y * w;
+  const uint4 raw = *reinterpret_cast<const uint4*>(src.ptr + src.chunk_base(n, chunk0 + cc) + src.pos(y * sub, x * sub) * 8);
+  const __nv_bfloat16* v = reinterpret_cast<const __nv_bfloat16*>(&raw);
+  float* out = dst + ((size_t)n * channels + cc * 8) * h * w + i;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) out[(size_t)j * h * w] = __bfloat162float(v[j]);
+}
+
 int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st, int sub) {
   HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8 && (sub == 1 || sub == 2), "tc_unpack_nchw: bad argument");
+  if ((ch0 & 7) == 0 && (channels & 7) == 0) {
+    unpack_nchw_chunks_kernel<<<dim3((src.h / sub * (src.w / sub) + 255) / 256, channels / 8, src.n), 256, 0, st>>>(src, ch0 >> 3, channels, dst, sub);
+    HV_LAUNCH_CHECK();
+    return HV_OK;
+  }
   dim3 grid((src.h / sub * (src.w / sub) + 255) / 256, channels, src.n);
   unpack_nchw_kernel<<<grid, 256, 0, st>>>(src, ch0, channels, dst, sub);
   HV_LAUNCH_CHECK();

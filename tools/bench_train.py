@@ -54,6 +54,7 @@ def main():
         m.set_input(batch)
         m.optimize_parameters()
     e1.record()
+    host = (time.perf_counter() - t0) / args.steps * 1e3     # time to ENQUEUE a step (the host runs ahead of the device unless it is the bound)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / args.steps
     wall = (time.perf_counter() - t0) / args.steps * 1e3
@@ -63,7 +64,7 @@ def main():
         ms = float(t)
     if rank == 0:
         print(json.dumps({"workload": "pix2pix optimize_parameters (BASELINE.json configs[3])", "global_batch": args.batch, "n_gpus": world,
-                          "ms_per_step_device": ms, "ms_per_step_wall": wall, "samples_per_s": args.batch / ms * 1e3,
+                          "ms_per_step_device": ms, "ms_per_step_wall": wall, "ms_per_step_host_enqueue": host, "samples_per_s": args.batch / ms * 1e3,
                           "launches_per_step": (_lib.launch_count() - l0) / args.steps, "precision": args.precision, "d_precision": args.d_precision or args.precision,
                           "losses": {k: round(v, 4) for k, v in m.get_current_losses().items()}}))
     if world > 1:
