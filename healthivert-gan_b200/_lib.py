@@ -82,6 +82,8 @@ SIGNATURES = {
     "hv_debug_conv_timeline": (c_int, [c_void_p]),
     "hv_debug_trunk_trace": (c_int, [c_void_p, c_int]),
     "hv_debug_backward_paths": (c_int, [c_int]),
+    "hv_sn_prepare_multi": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "hv_sn_bwd_multi": (c_int, [c_void_p, c_int, c_void_p]),
     "hv_post_forward": (c_int, [c_void_p] * 12 + [c_int, c_int, c_int] + [c_void_p] * 12 + [c_int, c_int, c_int, c_void_p]),
     "hv_conv2d_wgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),
     "hv_conv2d_dgrad_bf16_workspace_bytes": (c_size_t, [POINTER(hv_conv_desc)]),

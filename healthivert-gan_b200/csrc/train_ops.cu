@@ -424,6 +424,29 @@ int sn_bwd(const float* dweff, const float* weff, const float* u, const float* v
   return HV_OK;
 }
 
+// all layers of a net in one launch (one CTA per layer): rows of seven 64-bit words {dweff, weff, u, v, sigma, dw, cout | kdim << 32}
+struct SnBwdJob { const float* dweff; const float* weff; const float* u; const float* v; const float* sigma; float* dw; int cout, kdim; };
+__global__ void __launch_bounds__(512) sn_bwd_multi_kernel(const SnBwdJob* __restrict__ jobs) {
+  const SnBwdJob j = jobs[blockIdx.x];
+  __shared__ float red[32];
+  const int total = j.cout * j.kdim;
+  float dot = 0.f;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) dot = fmaf(j.dweff[i], j.weff[i], dot);
+  dot = block_sum(dot, red);
+  const float inv = 1.f / j.sigma[0];
+  for (int i = threadIdx.x; i < total; i += blockDim.x) {
+    const int r = i / j.kdim, c = i - r * j.kdim;
+    j.dw[i] = (j.dweff[i] - dot * j.u[r] * j.v[c]) * inv;
+  }
+}
+
+int sn_bwd_multi(const void* d_jobs, int njobs, cudaStream_t st) {
+  HV_CHECK_ARG(d_jobs && njobs > 0, "sn_bwd_multi: bad argument");
+  sn_bwd_multi_kernel<<<njobs, 512, 0, st>>>(static_cast<const SnBwdJob*>(d_jobs));
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 // ------------------------------------------------------------------ SHRM height head backward (:90-93,:211-214)
 // s = sigmoid(fc(mean_HW(x))): dx[n][c][:] = ds[n] s(1-s) w[c] / HW ; dw[c] = sum_n ds s(1-s) mean[n][c] ; db = sum_n ds s(1-s)
 __global__ void __launch_bounds__(256) gap_fc_bwd_dx_kernel(const float* __restrict__ s, const float* __restrict__ ds,
@@ -829,6 +852,12 @@ int hv_masked_center(const float* x, const float* mask, float* out, int w, int c
 }
 int hv_sn_bwd(const float* dweff, const float* weff, const float* u, const float* v, const float* sigma, float* dw, int cout, int kdim, hv_stream_t s) {
   return sn_bwd(dweff, weff, u, v, sigma, dw, cout, kdim, as_stream(s));
+}
+int hv_sn_bwd_multi(const void* d_jobs, int njobs, hv_stream_t s) { return sn_bwd_multi(d_jobs, njobs, as_stream(s)); }
+int hv_sn_prepare_multi(const void* d_jobs, int njobs, int training, hv_stream_t s) {
+  HV_CHECK_ARG(d_jobs && njobs > 0, "sn_prepare_multi: bad argument");
+  static_assert(sizeof(SnJob) == 48, "hv_sn_prepare_multi documents rows of six 64-bit words");
+  return sn_prepare_batched(static_cast<const SnJob*>(d_jobs), njobs, training, as_stream(s));
 }
 int hv_gap_fc_sigmoid_bwd(const float* x, const float* sg, const float* ds, const float* fw, float* dx, int accumulate, float* dfw, float* dfb,
                           int n, int c, int hw, hv_stream_t s) {

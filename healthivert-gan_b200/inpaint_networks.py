@@ -53,6 +53,10 @@ class SNConv2d(nn.Module):
     def effective_weight(self, training):
         """(W_orig / sigma, sigma) on the device; runs one power iteration in place on
         ``weight_u`` / ``weight_v`` first when ``training`` (spectral_norm.py:92-114)."""
+        ready = getattr(self, "_prepared", None)
+        self._prepared = None
+        if ready is not None and training:   # SpectralNormBatch.prepare() ran this layer's power iteration with all the others
+            return ready
         w = self.weight_orig.detach().contiguous()
         w_eff = torch.empty_like(w)
         sigma = torch.empty(1, device=w.device, dtype=torch.float32)
@@ -62,6 +66,78 @@ class SNConv2d(nn.Module):
             torch.autograd.graph.increment_version(self.weight_u)
             torch.autograd.graph.increment_version(self.weight_v)
         return w_eff, sigma
+
+
+class _SpectralNormStep:
+    """Buffers and job tables of ONE training forward (see SpectralNormBatch)."""
+    __slots__ = ("convs", "flat", "w_eff", "dw_eff", "dw", "sigma", "tables", "pending")
+
+    def finish(self):
+        """After the tape's backward: dw_orig of every layer whose weight gradient was written (all of them, normally) in one launch."""
+        from . import train_ops as T
+        L = _lib.lib()
+        n = len(self.convs)
+        if len(self.pending) == n:
+            check(L.hv_sn_bwd_multi(ptr(self.tables[6 * n:]), n, _lib.stream()))
+        else:
+            for i in sorted(self.pending):
+                c = self.convs[i]
+                check(L.hv_sn_bwd(ptr(self.dw_eff[i]), ptr(self.w_eff[i]), ptr(c.weight_u), ptr(c.weight_v), ptr(self.sigma[i:i + 1]),
+                                  ptr(self.dw[i]), c.out_channels, self.w_eff[i][0].numel(), _lib.stream()))
+        for i in sorted(self.pending):
+            T.accumulate_param(self.convs[i].weight_orig, self.dw[i])
+        self.pending = set()
+
+
+class SpectralNormBatch:
+    """Spectral norm of ALL conv blocks of a generator in one launch per direction (training path): the per-layer power iteration and
+    adjoint are single-CTA kernels of ~25 us each, 2 x 47 of them per step (hv_sn_prepare_multi / hv_sn_bwd_multi).  Per forward one
+    flat buffer holds every layer's w_eff, dw_eff (the conv weight gradient is written straight into it) and dw_orig; the device job
+    tables are cached by that buffer's address (the caching allocator hands the same block back once the step has settled, so a
+    steady-state step uploads nothing)."""
+
+    def __init__(self, convs):
+        self.convs = list(convs)
+        self.cache = {}          # flat.data_ptr() -> (rows, device table)
+
+    def prepare(self, tape):
+        L = _lib.lib()
+        convs = self.convs
+        dev = convs[0].weight_orig.device
+        sizes = [c.weight_orig.numel() for c in convs]
+        total, n = sum(sizes), len(convs)
+        st = _SpectralNormStep()
+        st.convs = convs
+        st.flat = flat = torch.empty(3 * total + n, device=dev, dtype=torch.float32)
+        st.sigma = flat[3 * total:]
+        st.w_eff, st.dw_eff, st.dw, st.pending = [], [], [], set()
+        prep, bwd, off = [], [], 0
+        for i, (c, sz) in enumerate(zip(convs, sizes)):
+            shape = c.weight_orig.shape
+            we, de, dw = (flat[k * total + off:k * total + off + sz].view(shape) for k in range(3))
+            st.w_eff.append(we); st.dw_eff.append(de); st.dw.append(dw)
+            dims = c.out_channels | ((sz // c.out_channels) << 32)
+            sg = st.sigma[i:i + 1].data_ptr()
+            u, v = c.weight_u.data_ptr(), c.weight_v.data_ptr()
+            prep.append((c.weight_orig.data_ptr(), u, v, dims, we.data_ptr(), sg))
+            bwd.append((de.data_ptr(), we.data_ptr(), u, v, sg, dw.data_ptr(), dims))
+            off += sz
+        rows = (prep, bwd)
+        hit = self.cache.get(flat.data_ptr())
+        if hit is None or hit[0] != rows or hit[1].device != dev:
+            words = [w for r in prep for w in r] + [w for r in bwd for w in r]
+            if len(self.cache) >= 8:
+                self.cache.clear()
+            hit = (rows, torch.tensor(words, dtype=torch.int64).to(dev))       # blocking upload; a settled step never gets here
+            self.cache[flat.data_ptr()] = hit
+        st.tables = hit[1]
+        check(L.hv_sn_prepare_multi(ptr(st.tables), n, 1, _lib.stream()))
+        for i, c in enumerate(convs):     # the power iteration wrote u / v through raw pointers: bump their version counters
+            torch.autograd.graph.increment_version(c.weight_u)
+            torch.autograd.graph.increment_version(c.weight_v)
+            c._prepared = (st.w_eff[i], st.sigma[i:i + 1])
+            c._sn_slot = (st, i)
+        tape.finalizers.append(st.finish)
 
 
 def conv2d_fused(sources, w_eff, bias, k, stride, pad, dil, act, hin, win, y2_head=False):
@@ -134,17 +210,21 @@ def _conv_run(block, tape, sources, extent, act=None):
     recorded backward = act' -> wgrad/dgrad -> spectral-norm adjoint into ``weight_orig.grad`` / ``bias.grad``."""
     from . import train_ops as T
     c = block.conv
+    slot = getattr(c, "_sn_slot", None) if (getattr(c, "_prepared", None) is not None and block.training) else None
     w_eff, sigma = c.effective_weight(block.training)
 
     def on_grad(dw_eff, db):
-        dw = torch.empty_like(dw_eff)
-        check(_lib.lib().hv_sn_bwd(ptr(dw_eff), ptr(w_eff), ptr(c.weight_u), ptr(c.weight_v), ptr(sigma), ptr(dw),
-                                   c.out_channels, w_eff[0].numel(), _lib.stream()))
-        T.accumulate_param(c.weight_orig, dw)
+        if slot is not None:       # batched adjoint after the tape's backward (SpectralNormBatch.finish); dw_eff is its buffer already
+            slot[0].pending.add(slot[1])
+        else:
+            dw = torch.empty_like(dw_eff)
+            check(_lib.lib().hv_sn_bwd(ptr(dw_eff), ptr(w_eff), ptr(c.weight_u), ptr(c.weight_v), ptr(sigma), ptr(dw),
+                                       c.out_channels, w_eff[0].numel(), _lib.stream()))
+            T.accumulate_param(c.weight_orig, dw)
         T.accumulate_param(c.bias, db)
 
     return T.conv2d(tape, sources, w_eff, c.bias.detach(), c.kernel_size, c.stride, c.padding, c.dilation,
-                    act or block.activation_name, extent, on_grad)
+                    act or block.activation_name, extent, on_grad, dw_buffer=slot[0].dw_eff[slot[1]] if slot is not None else None)
 
 
 def gen_conv(input_dim, output_dim, kernel_size=3, stride=1, padding=0, rate=1, activation="elu"):
@@ -566,6 +646,10 @@ class Generator(nn.Module):
         x = x.to(torch.float32).contiguous()
         mask = mask.to(device=dev, dtype=torch.float32).contiguous()
         CAM = CAM.to(device=dev, dtype=torch.float32).contiguous()
+        if self.training and tape is not None:
+            if getattr(self, "_sn_batch", None) is None:
+                self._sn_batch = SpectralNormBatch(m.conv for m in self.modules() if isinstance(m, Conv2dBlock))
+            self._sn_batch.prepare(tape)
         coarse_seg, x_stage1, pred1_h = _coarse_forward_tape(self.coarse_generator, tape, x, mask, CAM, slice_ratio)
         fine_seg, x_stage2, flow, pred2_h = _fine_forward_tape(self.fine_generator, tape, x, x_stage1, mask, coarse_seg,
                                                               slice_ratio)

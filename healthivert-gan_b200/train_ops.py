@@ -69,6 +69,7 @@ class Tape:
     def __init__(self):
         self.ops = []
         self.keep = []   # tensors that must outlive the enqueued kernels of the forward
+        self.finalizers = []   # run once after the last recorded op's backward (batched per-net work, e.g. the spectral-norm adjoint)
 
     def record(self, fn):
         self.ops.append(fn)
@@ -76,8 +77,11 @@ class Tape:
     def backward(self):
         for fn in reversed(self.ops):
             fn()
+        for fn in self.finalizers:
+            fn()
         self.ops = []
         self.keep = []
+        self.finalizers = []
 
 
 def _desc(sources, cin, cout, k, stride, pad, dil, act, hin, win, n):
@@ -94,11 +98,12 @@ def _desc(sources, cin, cout, k, stride, pad, dil, act, hin, win, n):
     return d, keep
 
 
-def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_weight_grad, param_grads=True):
+def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_weight_grad, param_grads=True, dw_buffer=None):
     """act(conv2d(cat(sources), weight) + bias) with the fused source gather of hv_conv2d_fwd.
 
     sources: [(Var | tensor, hv_src_mode)]; plain tensors are constants.  weight: effective weight TENSOR [cout,cin,k,k];
-    on_weight_grad(dw, db): receives the gradients w.r.t. weight / bias (skipped when param_grads is False)."""
+    on_weight_grad(dw, db): receives the gradients w.r.t. weight / bias (skipped when param_grads is False); dw_buffer: tensor the weight
+    gradient is written to (default: a fresh one)."""
     srcs = [((s.data if isinstance(s, Var) else s), m) for s, m in sources]
     first = srcs[0][0]
     n = first.shape[0]
@@ -132,7 +137,7 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
         dd, keep2 = _desc(srcs, cin, cout, k, stride, pad, dil, "none", hin, win, n)
         tc = BACKWARD_PRECISION == "bf16"
         if param_grads:
-            dw = torch.empty_like(weight)
+            dw = dw_buffer if dw_buffer is not None else torch.empty_like(weight)
             db = torch.empty(cout, device=y.device, dtype=torch.float32) if bias is not None else None
             if tc:
                 ws = _workspace(L.hv_conv2d_wgrad_bf16_workspace_bytes(dd), y.device)

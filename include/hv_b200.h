@@ -242,6 +242,12 @@ int hv_masked_center(const float* x, const float* mask, float* out, int w, int c
  * dw_orig = (dw_eff - <dw_eff, w_eff> u v^T) / sigma                                      */
 int hv_sn_bwd(const float* dw_eff, const float* w_eff, const float* u, const float* v, const float* sigma,
               float* dw_orig, int cout, int kdim, hv_stream_t stream);
+/* Every spectral-norm layer of a net in ONE launch (one CTA per layer; the per-layer calls are latency-bound at ~25 us each).
+ * d_jobs: DEVICE array of njobs rows of 64-bit words.
+ *   hv_sn_prepare_multi rows: {w_orig, u, v, cout | kdim << 32, w_eff, sigma}            (same semantics as hv_sn_prepare)
+ *   hv_sn_bwd_multi rows:     {dw_eff, w_eff, u, v, sigma, dw, cout | kdim << 32}        (same semantics as hv_sn_bwd)      */
+int hv_sn_prepare_multi(const void* d_jobs, int njobs, int training, hv_stream_t stream);
+int hv_sn_bwd_multi(const void* d_jobs, int njobs, hv_stream_t stream);
 /* backward of hv_gap_fc_sigmoid: s = forward output [n], ds = its gradient; dx [n,c,hw]
  * (accumulate != 0 adds), dfc_w [c], dfc_b [1]                                            */
 int hv_gap_fc_sigmoid_bwd(const float* x, const float* s, const float* ds, const float* fc_w, float* dx, int accumulate,
