@@ -66,6 +66,10 @@ SIGNATURES = {
     "hv_ctx_attn_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "hv_ctx_attn_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
                                 c_void_p]),
+    "hv_ctx_attn_fwd_tc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                c_float, c_int, c_int, c_void_p, c_void_p]),
+    "hv_ctx_attn_bwd_tc": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_void_p,
+                                c_void_p]),
     "hv_bn_lrelu_fwd": (c_int, [c_void_p] * 8 + [c_int, c_int, c_int, c_float, c_float, c_float, c_void_p]),
     "hv_bn_lrelu_bwd": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
     "hv_reduce_scalar": (c_int, [c_void_p, c_void_p, c_float, c_int, c_size_t, c_float, c_void_p, c_void_p, c_void_p]),

@@ -1001,7 +1001,8 @@ static int tc_issue_code(const TcConv& c) {
   X(64, HV_ACT_ELU, 5 << 16 | tc_shape_code(1, 3, 3, 2)) \
   X(128, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2)) \
   X(128, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 1, 3, 4)) \
-  X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 2))
+  X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(64, -1, 1 << 16 | tc_shape_code(1, 3, 3, 4))   /* 64 -> 64 3x3 without a compiled-in activation: the data gradient of the trunk layers */
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {

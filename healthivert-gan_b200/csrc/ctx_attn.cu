@@ -9,6 +9,7 @@
 //   A  = softmax_b(scale * U * mm_b) * mm_b ; argmax_b A
 //   y  = fold(R^T A) / 4                                   (tensor contraction 2 + overlap-add)
 // Per-sample intermediates live in a caller-provided workspace.
+#include <cuda_bf16.h>
 #include "hv_common.cuh"
 #include "kernels.h"
 
@@ -93,6 +94,74 @@ int sgemm_batched(const float* A, const float* B, float* C, const float* rowscal
   else sgemm_kernel<false, true><<<grid, 256, 0, st>>>(A, B, C, rowscale, M, N, K, sA, sB, sC, sS);
   HV_LAUNCH_CHECK();
   return HV_OK;
+}
+
+// ------------------------------------------------------------------ the same contractions on the tensor cores
+// Training in the tensor-core mode: every dense contraction of the module (2 forward, 4 backward; 19 - 34 GFLOP each at batch 16) runs
+// on gemm_tc_nt with operands ROUNDED TO BF16 and fp32 accumulation; inputs, outputs and the workspace tensors the backward reads stay
+// fp32.  The operands are cast (and transposed where the contraction index is not the contiguous one) into the stream's scratch.
+int gemm_tc_nt(const __nv_bfloat16* A, const __nv_bfloat16* B, void* C, const float* colscale, int M, int N, int K, int batch,
+               long long strideA, long long strideB, int out_bf16, cudaStream_t st);
+
+// dst bf16 [b][rows][cols] = src fp32 [b][rows][cols] * rowscale[b][row]; one thread = 8 consecutive columns
+__global__ void __launch_bounds__(256) ca_cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, const float* __restrict__ rowscale,
+                                                      int rows, int cols, long long src_stride, long long scale_stride) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = cols >> 3;
+  if (i >= (long long)rows * c8) return;
+  const int b = blockIdx.y, r = (int)(i / c8), c0 = (int)(i - (long long)r * c8) * 8;
+  const float sc = rowscale ? rowscale[(size_t)b * scale_stride + r] : 1.f;
+  const float4* p = reinterpret_cast<const float4*>(src + (size_t)b * src_stride + (size_t)r * cols + c0);
+  const float4 a = __ldg(p), c = __ldg(p + 1);
+  __align__(16) __nv_bfloat16 v[8] = {__float2bfloat16(a.x * sc), __float2bfloat16(a.y * sc), __float2bfloat16(a.z * sc), __float2bfloat16(a.w * sc),
+                                      __float2bfloat16(c.x * sc), __float2bfloat16(c.y * sc), __float2bfloat16(c.z * sc), __float2bfloat16(c.w * sc)};
+  *reinterpret_cast<uint4*>(dst + ((size_t)b * rows + r) * cols + c0) = *reinterpret_cast<const uint4*>(v);
+}
+
+// dst bf16 [b][cols][rows] = transpose of src fp32 [b][rows][cols]; 32 x 32 tiles through shared memory; grid (cols / 32, rows / 32, b)
+__global__ void __launch_bounds__(256) ca_tcast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols, long long src_stride) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + (size_t)b * src_stride;
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) tile[r][tx] = s[(size_t)(r0 + r) * cols + c0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int c = ty; c < 32; c += 8) dst[((size_t)b * cols + c0 + c) * rows + r0 + tx] = __float2bfloat16(tile[tx][c]);
+}
+
+// same contract as sgemm_batched (C[m][n] = rowscale[m] * sum_k A(m,k) B(n,k); a_kmajor: A stored [M][K], else [K][M]; same for B)
+static int tc_contract(const float* A, const float* B, float* C, const float* rowscale, int M, int N, int K, bool a_kmajor, bool b_kmajor,
+                       long long sA, long long sB, long long sC, long long sS, int batch, cudaStream_t st) {
+  HV_CHECK_ARG(M % 128 == 0 && N % 128 == 0 && K % 64 == 0 && sC == (long long)M * N, "ctx_attn (tensor-core mode): contraction %d x %d x %d", M, N, K);
+  const size_t a_bytes = ((size_t)batch * M * K * 2 + 255) & ~(size_t)255, b_bytes = (size_t)batch * N * K * 2;
+  char* scratch = static_cast<char*>(stream_scratch(st, a_bytes + b_bytes));
+  HV_CHECK_ARG(scratch, "ctx_attn (tensor-core mode): no memory for %zu bytes of operand scratch", a_bytes + b_bytes);
+  __nv_bfloat16* Ab = reinterpret_cast<__nv_bfloat16*>(scratch);
+  __nv_bfloat16* Bb = reinterpret_cast<__nv_bfloat16*>(scratch + a_bytes);
+  auto stage = [&](const float* src, __nv_bfloat16* dst, int R, bool kmajor, long long stride, const float* scale) -> int {
+    if (kmajor) {
+      ca_cast_kernel<<<dim3((unsigned)(((long long)R * (K / 8) + 255) / 256), batch), 256, 0, st>>>(src, dst, scale, R, K, stride, sS);
+    } else {
+      HV_CHECK_ARG(!scale, "ctx_attn (tensor-core mode): row scale on a transposed operand");
+      ca_tcast_kernel<<<dim3(R / 32, K / 32, batch), 256, 0, st>>>(src, dst, K, R, stride);   // stored [K][R] -> [R][K]
+    }
+    HV_LAUNCH_CHECK();
+    return HV_OK;
+  };
+  int rc = stage(A, Ab, M, a_kmajor, sA, rowscale);
+  if (rc) return rc;
+  if (B == A && a_kmajor == b_kmajor && !rowscale && M == N) Bb = Ab;
+  else rc = stage(B, Bb, N, b_kmajor, sB, nullptr);
+  if (rc) return rc;
+  return gemm_tc_nt(Ab, Bb, C, nullptr, M, N, K, batch, (long long)M * K, (long long)N * K, 0, st);
+}
+
+static int contract(bool tc, const float* A, const float* B, float* C, const float* rowscale, int M, int N, int K, bool a_kmajor, bool b_kmajor,
+                    long long sA, long long sB, long long sC, long long sS, int batch, cudaStream_t st) {
+  return tc ? tc_contract(A, B, C, rowscale, M, N, K, a_kmajor, b_kmajor, sA, sB, sC, sS, batch, st)
+            : sgemm_batched(A, B, C, rowscale, M, N, K, a_kmajor, b_kmajor, sA, sB, sC, sS, batch, st);
 }
 
 // ------------------------------------------------------------------ patch extraction
@@ -376,7 +445,7 @@ static size_t ca_layout(int n, int c, int h, int w, char* base, CaWorkspace* ws)
 size_t ctx_attn_workspace_bytes(int n, int c, int h, int w) { return ca_layout(n, c, h, w, nullptr, nullptr); }
 
 int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offsets, float* flow, int n, int c,
-                      int h, int w, float scale, int fuse, int per_sample_mask, void* workspace, cudaStream_t st) {
+                      int h, int w, float scale, int fuse, int per_sample_mask, void* workspace, cudaStream_t st, bool tc) {
   HV_CHECK_ARG(f && mask && y && workspace, "ctx_attn_fwd: null argument");
   HV_CHECK_ARG(n > 0 && n <= 65535 && c > 0 && h > 0 && w > 0, "ctx_attn_fwd: bad extent");
   HV_CHECK_ARG(h == w && (h % 2) == 0, "ctx_attn_fwd: square even feature maps only (h=%d w=%d)", h, w);
@@ -388,8 +457,9 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
   HV_LAUNCH_CHECK();
   ca_mask_kernel<<<(n * L + 255) / 256, 256, 0, st>>>(mask, ws.mm, n, side, side, 4 * h, 4 * w, 8, per_sample_mask);
   HV_LAUNCH_CHECK();
-  int rc = sgemm_batched(ws.P, ws.P, ws.S, ws.inv_norm, L, L, c * 9, true, true, (long long)L * c * 9,
-                         (long long)L * c * 9, (long long)L * L, L, n, st);
+  HV_CHECK_ARG(!tc || (c * 9) % 64 == 0, "ctx_attn_fwd (tensor-core mode): needs c * 9 %% 64 == 0");
+  int rc = contract(tc, ws.P, ws.P, ws.S, ws.inv_norm, L, L, c * 9, true, true, (long long)L * c * 9,
+                    (long long)L * c * 9, (long long)L * L, L, n, st);
   if (rc) return rc;
   float* A = ws.S;
   if (fuse) {
@@ -400,8 +470,8 @@ int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offs
   ca_softmax_kernel<<<dim3(L / 32, n), 256, 0, st>>>(A, ws.mm, ws.argmax, L, scale, L);
   HV_LAUNCH_CHECK();
   // cols[ck][f] = sum_b R[b][ck] * A[b][f]
-  rc = sgemm_batched(ws.R, A, ws.cols, nullptr, c * 16, L, L, false, false, (long long)L * c * 16,
-                     (long long)L * L, (long long)L * c * 16, 0, n, st);
+  rc = contract(tc, ws.R, A, ws.cols, nullptr, c * 16, L, L, false, false, (long long)L * c * 16,
+                (long long)L * L, (long long)L * c * 16, 0, n, st);
   if (rc) return rc;
   const size_t per = (size_t)c * h * w;
   ca_fold_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(ws.cols, y, c, h, w);
@@ -568,7 +638,7 @@ static size_t ca_bwd_layout(int n, int c, int h, int w, char* base, CaBwdWorkspa
 size_t ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w) { return ca_bwd_layout(n, c, h, w, nullptr, nullptr); }
 
 int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, float scale, int fuse, void* fwd_workspace,
-                      void* bwd_workspace, cudaStream_t st) {
+                      void* bwd_workspace, cudaStream_t st, bool tc) {
   HV_CHECK_ARG(dy && df && fwd_workspace && bwd_workspace, "ctx_attn_bwd: null argument");
   HV_CHECK_ARG(h == w && (h % 2) == 0, "ctx_attn_bwd: square even feature maps only");
   const int side = h / 2, L = side * side, kp = c * 9, kr = c * 16;
@@ -584,10 +654,10 @@ int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, fl
   ca_unfold_dy_kernel<<<dim3((unsigned)((per_cols + 255) / 256), n), 256, 0, st>>>(dy, dcols, c, h, w);
   HV_LAUNCH_CHECK();
   // dA[b][f] = sum_ck R[b][ck] dcols[ck][f]
-  int rc = sgemm_batched(fw.R, dcols, bw.X1, nullptr, L, L, kr, true, false, (long long)L * kr, (long long)kr * L, (long long)L * L, 0, n, st);
+  int rc = contract(tc, fw.R, dcols, bw.X1, nullptr, L, L, kr, true, false, (long long)L * kr, (long long)kr * L, (long long)L * L, 0, n, st);
   if (rc) return rc;
   // dR[b][ck] = sum_f A[b][f] dcols[ck][f]
-  rc = sgemm_batched(A, dcols, bw.dR, nullptr, L, kr, L, true, true, (long long)L * L, (long long)kr * L, (long long)L * kr, 0, n, st);
+  rc = contract(tc, A, dcols, bw.dR, nullptr, L, kr, L, true, true, (long long)L * L, (long long)kr * L, (long long)L * kr, 0, n, st);
   if (rc) return rc;
   ca_softmax_bwd_kernel<<<dim3(L / 32, n), 256, 0, st>>>(A, bw.X1, fw.mm, L, scale, L);
   HV_LAUNCH_CHECK();
@@ -605,9 +675,9 @@ int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, fl
   ca_pad_rows_kernel<<<(unsigned)((rows * kpad + 255) / 256), 256, 0, st>>>(fw.P, bw.Ppad, kp, kpad, rows);
   HV_LAUNCH_CHECK();
   // C1[b][k] = sum_f dG[b][f] P[f][k];  C2[f][k] = sum_b dG[b][f] P[b][k]
-  rc = sgemm_batched(dS, bw.Ppad, bw.C1, nullptr, L, kpad, L, true, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
+  rc = contract(tc, dS, bw.Ppad, bw.C1, nullptr, L, kpad, L, true, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
   if (rc) return rc;
-  rc = sgemm_batched(dS, bw.Ppad, bw.C2, nullptr, L, kpad, L, false, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
+  rc = contract(tc, dS, bw.Ppad, bw.C2, nullptr, L, kpad, L, false, false, (long long)L * L, (long long)L * kpad, (long long)L * kpad, 0, n, st);
   if (rc) return rc;
   const size_t per = (size_t)c * h * w;
   ca_gather_df_kernel<<<dim3((unsigned)((per + 255) / 256), n), 256, 0, st>>>(bw.dR, bw.C1, bw.C2, fw.P, fw.inv_norm, bw.dinv, df, c, h, w, kpad);

@@ -235,7 +235,7 @@ static void gp_geom(GpGeom& q, const GcGeom& g) {
   const int first = g.pad * q.pitch + q.bl, last = (g.pad + g.hin - 1) * q.pitch + q.bl + g.win;   // real pixels of X: [first, last)
   q.kb0 = first / 64;
   const int kb_total = (last + 63) / 64 - q.kb0;
-  int nkc = (296 + g.n * q.ntg - 1) / (g.n * q.ntg);
+  int nkc = 296 / (g.n * q.ntg);          // <= two full rounds of tiles on 148 SMs
   if (nkc > kb_total / 8) nkc = kb_total / 8;
   if (nkc < 1) nkc = 1;
   q.kblocks = (kb_total + nkc - 1) / nkc;

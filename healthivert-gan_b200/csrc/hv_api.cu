@@ -91,6 +91,17 @@ int hv_ctx_attn_bwd(const float* dy, float* df, int n, int c, int h, int w, floa
   return ctx_attn_bwd_fp32(dy, df, n, c, h, w, softmax_scale, fuse, fwd_workspace, bwd_workspace, as_stream(stream));
 }
 
+int hv_ctx_attn_fwd_tc(const float* f, const float* mask, float* y, int32_t* offsets, float* flow, int n, int c, int h,
+                       int w, float softmax_scale, int fuse, int per_sample_mask, void* workspace, hv_stream_t stream) {
+  return ctx_attn_fwd_fp32(f, mask, y, offsets, flow, n, c, h, w, softmax_scale, fuse, per_sample_mask, workspace,
+                           as_stream(stream), true);
+}
+
+int hv_ctx_attn_bwd_tc(const float* dy, float* df, int n, int c, int h, int w, float softmax_scale, int fuse, void* fwd_workspace,
+                       void* bwd_workspace, hv_stream_t stream) {
+  return ctx_attn_bwd_fp32(dy, df, n, c, h, w, softmax_scale, fuse, fwd_workspace, bwd_workspace, as_stream(stream), true);
+}
+
 int hv_stitch(const float* gen, const float* real, const float* pred_h, const int32_t* x1, const int32_t* x2,
               const int32_t* height, int maxheight, float* out, int32_t* rows_out, int n, int h, int w,
               hv_stream_t stream) {

@@ -41,7 +41,7 @@ int gap_fc_sigmoid(const float* x, const float* fc_w, const float* fc_b, float* 
 size_t ctx_attn_workspace_bytes(int n, int c, int h, int w);
 int ctx_attn_fwd_fp32(const float* f, const float* mask, float* y, int32_t* offsets, float* flow,
                       int n, int c, int h, int w, float scale, int fuse, int per_sample_mask,
-                      void* workspace, cudaStream_t st);
+                      void* workspace, cudaStream_t st, bool tc = false);   // tc: the contractions on tcgen05 (bf16 operands)
 
 // C[m][n] = rowscale[m] * sum_k A(m,k) * B(n,k); batched over blockIdx.z.
 // a_kmajor: A stored [M][K] (lda = K) else [K][M];  b_kmajor: B stored [N][K] else [K][N].
@@ -51,7 +51,7 @@ int sgemm_batched(const float* A, const float* B, float* C, const float* rowscal
 
 size_t ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w);
 int ctx_attn_bwd_fp32(const float* dy, float* df, int n, int c, int h, int w, float scale, int fuse, void* fwd_workspace,
-                      void* bwd_workspace, cudaStream_t st);
+                      void* bwd_workspace, cudaStream_t st, bool tc = false);
 
 int stitch(const float* gen, const float* real, const float* pred_h, const int32_t* x1, const int32_t* x2,
            const int32_t* height, int maxheight, float* out, int32_t* rows_out, int n, int h, int w,

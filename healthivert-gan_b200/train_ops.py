@@ -146,7 +146,29 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
                 check(L.hv_conv2d_wgrad(dd, ptr(dpre), ptr(dw), ptr(db), st))
             on_weight_grad(dw, db)
         need = [isinstance(s, Var) and s.requires_grad for s, _ in sources]
-        if any(need):
+        per_source = (tc and cin > 64 and stride == 1 and k in (3, 5) and pad == (k - 1) // 2 * dil
+                      and all((m in (HV_SRC_DIRECT, HV_SRC_UP2) and t.shape[1] <= 64) or not nd for (_, m), (t, _), nd in zip(sources, srcs, need)))
+        if any(need) and per_source:
+            # more input channels than the conv-form data gradient writes at once (64): one convolution per SOURCE that needs a
+            # gradient, over that source's slice of the filters (conv20: only the 64 upsampled channels of its 65; allconv11: 64 + 64)
+            c0 = 0
+            for (s, m), (t, _), nd in zip(sources, srcs, need):
+                ch = 1 if m == HV_SRC_SCALAR else t.shape[1]
+                if nd:
+                    sub, keep3 = _desc([(t, HV_SRC_DIRECT)], ch, cout, k, stride, pad, dil, "none", hin, win, n)
+                    sub.src[0].ptr = None        # the data gradient does not read the source
+                    wsub = weight[:, c0:c0 + ch].contiguous()
+                    dxs = torch.empty(n, ch, hin, win, device=y.device, dtype=torch.float32)
+                    ws = _workspace(L.hv_conv2d_dgrad_bf16_workspace_bytes(sub), y.device)
+                    check(L.hv_conv2d_dgrad_bf16(sub, ptr(wsub), ptr(dpre), ptr(dxs), ptr(ws), st))
+                    if m == HV_SRC_UP2:
+                        g = torch.empty_like(t)
+                        check(L.hv_upsample2_bwd(ptr(dxs), ptr(g), n, ch, hin // 2, win // 2, ch, 0, st))
+                    else:
+                        g = dxs
+                    accumulate(s, g)
+                c0 += ch
+        elif any(need):
             dx = torch.empty(n, cin, hin, win, device=y.device, dtype=torch.float32)
             if tc:
                 ws = _workspace(L.hv_conv2d_dgrad_bf16_workspace_bytes(dd), y.device)
@@ -239,17 +261,20 @@ def gap_fc_sigmoid(tape, x, fc):
 
 
 def ctx_attention(tape, f, mask, scale, fuse, per_sample_mask, want_flow=True):
-    """ContextualAttention.forward(f, f, mask) with its hand-written adjoint (fp32)."""
+    """ContextualAttention.forward(f, f, mask) with its hand-written adjoint (fp32 tensors; in the tensor-core training mode the six
+    dense contractions run on tcgen05 with bf16-rounded operands: hv_ctx_attn_fwd_tc / hv_ctx_attn_bwd_tc)."""
     n, c, h, w = f.data.shape
     L = _L()
+    tc = BACKWARD_PRECISION == "bf16" and (c * 9) % 64 == 0
+    fwd, bwd_fn = (L.hv_ctx_attn_fwd_tc, L.hv_ctx_attn_bwd_tc) if tc else (L.hv_ctx_attn_fwd, L.hv_ctx_attn_bwd)
     dev = f.data.device
     y = torch.empty_like(f.data)
     offsets = torch.empty(n, 2, h // 2, w // 2, device=dev, dtype=torch.int32)
     flow = torch.empty(n, 3, 4 * h, 4 * w, device=dev, dtype=torch.float32) if want_flow else None
     ws = torch.empty(L.hv_ctx_attn_workspace_bytes(n, c, h, w), device=dev, dtype=torch.uint8)
     mask = mask.contiguous()
-    check(L.hv_ctx_attn_fwd(ptr(f.data), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w, float(scale), int(bool(fuse)),
-                            int(per_sample_mask), ptr(ws), _lib.stream()))
+    check(fwd(ptr(f.data), ptr(mask), ptr(y), ptr(offsets), ptr(flow), n, c, h, w, float(scale), int(bool(fuse)),
+              int(per_sample_mask), ptr(ws), _lib.stream()))
     out = Var(y)
     if tape is not None:
         def bwd():
@@ -257,8 +282,8 @@ def ctx_attention(tape, f, mask, scale, fuse, per_sample_mask, want_flow=True):
                 return
             bws = torch.empty(L.hv_ctx_attn_bwd_workspace_bytes(n, c, h, w), device=dev, dtype=torch.uint8)
             df = torch.empty_like(f.data)
-            check(L.hv_ctx_attn_bwd(ptr(out.grad.contiguous()), ptr(df), n, c, h, w, float(scale), int(bool(fuse)), ptr(ws),
-                                    ptr(bws), _lib.stream()))
+            check(bwd_fn(ptr(out.grad.contiguous()), ptr(df), n, c, h, w, float(scale), int(bool(fuse)), ptr(ws),
+                         ptr(bws), _lib.stream()))
             accumulate(f, df)
 
         tape.record(bwd)

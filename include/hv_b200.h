@@ -257,6 +257,14 @@ int hv_gap_fc_sigmoid_bwd(const float* x, const float* s, const float* ds, const
 size_t hv_ctx_attn_bwd_workspace_bytes(int n, int c, int h, int w);
 int hv_ctx_attn_bwd(const float* dy, float* df, int n, int c, int h, int w, float softmax_scale, int fuse,
                     void* fwd_workspace, void* bwd_workspace, hv_stream_t stream);
+/* hv_ctx_attn_fwd / hv_ctx_attn_bwd with their six dense contractions (2 forward, 4 backward) on tcgen05: the operands are rounded to
+ * bf16 (cast / transposed into internal scratch), accumulation and every tensor of the interface and of the workspaces stay fp32.
+ * Same arguments and workspaces; the tensor-core training mode (opt.precision = 'bf16') calls these.  Needs c * 9 % 64 == 0.          */
+int hv_ctx_attn_fwd_tc(const float* f, const float* mask, float* y, int32_t* offsets, float* flow,
+                       int n, int c, int h, int w, float softmax_scale, int fuse, int per_sample_mask,
+                       void* workspace, hv_stream_t stream);
+int hv_ctx_attn_bwd_tc(const float* dy, float* df, int n, int c, int h, int w, float softmax_scale, int fuse,
+                       void* fwd_workspace, void* bwd_workspace, hv_stream_t stream);
 
 /* ---- A7: BatchNorm2d(train) + LeakyReLU(0.2) of NLayerDiscriminator (models/networks.py:583-597).
  * running_mean / running_var may be NULL; save_mean / save_invstd [c] feed the backward.   */

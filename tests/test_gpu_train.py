@@ -239,6 +239,28 @@ def test_contextual_attention_backward_against_oracle_autograd():
     assert rel(fv.grad, f.grad) <= 2e-3
 
 
+def test_contextual_attention_tensor_core_contractions(bf16_backward):
+    """hv_ctx_attn_fwd_tc / hv_ctx_attn_bwd_tc (the six contractions on tcgen05, operands rounded to bf16) against the oracle's fp32
+    autograd: the attention is a softmax at scale 10 over cosine similarities, so bf16 operand rounding (2^-9) moves single attention
+    weights by a few per cent; output and input gradient stay within 2 % / 8 % relative L2 (observed 0.3 % / 4.9 %)."""
+    g = torch.Generator().manual_seed(6)
+    f = torch.relu(torch.randn(2, 64, 64, 64, generator=g)).requires_grad_()
+    mask = torch.zeros(2, 1, 256, 256)
+    mask[:, :, 100:141] = 1
+    y_ref, _ = gr.contextual_attention(f, mask)
+    dy = torch.randn(y_ref.shape, generator=g)
+    y_ref.backward(dy)
+    tape = T.Tape()
+    fv = T.Var(f.detach().cuda())
+    y, flow, offs = T.ctx_attention(tape, fv, mask.cuda(), 10.0, True, False)
+    y.grad = dy.cuda()
+    tape.backward()
+    torch.cuda.synchronize()
+    print("tensor-core attention: y rel", rel(y.data, y_ref.detach()), "df rel", rel(fv.grad, f.grad))
+    assert 1e-6 < rel(y.data, y_ref.detach()) <= 2e-2          # > 1e-6: it really ran with rounded operands
+    assert rel(fv.grad, f.grad) <= 8e-2
+
+
 def test_losses_and_adam_against_torch():
     g = torch.Generator().manual_seed(9)
     a = torch.randn(2, 1, 64, 64, generator=g, requires_grad=True)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"], help="bf16: tensor-core training mode (D convs + G conv backward)")
     ap.add_argument("--d-precision", default=None, choices=["fp32", "bf16"], help="override for the PatchGAN convolutions alone")
+    ap.add_argument("--device-batch", action="store_true", help="keep the batch on the device (no per-step H2D copy, no host sync): shows whether the host or the device bounds a step")
     ap.add_argument("--g-forward", default=None, choices=["fp32", "bf16"], help="override for the generator's conv forward alone")
     args = ap.parse_args()
     rank, world, local = sharding.world_from_env()
@@ -40,6 +41,8 @@ def main():
     full = synth.synthetic_train_batch(n=args.batch, seed=7)
     idx = list(sharding.shard_contiguous(args.batch, rank, world))
     batch = {k: (v[idx[0]:idx[-1] + 1] if torch.is_tensor(v) else v[idx[0]:idx[-1] + 1]) for k, v in full.items()}
+    if args.device_batch:
+        batch = {k: (v.cuda() if torch.is_tensor(v) and k != "h2" else v) for k, v in batch.items()}
     for _ in range(args.warmup):
         m.set_input(batch)
         m.optimize_parameters()
