@@ -275,7 +275,8 @@ def _train_step_rate(rank, world, local, steps=5, warmup=2, precision="bf16"):
     return {"workload": "pix2pix optimize_parameters, global batch 16 (BASELINE.json configs[3])", "n_gpus": world,
             "samples_per_rank": len(idx), "ms_per_step": ms, "steps_per_s": 1e3 / ms, "samples_per_s": BATCH / ms * 1e3,
             "launches_per_step_rank0": launches,
-            "dtype": ("generator forward fp32 SIMT; generator conv backward and discriminator convs: bf16 operands on tcgen05, fp32 accumulate"
+            "dtype": ("tensor-core mode: generator conv forward / data / weight gradients, PatchGAN convs and the attention contractions with bf16 operands on "
+                      "tcgen05, fp32 accumulate; output heads, losses, BatchNorm, spectral norm and Adam in fp32"
                       if precision == "bf16" else "fp32 SIMT kernels everywhere (parity mode)"),
             "collective": "4 NCCL all-reduces per step on flat gradient buckets (D_1, D_2, D_3, G)" if world > 1 else "none",
             "losses_rank0": losses}
