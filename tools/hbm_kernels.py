@@ -140,5 +140,14 @@ algo["pack_kx_kernel<1, 5>"] = px * (4 + 32)            # the coarse mask plane 
 algo["pack_kx_kernel<1, 3>"] = None
 algo["pack_nbhd4_kernel"] = px * 4 + (px // 4) * 32     # the CAM plane in, its 4x4 neighbourhood per low-res position out
 pipe.close()
+
+# ---- N4 spine straightening: trilinear gather of a float64 256^3 volume on 300 curve planes of 128 x 128 samples (hv_resample_curve)
+from healthivert_gan_b200 import straighten as stn
+vol = torch.rand(256, 256, 256, generator=g, dtype=torch.float64).cuda()
+curve = np.stack([np.linspace(20, 235, 40), 128 + 20 * np.sin(np.linspace(0, 3, 40)), 128 + 10 * np.cos(np.linspace(0, 2, 40))], axis=1)
+inter = stn.Interpolator(curve, step=1, get_local_basis=stn.get_local_basis)
+npts = inter.knots.shape[0]
+timed("resample_curve (trilinear)", lambda: inter.interpolate_along(vol, (128, 128), order=1, return_device=True), reps=5)
+algo["resample_curve_kernel"] = npts * 128 * 128 * (8 * 8 + 8)      # eight float64 corner reads + one float64 write per sample (upper bound: neighbours share corners)
 torch.cuda.synchronize()
 print(json.dumps({"algorithmic_bytes": algo, "warm_us_cuda_events": warm}))
