@@ -304,17 +304,31 @@ __global__ void __launch_bounds__(256) gp_planes_dy_kernel(const float* __restri
   }
 }
 
-// dw[co][ci][t] = sum over the (image, K chunk) blocks of part[(blk * ntg + t / tpm)][(t % tpm) * co8 + co][ci]; ci fastest: coalesced reads
+// dw[co][ci][t] = sum over the (image, K chunk) blocks of part[(blk * ntg + t / tpm)][(t % tpm) * co8 + co][ci].  32 outputs per CTA (ci
+// fastest: coalesced reads), the blocks split over 8 warps and added in a fixed order (a single thread per output walked up to ~300
+// strided partials serially: 29 us per call for a few KB of output).
 __global__ void __launch_bounds__(256) gp_reduce_dw_kernel(const float* __restrict__ part, float* __restrict__ dw, int blocks, int cout, int cin, int kk,
                                                            int tpm, int ntg, int co8, int bn) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= cout * cin * kk) return;
-  const int ci = i % cin, co = (i / cin) % cout, t = i / (cin * cout);
-  const float* src = part + ((size_t)(t / tpm) * 128 + (size_t)(t % tpm) * co8 + co) * bn + ci;
-  const size_t step = (size_t)ntg * 128 * bn;
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const bool live = i < cout * cin * kk;
+  int ci = 0, co = 0, t = 0;
   float s = 0.f;
-  for (int b = 0; b < blocks; ++b) s += src[(size_t)b * step];
-  dw[((size_t)co * cin + ci) * kk + t] = s;
+  if (live) {
+    ci = i % cin; co = (i / cin) % cout; t = i / (cin * cout);
+    const float* src = part + ((size_t)(t / tpm) * 128 + (size_t)(t % tpm) * co8 + co) * bn + ci;
+    const size_t step = (size_t)ntg * 128 * bn;
+    for (int b = slice; b < blocks; b += 8) s += src[(size_t)b * step];
+  }
+  red[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && live) {
+    float r = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += red[k][lane];
+    dw[((size_t)co * cin + ci) * kk + t] = r;
+  }
 }
 
 size_t gconv_wgrad_workspace_bytes(const hv_conv_desc* d) {
@@ -364,7 +378,7 @@ int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* 
     rc = gemm_tc_taps(DY, X, part, g.n, g.cout, g.cin, q.plane, q.tap_off, q.tap_rep, q.nrep, g.kk, q.tpm, q.co8, q.bn, q.nkc, q.kb0, q.kblocks, st);
     if (rc) return rc;
     GP_DBG("gemm_tc_taps");
-    gp_reduce_dw_kernel<<<gc_blocks((long long)g.cout * g.cin * g.kk), 256, 0, st>>>(part, dw, g.n * q.nkc, g.cout, g.cin, g.kk, q.tpm, q.ntg, q.co8, q.bn);
+    gp_reduce_dw_kernel<<<(unsigned)((g.cout * g.cin * g.kk + 31) / 32), 256, 0, st>>>(part, dw, g.n * q.nkc, g.cout, g.cin, g.kk, q.tpm, q.ntg, q.co8, q.bn);
     HV_LAUNCH_CHECK();
     GP_DBG("reduce");
 #undef GP_DBG

@@ -291,6 +291,54 @@ int act_bwd(const float* out, const float* dy, float* dx, int act, size_t count,
   return HV_OK;
 }
 
+// dx = dy * act'(out) AND db[c] = sum over (n, hw) of dx, in ONE pass over the tensors (the bias gradient of a conv block is the channel
+// sum of its pre-activation gradient: computing it separately re-reads dx: ~1 ms per training step over 47 layers).  Same two-pass,
+// deterministic slice scheme as channel_sum.
+__device__ __forceinline__ float act_deriv(float o, int act) {
+  switch (act) {
+    case HV_ACT_ELU: return o > 0.f ? 1.f : o + 1.f;
+    case HV_ACT_RELU: return o > 0.f ? 1.f : 0.f;
+    case HV_ACT_SIGMOID: return o * (1.f - o);
+    case HV_ACT_LRELU02: return o > 0.f ? 1.f : 0.2f;
+    case HV_ACT_CLAMP1: return (o > -1.f && o < 1.f) ? 1.f : 0.f;
+    default: return 1.f;
+  }
+}
+__global__ void __launch_bounds__(256) act_bwd_bias_kernel(const float* __restrict__ out, const float* __restrict__ dy, float* __restrict__ dx,
+                                                           float* __restrict__ partial, int act, int n, int c, int hw) {
+  __shared__ float red[32];
+  const int ch = blockIdx.y, split = blockIdx.x;
+  const long long total = (long long)n * hw, lo = (long long)split * kSumSlice, hi = min(total, lo + kSumSlice);
+  float s = 0.f;
+  long long e = lo + threadIdx.x;
+  long long i = e / hw;
+  int j = (int)(e - i * hw);
+  for (; e < hi; e += blockDim.x) {
+    const size_t at = ((size_t)i * c + ch) * hw + j;
+    const float v = dy[at] * act_deriv(out[at], act);
+    dx[at] = v;
+    s += v;
+    j += blockDim.x;
+    while (j >= hw) { j -= hw; ++i; }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[(size_t)split * c + ch] = s;
+}
+
+int act_bwd_bias(const float* out, const float* dy, float* dx, float* db, int act, int n, int c, int hw, cudaStream_t st) {
+  HV_CHECK_ARG(out && dy && dx && db && n > 0 && c > 0 && c <= 65535 && hw > 0, "act_bwd_bias: bad argument");
+  const long long total = (long long)n * hw;
+  const int splits = (int)((total + kSumSlice - 1) / kSumSlice);
+  float* partial = static_cast<float*>(stream_scratch(st, sizeof(float) * (size_t)splits * c + 256));
+  HV_CHECK_ARG(partial, "act_bwd_bias: scratch allocation failed");
+  partial += 64;
+  act_bwd_bias_kernel<<<dim3(splits, c), 256, 0, st>>>(out, dy, dx, partial, act, n, c, hw);
+  HV_LAUNCH_CHECK();
+  channel_sum_final_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, db, splits, c);
+  HV_LAUNCH_CHECK();
+  return HV_OK;
+}
+
 // adjoint of the nearest x2 upsample: dx[n][c][y][x] = sum of the 2x2 block of dy (dy has channel stride `dy_cstride`
 // planes per image so that a channel range of a concatenated gradient can be read in place)
 __global__ void upsample2_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int c, int h, int w, int dy_channels,
@@ -852,6 +900,9 @@ int hv_masked_center(const float* x, const float* mask, float* out, int w, int c
 }
 int hv_sn_bwd(const float* dweff, const float* weff, const float* u, const float* v, const float* sigma, float* dw, int cout, int kdim, hv_stream_t s) {
   return sn_bwd(dweff, weff, u, v, sigma, dw, cout, kdim, as_stream(s));
+}
+int hv_act_bwd_bias(const float* out, const float* dy, float* dx, float* db, int act, int n, int c, int hw, hv_stream_t s) {
+  return act_bwd_bias(out, dy, dx, db, act, n, c, hw, as_stream(s));
 }
 int hv_sn_bwd_multi(const void* d_jobs, int njobs, hv_stream_t s) { return sn_bwd_multi(d_jobs, njobs, as_stream(s)); }
 int hv_sn_prepare_multi(const void* d_jobs, int njobs, int training, hv_stream_t s) {

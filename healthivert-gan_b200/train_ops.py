@@ -131,17 +131,22 @@ def conv2d(tape, sources, weight, bias, k, stride, pad, dil, act, extent, on_wei
         L = _L()
         st = _lib.stream()
         dpre = out.grad
+        tc = BACKWARD_PRECISION == "bf16"
+        db = torch.empty(cout, device=y.device, dtype=torch.float32) if (bias is not None and param_grads) else None
+        db_done = False
         if act != "none":
             dpre = torch.empty_like(y)
-            check(L.hv_act_bwd(ptr(y), ptr(out.grad), ptr(dpre), HV_ACT[act], y.numel(), st))
+            if db is not None and tc:      # pre-activation gradient and its channel sums (the bias gradient) in one pass
+                check(L.hv_act_bwd_bias(ptr(y), ptr(out.grad), ptr(dpre), ptr(db), HV_ACT[act], n, cout, hout * wout, st))
+                db_done = True
+            else:
+                check(L.hv_act_bwd(ptr(y), ptr(out.grad), ptr(dpre), HV_ACT[act], y.numel(), st))
         dd, keep2 = _desc(srcs, cin, cout, k, stride, pad, dil, "none", hin, win, n)
-        tc = BACKWARD_PRECISION == "bf16"
         if param_grads:
             dw = dw_buffer if dw_buffer is not None else torch.empty_like(weight)
-            db = torch.empty(cout, device=y.device, dtype=torch.float32) if bias is not None else None
             if tc:
                 ws = _workspace(L.hv_conv2d_wgrad_bf16_workspace_bytes(dd), y.device)
-                check(L.hv_conv2d_wgrad_bf16(dd, ptr(dpre), ptr(dw), ptr(db), ptr(ws), st))
+                check(L.hv_conv2d_wgrad_bf16(dd, ptr(dpre), ptr(dw), None if db_done else ptr(db), ptr(ws), st))
             else:
                 check(L.hv_conv2d_wgrad(dd, ptr(dpre), ptr(dw), ptr(db), st))
             on_weight_grad(dw, db)

@@ -222,6 +222,9 @@ int hv_conv2d_wgrad(const hv_conv_desc* d, const float* dy, float* dw, float* db
 /* dx = dy * act'(.) through the activation OUTPUT (nn.ELU / ReLU / Sigmoid / LeakyReLU(0.2) /
  * clamp(-1,1) backward, inpaint_networks.py:460-472,:115,:230)                            */
 int hv_act_bwd(const float* out, const float* dy, float* dx, int act, size_t count, hv_stream_t stream);
+/* hv_act_bwd plus the bias gradient of the conv block in the same pass: dx = dy * act'(out) over [n, c, hw] and
+ * db[c] = sum over (n, hw) of dx (deterministic two-pass slice sums).                                           */
+int hv_act_bwd_bias(const float* out, const float* dy, float* dx, float* db, int act, int n, int c, int hw, hv_stream_t stream);
 /* adjoint of F.interpolate(scale_factor=2, mode='nearest') (:97,:105,:219,:222): channels
  * [dy_ch0, dy_ch0+c) of dy [n,dy_channels,2h,2w] -> dx [n,c,h,w]                          */
 int hv_upsample2_bwd(const float* dy, float* dx, int n, int c, int h, int w, int dy_channels,
