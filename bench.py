@@ -212,22 +212,33 @@ def _torch_gpu_train_baseline(dev, steps=3):
         m.setup(opt)
     m.netG.load_state_dict(synth.synthetic_generator_state_dict())
     batch = synth.synthetic_train_batch(n=BATCH, seed=7)
-    torch.backends.cudnn.allow_tf32 = False
-    for _ in range(2):
-        m.set_input(batch)
-        m.optimize_parameters()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        m.set_input(batch)
-        m.optimize_parameters()
-    e1.record()
-    torch.cuda.synchronize()
+    out = {}
+    for name, tf32 in (("fp32", False), ("tf32_cudnn_benchmark", True)):
+        torch.backends.cudnn.allow_tf32 = tf32
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.benchmark = tf32       # the reference sets cudnn.benchmark = True (models/base_model.py:37-38)
+        for _ in range(3 if tf32 else 2):
+            m.set_input(batch)
+            m.optimize_parameters()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            m.set_input(batch)
+            m.optimize_parameters()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out[name] = {"ms_per_step": ms, "samples_per_s": BATCH / ms * 1e3}
     torch.backends.cudnn.allow_tf32 = True
-    ms = e0.elapsed_time(e1) / steps
-    return {"ms_per_step": ms, "samples_per_s": BATCH / ms * 1e3, "kind": "reference",
-            "what": f"unmodified reference Pix2PixModel.optimize_parameters on cuda, batch {BATCH}, fp32 (TF32 off), eager PyTorch"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = False
+    out["ms_per_step"] = out["fp32"]["ms_per_step"]
+    out["samples_per_s"] = out["fp32"]["samples_per_s"]
+    out["kind"] = "reference"
+    out["what"] = (f"unmodified reference Pix2PixModel.optimize_parameters on cuda, batch {BATCH}, eager PyTorch: fp32 (TF32 off; the top-level keys) and "
+                   "TF32 + cudnn.benchmark")
+    return out
 
 
 def _train_step_rate(rank, world, local, steps=5, warmup=2, precision="bf16"):
