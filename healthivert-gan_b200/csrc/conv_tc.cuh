@@ -41,7 +41,10 @@ struct TcBuf {
   }
   __host__ __device__ int sub_h() const { return s2d ? h / 2 : h; }
   __host__ __device__ int sub_w() const { return s2d ? w / 2 : w / xp; }
-  __host__ __device__ int pitch() const { return sub_w() + 2 * border; }
+  // ONE zero gap of `border` columns between consecutive rows: it is the right border of row y and the left border of row y + 1 (a tap is
+  // a shift of the flattened position, so x + dx >= w lands in the next row's gap).  The tiles of a layer cover rows x pitch positions:
+  // w + border instead of w + 2 border is 17 % fewer tiles at dilation 16, 1.5 % at dilation 1 (64 x 64 maps).
+  __host__ __device__ int pitch() const { return sub_w() + border; }
   __host__ __device__ int rows() const { return sub_h() + 2 * border; }
   __host__ __device__ int sub_plane() const { return (pitch() * rows() + 7) & ~7; }
   __host__ __device__ int plane() const { return s2d ? 4 * sub_plane() : xp * sub_plane(); }
