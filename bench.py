@@ -325,8 +325,9 @@ def _volume_rate(g, rank, world, n_volumes, depth, batch=64):
     for v in mine:
         label, ct, cam = vols[v]
         t0 = time.perf_counter()
-        _, lab_s = vs.synthesize(ct, label, cam, 20, axis=2)
-        lab_c = vs.synthesize(ct, label, cam, 20, axis=1)[1] if coronal else lab_s
+        lab_dev = torch.as_tensor(label).cuda() if coronal else label      # two orientations: the label volume crosses PCIe once
+        _, lab_s = vs.synthesize(ct, lab_dev, cam, 20, axis=2)
+        lab_c = vs.synthesize(ct, lab_dev, cam, 20, axis=1)[1] if coronal else lab_s
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         slices += int(lab_s.any(axis=(0, 1)).sum()) + (int(lab_c.any(axis=(0, 2)).sum()) if coronal else 0)

@@ -31,12 +31,21 @@ class VolumeSynthesizer:
 
     # ---------------------------------------------------------------------------------------- helpers
     def _to_u8_slices(self, vol, axis, scale):
-        v = torch.as_tensor(np.ascontiguousarray(vol, dtype=np.float64)).to(self.dev)
+        """[d0, d1, d2] float64 volume (numpy, or a torch tensor already on the device) -> uint8 slices [S, d0, ncol] along ``axis``."""
+        if isinstance(vol, torch.Tensor):
+            v = vol.to(self.dev, dtype=torch.float64).contiguous()
+        else:
+            v = torch.as_tensor(np.ascontiguousarray(vol, dtype=np.float64)).to(self.dev)
         d0, d1, d2 = v.shape
         s, ncol = (d2, d1) if axis == 2 else (d1, d2)
         out = torch.empty(s, d0, ncol, device=self.dev, dtype=torch.uint8)
         check(_lib.lib().hv_vol_to_u8(ptr(v), ptr(out), d0, d1, d2, axis, float(scale), _lib.stream()))
         return out
+
+    @staticmethod
+    def _window(vol, axis, a, b):
+        """The slices a .. b (inclusive) of a volume along ``axis`` (2: vol[:, :, z], 1: vol[:, z, :])."""
+        return vol[:, :, a:b + 1] if axis == 2 else vol[:, a:b + 1, :]
 
     def _stage(self, slices, vert_id, label_in, label_next, ct_u8, cam_u8, ratios, ct_out, label_out):
         """One run_model() per entry of ``slices`` (all with the same vertebra id), batched."""
@@ -74,45 +83,70 @@ class VolumeSynthesizer:
         prev_flags = (self.g.per_sample_mask, self.g.return_flow)
         self.g.per_sample_mask, self.g.return_flow = True, False     # the reference driver is batch-1: every slice has its own mask
         try:
-            ct_u8 = self._to_u8_slices(ct_vol, axis, 1.0)
-            lab_a = self._to_u8_slices(label_vol, axis, 1.0)
-            cam_u8 = self._to_u8_slices(cam_vol, axis, cam_scale)
-            S, h, w = lab_a.shape
+            # the label volume is scanned whole (which slices hold the vertebra and its neighbours, eval:186-197, :204, :213) ...
+            lab_all = self._to_u8_slices(label_vol, axis, 1.0)
+            S, h, w = lab_all.shape
             counts = torch.empty(S, 3, device=self.dev, dtype=torch.int32)
-            check(_lib.lib().hv_slice_id_counts(ptr(lab_a), S, h * w, vert_id - 1, vert_id, vert_id + 1, ptr(counts), _lib.stream()))
+            check(_lib.lib().hv_slice_id_counts(ptr(lab_all), S, h * w, vert_id - 1, vert_id, vert_id + 1, ptr(counts), _lib.stream()))
             cnt = counts.cpu().numpy()
-            ct_out = torch.zeros(S, h, w, device=self.dev, dtype=torch.float32)
-            label_out = torch.zeros(S, h, w, device=self.dev, dtype=torch.float32)
             present = np.nonzero(cnt[:, 1] > 0)[0]
-            if present.size:
-                z0, z1 = int(present.min()), int(present.max())                      # eval:186-197
-                range_length = z1 - z0 + 1
-                new_len = int(range_length * 4 / 5)
-                new_z0 = z0 + (range_length - new_len) // 2
-                new_z1 = new_z0 + new_len - 1
-                center = (new_z0 + new_z1) // 2
-                zs = list(range(new_z0, new_z1 + 1))
-                ratios = {z: abs(z - center) / range_length * 2 for z in zs}         # eval:202-203
-                upper = [z for z in zs if vert_id > 8 and cnt[z, 0] > 200]           # eval:204
-                lower = [z for z in zs if vert_id < 24 and cnt[z, 2] > 200]          # eval:213
+            full_shape = tuple(label_vol.shape)
+            if not present.size:
+                if return_device:
+                    z = torch.zeros(full_shape, device=self.dev, dtype=torch.float32)
+                    return z, z.clone()
+                return np.zeros(full_shape, np.float32), np.zeros(full_shape, np.float32)
+            z0, z1 = int(present.min()), int(present.max())                          # eval:186-197
+            range_length = z1 - z0 + 1
+            new_len = int(range_length * 4 / 5)
+            new_z0 = z0 + (range_length - new_len) // 2
+            new_z1 = new_z0 + new_len - 1
+            center = (new_z0 + new_z1) // 2
+            zs = list(range(new_z0, new_z1 + 1))
+            ratios = {z - new_z0: abs(z - center) / range_length * 2 for z in zs}    # eval:202-203 (keys: index inside the window)
+            upper = [z - new_z0 for z in zs if vert_id > 8 and cnt[z, 0] > 200]      # eval:204
+            lower = [z - new_z0 for z in zs if vert_id < 24 and cnt[z, 2] > 200]     # eval:213
+            nwin = len(zs)
+            # ... but only the window's slices are ever read or written by the three stages (every run_model call works on ONE slice):
+            # CT and Grad-CAM are uploaded for the window alone (a 256^3 float64 volume is 134 MB of PCIe traffic, the window ~ 15 %
+            # of it), and only the window comes back
+            if nwin > 0:
+                ct_u8 = self._to_u8_slices(self._window(ct_vol, axis, new_z0, new_z1), axis, 1.0)
+                cam_u8 = self._to_u8_slices(self._window(cam_vol, axis, new_z0, new_z1), axis, cam_scale)
+                lab_a = lab_all[new_z0:new_z1 + 1].contiguous()
+            ct_out = torch.zeros(nwin, h, w, device=self.dev, dtype=torch.float32)
+            label_out = torch.zeros(nwin, h, w, device=self.dev, dtype=torch.float32)
+            if nwin > 0:
                 lab_b = lab_a.clone()
                 cur, nxt = lab_a, lab_b
-                for stage_slices, vid, final in ((upper, vert_id - 1, False), (lower, vert_id + 1, False), (zs, vert_id, True)):
+                for stage_slices, vid, final in ((upper, vert_id - 1, False), (lower, vert_id + 1, False), (list(range(nwin)), vert_id, True)):
                     if not stage_slices:
                         continue
                     nxt.copy_(cur)                                                   # slices outside the stage pass through
                     self._stage(stage_slices, vid, cur, nxt, ct_u8, cam_u8, ratios, ct_out if final else None,
                                 label_out if final else None)
                     cur, nxt = nxt, cur
-            # back to the volume's own axis order
-            if axis == 2:
-                ct_f, lab_f = ct_out.permute(1, 2, 0), label_out.permute(1, 2, 0)
-            else:
-                ct_f, lab_f = ct_out.permute(1, 0, 2), label_out.permute(1, 0, 2)
-            ct_f, lab_f = ct_f.contiguous(), lab_f.contiguous()
+            # back to the volume's own axis order, zeros outside the window (the reference's np.zeros_like outputs)
+            perm = (1, 2, 0) if axis == 2 else (1, 0, 2)
             if return_device:
-                return ct_f, lab_f
-            return ct_f.cpu().numpy(), lab_f.cpu().numpy()
+                outs = []
+                for win in (ct_out, label_out):
+                    full = torch.zeros(full_shape, device=self.dev, dtype=torch.float32)
+                    self._window(full, axis, new_z0, new_z1).copy_(win.permute(*perm))
+                    outs.append(full)
+                return outs[0], outs[1]
+            outs = []
+            for win in (ct_out, label_out):
+                host = torch.empty(win.shape, dtype=torch.float32, pin_memory=True)    # pinned: D2H at the PCIe rate
+                host.copy_(win, non_blocking=True)
+                outs.append(host)
+            torch.cuda.current_stream(self.dev).synchronize()
+            res = []
+            for host in outs:
+                full = np.zeros(full_shape, np.float32)
+                self._window(full, axis, new_z0, new_z1)[...] = host.numpy().transpose(*perm)
+                res.append(full)
+            return res[0], res[1]
         finally:
             self.g.per_sample_mask, self.g.return_flow = prev_flags
 

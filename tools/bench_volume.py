@@ -64,8 +64,9 @@ def main():
     for v in mine:
         label, ct, cam = vols[v]
         t0 = time.perf_counter()
-        ct_s, lab_s = vs.synthesize(ct, label, cam, 20, axis=2)
-        lab_c = vs.synthesize(ct, label, cam, 20, axis=1)[1] if coronal_synth else lab_s
+        lab_dev = torch.as_tensor(label).cuda() if coronal_synth else label   # two orientations: the label volume crosses PCIe once
+        ct_s, lab_s = vs.synthesize(ct, lab_dev, cam, 20, axis=2)
+        lab_c = vs.synthesize(ct, lab_dev, cam, 20, axis=1)[1] if coronal_synth else lab_s
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         slices += int(lab_s.any(axis=(0, 1)).sum()) + (int(lab_c.any(axis=(0, 2)).sum()) if coronal_synth else 0)
