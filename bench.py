@@ -304,7 +304,7 @@ def _volume_rate(g, rank, world, n_volumes, depth, batch=64):
     from oracle import synth
 
     def feats(label, fake, axis):
-        lab, fk = (label == 20).astype(np.float64), (fake == 20).astype(np.float64)
+        lab, fk = (label == 20), (fake == 20)      # calculate_heights only asks `!= 0`: no float64 copies of the volumes
         loc = np.where(lab)[axis]
         return mask_ops.calculate_rhlv(fk, lab, int(np.mean(loc)), int((loc.max() - loc.min()) // 5), None, 0.7, axis=axis)
 
