@@ -552,33 +552,52 @@ __global__ void __launch_bounds__(512) bn_stats_kernel(const float* __restrict__
   const float cnt = (float)n * hw;
   const bool vec = bn_vec_ok(x, hw);
   float s = 0.f;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && !vec; ++i) {
     const float* p = x + ((size_t)i * c + ch) * hw;
-    if (vec) {
-      const float4* p4 = reinterpret_cast<const float4*>(p);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int j = threadIdx.x; j < hw / 4; j += blockDim.x) { const float4 v = __ldg(p4 + j); a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w; }
-      s += (a0 + a1) + (a2 + a3);
-    } else {
-      for (int j = threadIdx.x; j < hw; j += blockDim.x) s += p[j];
+    for (int j = threadIdx.x; j < hw; j += blockDim.x) s += p[j];
+  }
+  if (vec) {
+    // one CTA per channel: four independent 16-byte loads in flight per thread (a single load per iteration left the CTA latency-bound:
+    // 25 us for a 33 MB tensor)
+    const int hw4 = hw >> 2, total4 = n * hw4;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e0 = threadIdx.x; e0 < total4; e0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * blockDim.x;
+        const int i = e / hw4, j = e - i * hw4;
+        v[u] = e < total4 ? __ldg(reinterpret_cast<const float4*>(x + ((size_t)i * c + ch) * hw) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] += (v[u].x + v[u].y) + (v[u].z + v[u].w);
     }
+    s = (a[0] + a[1]) + (a[2] + a[3]);
   }
   const float mean = block_sum(s, red) / cnt;
   float q = 0.f;
-  for (int i = 0; i < n; ++i) {
+  for (int i = 0; i < n && !vec; ++i) {
     const float* p = x + ((size_t)i * c + ch) * hw;
-    if (vec) {
-      const float4* p4 = reinterpret_cast<const float4*>(p);
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-      for (int j = threadIdx.x; j < hw / 4; j += blockDim.x) {
-        const float4 v = __ldg(p4 + j);
-        const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-        a0 = fmaf(d0, d0, a0); a1 = fmaf(d1, d1, a1); a2 = fmaf(d2, d2, a2); a3 = fmaf(d3, d3, a3);
+    for (int j = threadIdx.x; j < hw; j += blockDim.x) { const float d = p[j] - mean; q = fmaf(d, d, q); }
+  }
+  if (vec) {
+    const int hw4 = hw >> 2, total4 = n * hw4;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int e0 = threadIdx.x; e0 < total4; e0 += 4 * blockDim.x) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = e0 + u * blockDim.x;
+        const int i = e / hw4, j = e - i * hw4;
+        v[u] = e < total4 ? __ldg(reinterpret_cast<const float4*>(x + ((size_t)i * c + ch) * hw) + j) : make_float4(mean, mean, mean, mean);
       }
-      q += (a0 + a1) + (a2 + a3);
-    } else {
-      for (int j = threadIdx.x; j < hw; j += blockDim.x) { const float d = p[j] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float d0 = v[u].x - mean, d1 = v[u].y - mean, d2 = v[u].z - mean, d3 = v[u].w - mean;
+        a[u] += fmaf(d0, d0, d1 * d1) + fmaf(d2, d2, d3 * d3);
+      }
     }
+    q = (a[0] + a[1]) + (a[2] + a[3]);
   }
   const float var = block_sum(q, red) / cnt;
   if (threadIdx.x == 0) {
