@@ -1187,8 +1187,8 @@ int tc_pack_nbhd4(const float* src, const TcBuf& dst, cudaStream_t st) {
   return HV_OK;
 }
 
-__global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst, int sub) {
-  const int n = blockIdx.z, c = blockIdx.y, h = src.h / sub, w = src.w / sub;
+__global__ void unpack_nchw_kernel(TcBuf src, int ch0, int channels, float* __restrict__ dst, int sub, int c_begin) {
+  const int n = blockIdx.z, c = c_begin + blockIdx.y, h = src.h / sub, w = src.w / sub;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= h * w) return;
   const int y = i / w, x = i - y * w, ch = ch0 + c;
@@ -1211,14 +1211,17 @@ __global__ void __launch_bounds__(256) unpack_nchw_chunks_kernel(TcBuf src, int 
 
 int tc_unpack_nchw(const TcBuf& src, int ch0, int channels, float* dst, cudaStream_t st, int sub) {
   HV_CHECK_ARG(src.ptr && dst && ch0 + channels <= src.chunks * 8 && (sub == 1 || sub == 2), "tc_unpack_nchw: bad argument");
-  if ((ch0 & 7) == 0 && (channels & 7) == 0) {
-    unpack_nchw_chunks_kernel<<<dim3((src.h / sub * (src.w / sub) + 255) / 256, channels / 8, src.n), 256, 0, st>>>(src, ch0 >> 3, channels, dst, sub);
+  const unsigned px_blocks = (unsigned)((src.h / sub * (src.w / sub) + 255) / 256);
+  int done = 0;
+  if ((ch0 & 7) == 0 && channels >= 8) {       // whole chunks with 16-byte loads, the remainder channel by channel
+    unpack_nchw_chunks_kernel<<<dim3(px_blocks, channels / 8, src.n), 256, 0, st>>>(src, ch0 >> 3, channels, dst, sub);
     HV_LAUNCH_CHECK();
-    return HV_OK;
+    done = channels & ~7;
   }
-  dim3 grid((src.h / sub * (src.w / sub) + 255) / 256, channels, src.n);
-  unpack_nchw_kernel<<<grid, 256, 0, st>>>(src, ch0, channels, dst, sub);
-  HV_LAUNCH_CHECK();
+  if (done < channels) {
+    unpack_nchw_kernel<<<dim3(px_blocks, channels - done, src.n), 256, 0, st>>>(src, ch0, channels, dst, sub, done);
+    HV_LAUNCH_CHECK();
+  }
   return HV_OK;
 }
 

@@ -30,12 +30,33 @@ class VolumeSynthesizer:
             raise _lib.HvError("VolumeSynthesizer needs the generator on a CUDA device (no CPU fallback)")
 
     # ---------------------------------------------------------------------------------------- helpers
+    def _staging(self, numel):
+        """A pinned float64 staging block of >= numel elements that no copy in flight still reads: three grow-only blocks are rotated
+        (CT, label, Grad-CAM of one call), each guarded by the event recorded after its last host-to-device copy."""
+        if not hasattr(self, "_staged"):
+            self._staged = []
+        if len(self._staged) >= 3:
+            buf, ev = self._staged.pop(0)
+            ev.synchronize()
+        else:
+            buf, ev = None, torch.cuda.Event()
+        if buf is None or buf.numel() < numel:
+            buf = torch.empty(int(numel), dtype=torch.float64, pin_memory=True)
+        self._staged.append((buf, ev))
+        return buf[:numel]
+
     def _to_u8_slices(self, vol, axis, scale):
         """[d0, d1, d2] float64 volume (numpy, or a torch tensor already on the device) -> uint8 slices [S, d0, ncol] along ``axis``."""
         if isinstance(vol, torch.Tensor):
             v = vol.to(self.dev, dtype=torch.float64).contiguous()
         else:
-            v = torch.as_tensor(np.ascontiguousarray(vol, dtype=np.float64)).to(self.dev)
+            # gather (the window is a strided view) and dtype conversion go straight into a pinned staging tensor: one host pass, then an
+            # asynchronous copy at the PCIe rate (torch's pinned-memory allocator keeps the block until the copy has completed)
+            vol = np.asarray(vol)
+            host = self._staging(vol.size).view(vol.shape)
+            np.copyto(host.numpy(), vol, casting="unsafe")
+            v = host.to(self.dev, non_blocking=True)
+            self._staged[-1][1].record(torch.cuda.current_stream(self.dev))
         d0, d1, d2 = v.shape
         s, ncol = (d2, d1) if axis == 2 else (d1, d2)
         out = torch.empty(s, d0, ncol, device=self.dev, dtype=torch.uint8)
@@ -136,15 +157,20 @@ class VolumeSynthesizer:
                     outs.append(full)
                 return outs[0], outs[1]
             outs = []
-            for win in (ct_out, label_out):
-                host = torch.empty(win.shape, dtype=torch.float32, pin_memory=True)    # pinned: D2H at the PCIe rate
+            if not hasattr(self, "_out_staged"):
+                self._out_staged = [None, None]
+            for k, win in enumerate((ct_out, label_out)):
+                win = win.permute(*perm).contiguous()                                  # the volume's axis order, on the device
+                if self._out_staged[k] is None or self._out_staged[k].numel() < win.numel():   # grow-only pinned blocks: D2H at the PCIe rate
+                    self._out_staged[k] = torch.empty(win.numel(), dtype=torch.float32, pin_memory=True)
+                host = self._out_staged[k][:win.numel()].view(win.shape)
                 host.copy_(win, non_blocking=True)
                 outs.append(host)
             torch.cuda.current_stream(self.dev).synchronize()
             res = []
             for host in outs:
                 full = np.zeros(full_shape, np.float32)
-                self._window(full, axis, new_z0, new_z1)[...] = host.numpy().transpose(*perm)
+                self._window(full, axis, new_z0, new_z1)[...] = host.numpy()           # row-wise copies, no host-side transpose
                 res.append(full)
             return res[0], res[1]
         finally:

@@ -36,13 +36,14 @@ def timed(name, fn):
 
 vs._to_u8_slices = timed("to_u8_slices (H2D float64 + convert)", vs._to_u8_slices)
 vs._stage = timed("stages (prepare + forward + stitch + finish)", vs._stage)
-for axis in (2, 1):
+axes = (2, 1) if depth == 256 else (2,)
+for axis in axes:
     vs.synthesize(ct, label, cam, 20, axis=axis)
 for rep in range(2):
     acc.clear()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for axis in ((2, 1) if depth == 256 else (2,)):
+    for axis in axes:
         vs.synthesize(ct, label, cam, 20, axis=axis)
     torch.cuda.synchronize()
     total = time.perf_counter() - t0
