@@ -1002,7 +1002,20 @@ static int tc_issue_code(const TcConv& c) {
   X(128, HV_ACT_ELU, 5 << 16 | tc_shape_code(4, 0, 0, 2)) \
   X(128, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 1, 3, 4)) \
   X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
-  X(64, -1, 1 << 16 | tc_shape_code(1, 3, 3, 4))   /* 64 -> 64 3x3 without a compiled-in activation: the data gradient of the trunk layers */
+  X(64, -1, 1 << 16 | tc_shape_code(1, 3, 3, 4))   /* 64 -> 64 3x3 without a compiled-in activation: the data gradient of the trunk layers */ \
+  /* the stand-alone op inside the training step (forward of the thin layers, data gradients: HV_TC_DUMP=1 python tools/bench_train.py): \
+     the generic instance costs 2 - 4x a specialised one */ \
+  X(16, -1, 1 << 16 | tc_shape_code(1, 3, 3, 1)) \
+  X(16, -1, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(16, -1, 1 << 16 | tc_shape_code(1, 5, 5, 1)) \
+  X(32, -1, 1 << 16 | tc_shape_code(1, 3, 3, 1)) \
+  X(32, -1, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(32, -1, 1 << 16 | tc_shape_code(1, 3, 3, 4)) \
+  X(64, -1, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(16, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 5, 5, 1)) \
+  X(16, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 1)) \
+  X(16, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 2)) \
+  X(32, HV_ACT_ELU, 1 << 16 | tc_shape_code(1, 3, 3, 1))
 
 template <int N_PAD>
 static int tc_launch_n(const TcConv& c, cudaStream_t st) {
