@@ -640,7 +640,9 @@ def test_data_parallel_step_two_ranks_nccl(tmp_path):
     rep0, grads = data_parallel_truth(world=2, per_rank=2)
     for tag in ("G", "D_1", "D_3"):
         for a, b in zip(got[f"grad_{tag}"], grads[tag]):
-            assert rel(a, b) <= 1e-5, tag        # NCCL sums in a different order than torch.stack(...).sum(0): fp32 rounding only
+            # fp32 rounding only: NCCL sums in a different order than torch.stack(...).sum(0), and the fp32 weight-gradient kernel combines
+            # its split-K partial sums with atomicAdd (run-to-run order): observed 2e-6 .. 2e-5 on single tensors over repeated runs
+            assert rel(a, b) <= 5e-5, tag
     for name, net in (("G", rep0.netG), ("D_1", rep0.netD_1)):
         for k, v in net.state_dict().items():
             if v.dtype.is_floating_point:
