@@ -192,6 +192,90 @@ __global__ void __launch_bounds__(256) gc_flip_w_kernel(const float* __restrict_
   wf[((size_t)ci * cout + co) * kk + (kk - 1 - t)] = w[i];
 }
 
+// ---- single-filter layers over many input channels (the PatchGAN logit conv 512 -> 1, networks.py:598): their gradients are reductions,
+// not GEMMs - through the GEMM path the data gradient alone builds an [8192 rows x 1024 pixels] operand per image for 0.2 GFLOP of work.
+// dx[n][ci][y][x] = sum over the taps whose output pixel exists of w[ci][ky][kx] * dy[n][oy][ox]; one thread = one input element
+__global__ void __launch_bounds__(256) sf_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, float* __restrict__ dx, GcGeom g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)g.n * g.cin * g.hin * g.win) return;
+  const int x = (int)(i % g.win), y = (int)((i / g.win) % g.hin);
+  const long long bc = i / ((long long)g.win * g.hin);
+  const int ci = (int)(bc % g.cin), b = (int)(bc / g.cin);
+  const float* wp = w + (size_t)ci * g.kk;
+  const float* dyp = dy + (size_t)b * g.P;
+  float acc = 0.f;
+  for (int ky = 0; ky < g.k; ++ky) {
+    const int ty = y + g.pad - ky * g.dil;
+    if (ty < 0 || (g.stride == 2 && (ty & 1))) continue;
+    const int oy = g.stride == 2 ? ty >> 1 : ty;
+    if (oy >= g.hout) continue;
+    for (int kx = 0; kx < g.k; ++kx) {
+      const int tx = x + g.pad - kx * g.dil;
+      if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
+      const int ox = g.stride == 2 ? tx >> 1 : tx;
+      if (ox < g.wout) acc = fmaf(__ldg(wp + ky * g.k + kx), __ldg(dyp + (size_t)oy * g.wout + ox), acc);
+    }
+  }
+  dx[i] = acc;
+}
+
+// part[split][ci][tap] = sum over the split's share of the (image, output pixel) pairs of dy * x(tap); grid (splits, cin); the taps of a
+// thread live in registers (k <= 5), block sums through shared memory; a second kernel adds the splits in a fixed order
+__global__ void __launch_bounds__(256) sf_wgrad_kernel(const float* __restrict__ dy, float* __restrict__ part, GcGeom g, int splits) {
+  __shared__ float red[8][25];
+  const int ci = blockIdx.y, split = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = (long long)g.n * g.P, per = (total + splits - 1) / splits;
+  const long long lo = (long long)split * per, hi = min(total, lo + per);
+  float acc[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) acc[t] = 0.f;
+  for (long long e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    const int b = (int)(e / g.P), p = (int)(e - (long long)b * g.P);
+    const int oy = p / g.wout, ox = p - oy * g.wout;
+    const float gval = __ldg(dy + e);
+    const GcSrc src = gc_resolve(g, b, ci);
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      if (ky >= g.k) break;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        if (kx >= g.k) break;
+        acc[ky * 5 + kx] = fmaf(gval, gc_fetch(g, src, oy * g.stride + ky * g.dil - g.pad, ox * g.stride + kx * g.dil - g.pad), acc[ky * 5 + kx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 25; ++t) {
+    float v = acc[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < g.kk) {
+    const int ky = threadIdx.x / g.k, kx = threadIdx.x - ky * g.k;
+    float v = 0.f;
+#pragma unroll
+    for (int wq = 0; wq < 8; ++wq) v += red[wq][ky * 5 + kx];
+    part[((size_t)split * g.cin + ci) * g.kk + threadIdx.x] = v;
+  }
+}
+__global__ void __launch_bounds__(256) sf_wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += part[(size_t)s * count + i];
+  dw[i] = v;
+}
+
+static bool sf_eligible(const hv_conv_desc* d) { return d->cout == 1 && d->cin >= 64 && d->k <= 5; }
+static int sf_splits(const GcGeom& g) {
+  int s = (592 + g.cin - 1) / g.cin;
+  const long long total = (long long)g.n * g.P;
+  if (s > total / 1024) s = (int)(total / 1024);
+  return s < 1 ? 1 : s;
+}
+
 static inline unsigned gc_blocks(long long n) { return (unsigned)((n + 255) / 256); }
 static inline size_t gc_al(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -334,6 +418,7 @@ __global__ void __launch_bounds__(256) gp_reduce_dw_kernel(const float* __restri
 size_t gconv_wgrad_workspace_bytes(const hv_conv_desc* d) {
   GcGeom g;
   if (gc_geom(g, d)) return 0;
+  if (sf_eligible(d)) return gc_al((size_t)sf_splits(g) * g.cin * g.kk * 4);
   if (gp_eligible(d)) {
     GpGeom q;
     gp_geom(q, g);
@@ -356,6 +441,16 @@ int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* 
   int rc = gc_geom(g, d);
   if (rc) return rc;
   char* base = (char*)workspace;
+  if (sf_eligible(d)) {
+    const int splits = sf_splits(g);
+    float* part = reinterpret_cast<float*>(base);
+    sf_wgrad_kernel<<<dim3(splits, g.cin), 256, 0, st>>>(dy, part, g, splits);
+    HV_LAUNCH_CHECK();
+    sf_wgrad_reduce_kernel<<<gc_blocks((long long)g.cin * g.kk), 256, 0, st>>>(part, dw, splits, g.cin * g.kk);
+    HV_LAUNCH_CHECK();
+    if (db) return channel_sum(dy, db, g.n, g.cout, g.P, st);
+    return HV_OK;
+  }
   if (gp_eligible(d)) {
     GpGeom q;
     gp_geom(q, g);
@@ -408,6 +503,11 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
   int rc = gc_geom(g, d);
   if (rc) return rc;
   char* base = (char*)workspace;
+  if (sf_eligible(d)) {
+    sf_dgrad_kernel<<<gc_blocks((long long)g.n * g.cin * g.hin * g.win), 256, 0, st>>>(w, dy, dx, g);
+    HV_LAUNCH_CHECK();
+    return HV_OK;
+  }
   if (g_backward_paths < 0) g_backward_paths = (getenv("HV_DGRAD_GEMM") ? 1 : 0) | (getenv("HV_WGRAD_IM2COL") ? 2 : 0);
   const bool gemm_dgrad = (g_backward_paths & 1) != 0;   // A/B switch: the GEMM + col2im path for every layer
   if (!gemm_dgrad && d->stride == 1 && (d->k == 3 || d->k == 5) && d->pad == (d->k - 1) / 2 * d->dil && d->cin <= 64) {
