@@ -196,12 +196,11 @@ __global__ void __launch_bounds__(256) gc_flip_w_kernel(const float* __restrict_
 // not GEMMs - through the GEMM path the data gradient alone builds an [8192 rows x 1024 pixels] operand per image for 0.2 GFLOP of work.
 // dx[n][ci][y][x] = sum over the taps whose output pixel exists of w[ci][ky][kx] * dy[n][oy][ox]; one thread = one input element
 __global__ void __launch_bounds__(256) sf_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, float* __restrict__ dx, GcGeom g) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)g.n * g.cin * g.hin * g.win) return;
-  const int x = (int)(i % g.win), y = (int)((i / g.win) % g.hin);
-  const long long bc = i / ((long long)g.win * g.hin);
-  const int ci = (int)(bc % g.cin), b = (int)(bc / g.cin);
-  const float* wp = w + (size_t)ci * g.kk;
+  // grid (pixel blocks, cin, n): 32-bit index arithmetic only
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, ci = blockIdx.y, b = blockIdx.z;
+  if (i >= g.hin * g.win) return;
+  const int y = i / g.win, x = i - y * g.win;
+  const float* wp = w + ci * g.kk;
   const float* dyp = dy + (size_t)b * g.P;
   float acc = 0.f;
   for (int ky = 0; ky < g.k; ++ky) {
@@ -209,38 +208,41 @@ __global__ void __launch_bounds__(256) sf_dgrad_kernel(const float* __restrict__
     if (ty < 0 || (g.stride == 2 && (ty & 1))) continue;
     const int oy = g.stride == 2 ? ty >> 1 : ty;
     if (oy >= g.hout) continue;
+    const float* row = dyp + oy * g.wout;
     for (int kx = 0; kx < g.k; ++kx) {
       const int tx = x + g.pad - kx * g.dil;
       if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
       const int ox = g.stride == 2 ? tx >> 1 : tx;
-      if (ox < g.wout) acc = fmaf(__ldg(wp + ky * g.k + kx), __ldg(dyp + (size_t)oy * g.wout + ox), acc);
+      if (ox < g.wout) acc = fmaf(__ldg(wp + ky * g.k + kx), __ldg(row + ox), acc);
     }
   }
-  dx[i] = acc;
+  dx[((size_t)b * g.cin + ci) * g.hin * g.win + i] = acc;
 }
 
 // part[split][ci][tap] = sum over the split's share of the (image, output pixel) pairs of dy * x(tap); grid (splits, cin); the taps of a
-// thread live in registers (k <= 5), block sums through shared memory; a second kernel adds the splits in a fixed order
+// thread live in registers (k <= 5), block sums through shared memory; a second kernel adds the splits in a fixed order.  A split is a
+// run of whole images plus a pixel range, walked with 32-bit arithmetic.
 __global__ void __launch_bounds__(256) sf_wgrad_kernel(const float* __restrict__ dy, float* __restrict__ part, GcGeom g, int splits) {
   __shared__ float red[8][25];
   const int ci = blockIdx.y, split = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long total = (long long)g.n * g.P, per = (total + splits - 1) / splits;
-  const long long lo = (long long)split * per, hi = min(total, lo + per);
+  const int total = g.n * g.P, per = (total + splits - 1) / splits;
+  const int lo = split * per, hi = min(total, lo + per);
   float acc[25];
 #pragma unroll
   for (int t = 0; t < 25; ++t) acc[t] = 0.f;
-  for (long long e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-    const int b = (int)(e / g.P), p = (int)(e - (long long)b * g.P);
+  for (int e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+    const int b = e / g.P, p = e - b * g.P;
     const int oy = p / g.wout, ox = p - oy * g.wout;
     const float gval = __ldg(dy + e);
     const GcSrc src = gc_resolve(g, b, ci);
+    const int y0 = oy * g.stride - g.pad, x0 = ox * g.stride - g.pad;
 #pragma unroll
     for (int ky = 0; ky < 5; ++ky) {
       if (ky >= g.k) break;
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
         if (kx >= g.k) break;
-        acc[ky * 5 + kx] = fmaf(gval, gc_fetch(g, src, oy * g.stride + ky * g.dil - g.pad, ox * g.stride + kx * g.dil - g.pad), acc[ky * 5 + kx]);
+        acc[ky * 5 + kx] = fmaf(gval, gc_fetch(g, src, y0 + ky * g.dil, x0 + kx * g.dil), acc[ky * 5 + kx]);
       }
     }
   }
@@ -268,7 +270,9 @@ __global__ void __launch_bounds__(256) sf_wgrad_reduce_kernel(const float* __res
   dw[i] = v;
 }
 
-static bool sf_eligible(const hv_conv_desc* d) { return d->cout == 1 && d->cin >= 64 && d->k <= 5; }
+static bool sf_eligible(const hv_conv_desc* d) {
+  return d->cout == 1 && d->cin >= 64 && d->k <= 5 && d->n <= 65535 && (long long)d->n * d->hin * d->win < (1ll << 30);
+}
 static int sf_splits(const GcGeom& g) {
   int s = (592 + g.cin - 1) / g.cin;
   const long long total = (long long)g.n * g.P;
@@ -504,7 +508,7 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
   if (rc) return rc;
   char* base = (char*)workspace;
   if (sf_eligible(d)) {
-    sf_dgrad_kernel<<<gc_blocks((long long)g.n * g.cin * g.hin * g.win), 256, 0, st>>>(w, dy, dx, g);
+    sf_dgrad_kernel<<<dim3(gc_blocks((long long)g.hin * g.win), g.cin, g.n), 256, 0, st>>>(w, dy, dx, g);
     HV_LAUNCH_CHECK();
     return HV_OK;
   }
