@@ -195,25 +195,33 @@ __global__ void __launch_bounds__(256) gc_flip_w_kernel(const float* __restrict_
 // ---- single-filter layers over many input channels (the PatchGAN logit conv 512 -> 1, networks.py:598): their gradients are reductions,
 // not GEMMs - through the GEMM path the data gradient alone builds an [8192 rows x 1024 pixels] operand per image for 0.2 GFLOP of work.
 // dx[n][ci][y][x] = sum over the taps whose output pixel exists of w[ci][ky][kx] * dy[n][oy][ox]; one thread = one input element
+// K / S = 0: run-time kernel size / stride (the generic instance).  The kernels are instruction-bound (16 taps x address arithmetic per
+// element), so the PatchGAN shape (4 x 4, stride 1) gets compile-time loops: 157 us -> measured below in profiles/.
+template <int KT, int ST>
 __global__ void __launch_bounds__(256) sf_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ dy, float* __restrict__ dx, GcGeom g) {
   // grid (pixel blocks, cin, n): 32-bit index arithmetic only
   const int i = blockIdx.x * blockDim.x + threadIdx.x, ci = blockIdx.y, b = blockIdx.z;
   if (i >= g.hin * g.win) return;
+  const int k = KT ? KT : g.k, stride = ST ? ST : g.stride;
   const int y = i / g.win, x = i - y * g.win;
   const float* wp = w + ci * g.kk;
   const float* dyp = dy + (size_t)b * g.P;
   float acc = 0.f;
-  for (int ky = 0; ky < g.k; ++ky) {
+#pragma unroll
+  for (int ky = 0; ky < (KT ? KT : 5); ++ky) {
+    if (ky >= k) break;
     const int ty = y + g.pad - ky * g.dil;
-    if (ty < 0 || (g.stride == 2 && (ty & 1))) continue;
-    const int oy = g.stride == 2 ? ty >> 1 : ty;
+    if (ty < 0 || (stride == 2 && (ty & 1))) continue;
+    const int oy = stride == 2 ? ty >> 1 : ty;
     if (oy >= g.hout) continue;
     const float* row = dyp + oy * g.wout;
-    for (int kx = 0; kx < g.k; ++kx) {
+#pragma unroll
+    for (int kx = 0; kx < (KT ? KT : 5); ++kx) {
+      if (kx >= k) break;
       const int tx = x + g.pad - kx * g.dil;
-      if (tx < 0 || (g.stride == 2 && (tx & 1))) continue;
-      const int ox = g.stride == 2 ? tx >> 1 : tx;
-      if (ox < g.wout) acc = fmaf(__ldg(wp + ky * g.k + kx), __ldg(row + ox), acc);
+      if (tx < 0 || (stride == 2 && (tx & 1))) continue;
+      const int ox = stride == 2 ? tx >> 1 : tx;
+      if (ox < g.wout) acc = fmaf(__ldg(wp + ky * k + kx), __ldg(row + ox), acc);
     }
   }
   dx[((size_t)b * g.cin + ci) * g.hin * g.win + i] = acc;
@@ -221,10 +229,12 @@ __global__ void __launch_bounds__(256) sf_dgrad_kernel(const float* __restrict__
 
 // part[split][ci][tap] = sum over the split's share of the (image, output pixel) pairs of dy * x(tap); grid (splits, cin); the taps of a
 // thread live in registers (k <= 5), block sums through shared memory; a second kernel adds the splits in a fixed order.  A split is a
-// run of whole images plus a pixel range, walked with 32-bit arithmetic.
+// run of whole images plus a pixel range, walked with 32-bit arithmetic.  PLAIN: one directly stored source, stride 1 (no gather logic).
+template <int KT, bool PLAIN>
 __global__ void __launch_bounds__(256) sf_wgrad_kernel(const float* __restrict__ dy, float* __restrict__ part, GcGeom g, int splits) {
   __shared__ float red[8][25];
   const int ci = blockIdx.y, split = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = KT ? KT : g.k;
   const int total = g.n * g.P, per = (total + splits - 1) / splits;
   const int lo = split * per, hi = min(total, lo + per);
   float acc[25];
@@ -234,15 +244,33 @@ __global__ void __launch_bounds__(256) sf_wgrad_kernel(const float* __restrict__
     const int b = e / g.P, p = e - b * g.P;
     const int oy = p / g.wout, ox = p - oy * g.wout;
     const float gval = __ldg(dy + e);
-    const GcSrc src = gc_resolve(g, b, ci);
     const int y0 = oy * g.stride - g.pad, x0 = ox * g.stride - g.pad;
+    if (PLAIN) {
+      const float* plane = g.src[0].ptr + ((size_t)b * g.cin + ci) * g.hin * g.win;
 #pragma unroll
-    for (int ky = 0; ky < 5; ++ky) {
-      if (ky >= g.k) break;
+      for (int ky = 0; ky < (KT ? KT : 5); ++ky) {
+        if (ky >= k) break;
+        const int gy = y0 + ky * g.dil;
+        const bool row_ok = gy >= 0 && gy < g.hin;
+        const float* row = plane + gy * g.win;
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        if (kx >= g.k) break;
-        acc[ky * 5 + kx] = fmaf(gval, gc_fetch(g, src, y0 + ky * g.dil, x0 + kx * g.dil), acc[ky * 5 + kx]);
+        for (int kx = 0; kx < (KT ? KT : 5); ++kx) {
+          if (kx >= k) break;
+          const int gx = x0 + kx * g.dil;
+          const float v = (row_ok && gx >= 0 && gx < g.win) ? __ldg(row + gx) : 0.f;
+          acc[ky * 5 + kx] = fmaf(gval, v, acc[ky * 5 + kx]);
+        }
+      }
+    } else {
+      const GcSrc src = gc_resolve(g, b, ci);
+#pragma unroll
+      for (int ky = 0; ky < 5; ++ky) {
+        if (ky >= k) break;
+#pragma unroll
+        for (int kx = 0; kx < 5; ++kx) {
+          if (kx >= k) break;
+          acc[ky * 5 + kx] = fmaf(gval, gc_fetch(g, src, y0 + ky * g.dil, x0 + kx * g.dil), acc[ky * 5 + kx]);
+        }
       }
     }
   }
@@ -255,7 +283,7 @@ __global__ void __launch_bounds__(256) sf_wgrad_kernel(const float* __restrict__
   }
   __syncthreads();
   if (threadIdx.x < g.kk) {
-    const int ky = threadIdx.x / g.k, kx = threadIdx.x - ky * g.k;
+    const int ky = threadIdx.x / k, kx = threadIdx.x - ky * k;
     float v = 0.f;
 #pragma unroll
     for (int wq = 0; wq < 8; ++wq) v += red[wq][ky * 5 + kx];
@@ -448,7 +476,10 @@ int conv2d_wgrad_bf16(const hv_conv_desc* d, const float* dy, float* dw, float* 
   if (sf_eligible(d)) {
     const int splits = sf_splits(g);
     float* part = reinterpret_cast<float*>(base);
-    sf_wgrad_kernel<<<dim3(splits, g.cin), 256, 0, st>>>(dy, part, g, splits);
+    const bool plain = g.nsrc == 1 && g.src[0].mode == HV_SRC_DIRECT;
+    if (plain && g.k == 4) sf_wgrad_kernel<4, true><<<dim3(splits, g.cin), 256, 0, st>>>(dy, part, g, splits);
+    else if (plain) sf_wgrad_kernel<0, true><<<dim3(splits, g.cin), 256, 0, st>>>(dy, part, g, splits);
+    else sf_wgrad_kernel<0, false><<<dim3(splits, g.cin), 256, 0, st>>>(dy, part, g, splits);
     HV_LAUNCH_CHECK();
     sf_wgrad_reduce_kernel<<<gc_blocks((long long)g.cin * g.kk), 256, 0, st>>>(part, dw, splits, g.cin * g.kk);
     HV_LAUNCH_CHECK();
@@ -508,7 +539,9 @@ int conv2d_dgrad_bf16(const hv_conv_desc* d, const float* w, const float* dy, fl
   if (rc) return rc;
   char* base = (char*)workspace;
   if (sf_eligible(d)) {
-    sf_dgrad_kernel<<<dim3(gc_blocks((long long)g.hin * g.win), g.cin, g.n), 256, 0, st>>>(w, dy, dx, g);
+    const dim3 grid(gc_blocks((long long)g.hin * g.win), g.cin, g.n);
+    if (g.k == 4 && g.stride == 1) sf_dgrad_kernel<4, 1><<<grid, 256, 0, st>>>(w, dy, dx, g);
+    else sf_dgrad_kernel<0, 0><<<grid, 256, 0, st>>>(w, dy, dx, g);
     HV_LAUNCH_CHECK();
     return HV_OK;
   }
